@@ -1,0 +1,204 @@
+/*
+ * tapenv.h -- C ABI of the B200-native TAP packing-environment step.
+ *
+ * Drop-in boundary for ONE hot path of Juzhan/TAP-Net: the per-decode-step
+ * environment transition that model.py's pointer-network decode loop performs
+ * (model.py:376-458, :499-515).  The reference has no FFI layer; its "operator
+ * API" is a set of plain Python callables and one class.  Every entry point below
+ * cites the reference interface it replaces (file:line into the reference tree).
+ * The Python binding a maintainer adds is a ctypes stub -- see INTEGRATION.md and
+ * tap-net_b200/tapenv/_capi.py.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.  All data pointers are
+ *    DEVICE pointers (sm_100a, HBM) unless the name ends in _host.
+ *  - the caller owns every buffer (torch allocates them); the library never
+ *    allocates, frees or retains memory, has no global state, and is re-entrant.
+ *  - every function is stream-ordered on `stream` (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream) and never synchronises.
+ *  - outputs never alias inputs (the reference clones: pack.py:318,323,370).
+ *  - return value: TAPENV_OK (0) or a negative TAPENV_E* code; nothing is
+ *    launched when an error is returned.
+ *  - tensors are dense row-major with the reference's layouts:
+ *      static   f32 [B, static_rows, S]   row 0 = block id, rows 1..dim = edge lengths   (pack.py:144-147,186)
+ *      dynamic  f32 [B, dyn_rows, S]      3 bands of n rows: move | rot-small | rot-large (pack.py:195)
+ *      mask     f32 [B, S]                0/1                                               (model.py:297)
+ *      ptr      i64 [B]                   chosen candidate column                           (model.py:365-371)
+ *    S = n * rotate_types candidates, rotation-major (column j = r*n + i).
+ *  - `dynamic` entries must be non-negative (the dataset writes 0/1, pack.py:101-223):
+ *    the accessibility test `move_sum + small_sum*large_sum != 0` (pack.py:324-329) is
+ *    evaluated as `any(move) | (any(small) & any(large))`.
+ */
+#ifndef TAPENV_H_
+#define TAPENV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAPENV_VERSION 100
+
+/* error codes */
+#define TAPENV_OK 0
+#define TAPENV_EINVAL (-1)    /* NULL pointer / bad size */
+#define TAPENV_EENUM (-2)     /* unknown reward_type / packing_strategy / heightmap_type / input_type */
+#define TAPENV_ELIMIT (-3)    /* shape outside the compiled limits (see tapenv_limits) */
+#define TAPENV_ESHAPE (-4)    /* S != n*R, dyn_rows too small, ... */
+#define TAPENV_ECUDA (-5)     /* the launch itself failed (cudaGetLastError) */
+#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not built (e.g. MACS 3D) */
+
+/* packing_strategy (tools.py:3607, :3679-3701) */
+#define TAPENV_LB_GREEDY 0
+#define TAPENV_MACS 1
+/* heightmap_type (tools.py:3716-3743) */
+#define TAPENV_HM_FULL 0
+#define TAPENV_HM_ZERO 1
+#define TAPENV_HM_DIFF 2
+/* reward_flags: the substring tests the reference performs on reward_type */
+#define TAPENV_RF_HARD 1      /* reward_type.endswith('hard')   tools.py:2113 */
+#define TAPENV_RF_P 2         /* 'P' in reward_type             tools.py:2135 */
+#define TAPENV_RF_S 4         /* 'S' in reward_type             tools.py:2138 */
+#define TAPENV_RF_MCS_IN 8    /* 'mcs' in reward_type           tools.py:2718 */
+#define TAPENV_RF_MCS_START 16/* reward_type.startswith('mcs')  tools.py:2709 */
+/* ratio_mode: which branch of Container.calc_ratio applies (tools.py:3908-3966) */
+#define TAPENV_RATIO_C 0            /* 'comp'                      -> C/3            */
+#define TAPENV_RATIO_CS 1           /* 'soft','hard'               -> C*S/3          */
+#define TAPENV_RATIO_C_P 2          /* 'pyrm'                      -> (C+P)/3        */
+#define TAPENV_RATIO_CP_S 3         /* 'pyrm-soft','mcs-hard',...  -> (C+P)*S/3      */
+#define TAPENV_RATIO_SUM 4          /* every 'C+P*-*' type, '*-sum'-> (C+P+S)/3      */
+#define TAPENV_RATIO_2C_SUM 5       /* '*-SUM'                     -> (2C+P+S)/3     */
+#define TAPENV_RATIO_CPS 6          /* 'CPS'                       -> C*P*S/3        */
+#define TAPENV_RATIO_CP_HALF 7      /* 'C+P-lb-soft'               -> (C+P)/2  (:3961) */
+
+typedef struct tapenv_config {
+    int32_t batch;          /* B: environments in this call                                      */
+    int32_t blocks_num;     /* n: blocks per episode            (Container blocks_num, tools.py:3611) */
+    int32_t dim;            /* 2 or 3                           (len(container_size))              */
+    int32_t rotate_types;   /* R: dim! when allow_rot else 1    (pack.py:306-309)                  */
+    int32_t width;          /* container_size[0]                                                   */
+    int32_t length;         /* container_size[1] in 3D, 1 in 2D                                    */
+    int32_t height;         /* container_size[-1]                                                  */
+    int32_t strategy;       /* TAPENV_LB_GREEDY | TAPENV_MACS (after the reward-type override, tools.py:3617-3620) */
+    int32_t heightmap_type; /* TAPENV_HM_*                                                         */
+    int32_t reward_flags;   /* TAPENV_RF_* bits                                                    */
+    int32_t ratio_mode;     /* TAPENV_RATIO_*                                                      */
+    int32_t static_rows;    /* rows of `static`: 1+dim ('mul-with': 2+dim)                         */
+    int32_t dyn_rows;       /* rows of `dynamic`: 3n for 'bot'-like inputs, n for 'simple'/'rot'   */
+    int32_t update_time;    /* bands zeroed by update_dynamic: 3 or 1 (pack.py:349)                */
+} tapenv_config;
+
+/* Byte offsets of the arrays inside the opaque per-batch state buffer. */
+typedef struct tapenv_state_layout {
+    size_t scalars;    /* i32 [B,4]  valid_size, empty_size, stable count, current_blocks_num (tools.py:3635-3653) */
+    size_t heightmap;  /* i32 [B,W] or [B,W,L]                                        (tools.py:3630) */
+    size_t positions;  /* i32 [B,n,dim]                                               (tools.py:3628) */
+    size_t blocks;     /* i32 [B,n,dim]  blocks in arrival order                      (tools.py:3631,3674) */
+    size_t stable;     /* u8  [B,n]                                                   (tools.py:3633) */
+    size_t flags;      /* i32 [B] sticky anomaly bits: 1 = a stack reached container height (NumPy would raise IndexError) */
+    size_t total;      /* == tapenv_state_bytes() */
+} tapenv_state_layout;
+
+/* compiled limits */
+typedef struct tapenv_limits {
+    int32_t max_width_2d;      /* W  <= this for dim 2 */
+    int32_t max_cells_3d;      /* W*L <= this for dim 3 */
+    int32_t max_candidates;    /* S  <= this */
+    int32_t max_blocks;        /* n  <= this */
+} tapenv_limits;
+
+int tapenv_version(void);
+const char *tapenv_strerror(int code);
+void tapenv_get_limits(tapenv_limits *out);
+
+/*
+ * Fill `cfg` from the reference's own (string-typed) options.  Replaces the
+ * option handling spread over tools.Container.__init__ (tools.py:3611-3661),
+ * pack.update_mask / update_dynamic (pack.py:285-309, :338-365) and
+ * Container.calc_ratio (tools.py:3908-3966).  Unknown strings -> TAPENV_EENUM
+ * (the reference prints "... OHHH" and then fails with NameError).
+ *   container_size: int[dim];  allow_rot: 0/1
+ */
+int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, int32_t dim,
+                       int32_t allow_rot, const int32_t *container_size,
+                       const char *reward_type, const char *packing_strategy,
+                       const char *heightmap_type, const char *input_type);
+
+/* Validate a config against shapes and compiled limits. */
+int tapenv_config_check(const tapenv_config *cfg);
+
+/* Size / layout of the state buffer for cfg->batch environments. */
+size_t tapenv_state_bytes(const tapenv_config *cfg);
+int tapenv_state_get_layout(const tapenv_config *cfg, tapenv_state_layout *out);
+
+/* Elements per environment of the encoded heightmap that add_new_block returns
+ * (tools.py:3716-3743): 2D full/zero W, 2D diff W-1, 3D full/zero W*L, 3D diff 2*W*L. */
+int32_t tapenv_encoded_heightmap_len(const tapenv_config *cfg);
+
+/*
+ * K0 reset.  Replaces `[tools.Container(...) for _ in range(batch_size)]`
+ * (model.py:294 -> tools.py:3611-3661; also clear_container :3858-3885) and the
+ * initial accessibility mask (model.py:297-307).
+ *   dynamic may be NULL (state reset only); then the mask outputs are ignored.
+ *   cur_mask_out f32 [B,S] : current_mask at t=0 ; mask_out f32 [B,S] : ones.
+ */
+int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic,
+                 float *cur_mask_out, float *mask_out, void *stream);
+
+/* pack.update_dynamic(dynamic, static, chosen_idx, input_type, allow_rot) (pack.py:333-376).
+ * Out-of-place; block id is read from static[:,0,ptr] (pack.py:347). */
+int tapenv_update_dynamic(const tapenv_config *cfg, const float *dynamic, const float *static_,
+                          const int64_t *ptr, float *dynamic_out, void *stream);
+
+/* pack.update_mask(mask, dynamic, static, chosen_idx, input_type, allow_rot) (pack.py:276-331).
+ * `dynamic` is the ALREADY UPDATED tensor; block id is ptr mod n (pack.py:314-316).
+ * Returns (new_mask, chosen_mask) = (new_mask_out, chosen_mask_out). */
+int tapenv_update_mask(const tapenv_config *cfg, const float *mask, const float *dynamic,
+                       const int64_t *ptr, float *new_mask_out, float *chosen_mask_out, void *stream);
+
+/* Batched tools.Container.add_new_block(block, is_rotate) (tools.py:3663-3744) for all B
+ * environments: placement scan (tools.py:2027-2351 / :2456-2749), stability test
+ * (tools.py:710-765, :839-868), state commit, heightmap encoding.
+ *   blocks f32 [B,dim] -- the rows model.py:412 hands to the Python loop at :452-453
+ *   dec_dynamic_out f32 [B, tapenv_encoded_heightmap_len()] -- what model.py:456-463 builds */
+int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks,
+                      float *dec_dynamic_out, void *stream);
+
+/* The fused hot path: update_dynamic + update_mask + gather of the chosen block
+ * (model.py:404-406) + add_new_block, ONE launch per decode step.
+ *   dec_static_out f32 [B, static_rows-1] = static[:,1:,ptr]  (may be NULL)
+ *   all other arguments as above. */
+int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
+                const float *dynamic_in, const float *mask_in,
+                float *dynamic_out, float *cur_mask_out, float *mask_out,
+                float *dec_static_out, float *dec_dynamic_out, void *stream);
+
+/* Container.calc_ratio() for every environment (tools.py:3887-3966; consumed at
+ * model.py:499-515): reward_out f32 [B] = (float) ratio (fp64 -> fp32, NOT negated).
+ * partial_sums_out (may be NULL) f64 [3] = (sum r, sum r^2, B) reduced in a fixed
+ * order -- the per-rank operand of the end-of-episode all-reduce (trainer.py:216-225). */
+int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out,
+                  double *partial_sums_out, void *stream);
+
+/* Whole-episode entry (tools.calc_positions_lb_greedy tools.py:2393-2449,
+ * calc_positions_mcs :3213-3315, pack.reward pack.py:378-473): run `steps` decode steps
+ * for a known pointer sequence in ONE launch, without materialising the
+ * intermediate dynamic tensors.
+ *   ptr_seq i64 [steps,B].  Resets the state first.  Outputs (each may be NULL):
+ *   reward_out f32 [B] (calc_ratio), cur_mask_out/mask_out f32 [B,S] after the last
+ *   step, dec_dynamic_out f32 [B,enc] last encoded heightmap. */
+int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, const float *dynamic,
+                   const int64_t *ptr_seq, int32_t steps, float *reward_out,
+                   float *cur_mask_out, float *mask_out, float *dec_dynamic_out, void *stream);
+
+/* Launch-shape tuning knob (does not exist in the reference; never changes results):
+ * environments (= warps) per CTA, one of 1, 2, 4, 8; 0 restores the automatic choice
+ * (one CTA per environment). */
+void tapenv_set_envs_per_cta(int envs_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAPENV_H_ */
