@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the TAP packing-environment step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One bench "step" = ONE EPISODE of the hot path over one batch: K0 reset + n fused decode-step launches
+(update_dynamic + update_mask + add_new_block for all B environments) + K6 reward.  It advances B*n
+env-steps; reset and reward are inside the timed region but are not counted as env-steps
+(SURVEY.md section 8d).  The pointer for every decode step is a recorded random-valid policy
+(ptr ~ multinomial(current_mask), fixed seed) replayed from memory.
+
+Prints ONE JSON line (rank 0).  Keys: see the contract in DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tap-net_b200"))
+
+METRIC = "env-steps/sec 2D LB_GREEDY 10-block W=5 at 1/2/4/8 B200 vs CPU ref"
+UNIT = "env-steps/s"
+
+WORKLOADS = {
+    # name: (fixture, container_size, reward_type, heightmap_type, packing_strategy, default batch, description)
+    "c2": ("rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 4096,
+           "2D RAND nodes=10 width=5 LB_GREEDY C+P+S-lb-soft batch=4096 (BASELINE configs[1])"),
+    "c3": ("rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 4096,
+           "3D RAND nodes=10 width=5 LB_GREEDY C+P+S-lb-soft batch=4096 (BASELINE configs[2])"),
+    "c4": ("ppsg2d_n20.npz", [7, 50], "C+P+S-mcs-hard", "diff", "MACS", 1024,
+           "2D PPSG nodes=20 width=7 MACS C+P+S-mcs-hard batch=8192/8 per GPU (BASELINE configs[3])"),
+}
+
+
+def algorithmic_bytes_per_env_step(n, R, dim, W, L, macs):
+    """minimum HBM traffic of one env-step under the reference's tensor contract."""
+    S = n * R
+    cells = W if dim == 2 else W * L
+    dec_dyn = (W - 1) if dim == 2 else 2 * W * L
+    hist = (16 * n + 16) if macs else 0
+    return (2 * (3 * n * S * 4) + 3 * (S * 4) + 8 + 4 * (1 + dim) + 2 * 4 * cells + 2 * 16 + hist + 4 * dec_dyn + 4 * dim)
+
+
+def load_workload(name, batch, rank):
+    from tests.golden_io import load_inputs
+    fixture, size, rt, hm, strat, default_b, desc = WORKLOADS[name]
+    B = batch or default_b
+    static, dynamic = load_inputs(fixture)
+    pool = static.shape[0]
+    idx = (np.arange(B) + rank * 977) % pool         # tile the pool; ranks start at different offsets
+    return np.ascontiguousarray(static[idx]), np.ascontiguousarray(dynamic[idx]), size, rt, hm, strat, B, desc, pool
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md: sample DURING the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.02):
+        threading.Thread.__init__(self, daemon=True)
+        self.period = period
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.sm_max = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if self.ok and self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the Python reference cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------
+def cpu_episode_rate(static, dynamic, ptr_seq, size, rt, hm, strat, threads, min_seconds, max_reps=10000):
+    """Times oracle.episode_batch (update_dynamic + update_mask + add_new_block per env-step, calc_ratio per
+    episode -- model.py:376-453,:509-510 restated in C) over the whole batch, repeated for >= min_seconds."""
+    from oracle import oracle
+    oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        o = oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+        assert o["status"] == 0
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds or reps >= max_reps:
+            break
+    steps = reps * static.shape[0] * ptr_seq.shape[0]
+    return steps / el, el, reps
+
+
+def host_policy(static, dynamic, size, seed):
+    """Recorded random-valid policy for the CPU arm (checker-side code: uses the oracle's mask functions)."""
+    from tests.rollout import random_valid_ptrs
+    return random_valid_ptrs(static, dynamic, size, seed=seed)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    static, dynamic, size, rt, hm, strat, B, desc, pool = load_workload(args.workload, args.batch, 0)
+    threads = os.cpu_count() or 1
+    ptr_seq = host_policy(static, dynamic, size, seed=1234)
+    n = ptr_seq.shape[0]
+    from oracle import oracle
+    for _ in range(max(args.warmup, 1)):
+        oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+    el = time.perf_counter() - t0
+    value = args.steps * B * n / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 state + f64 score", "data": "synthetic",
+        "config": {"workload": desc, "batch": B, "blocks": n, "env_steps_per_step": B * n,
+                   "inputs": "reference RAND/PPSG generator fixtures (tests/golden), pool of %d tiled" % pool},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d episodes x %d envs x %d steps, oracle/tap_oracle.c on %d pthreads" % (args.steps, B, n, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is pure Python/NumPy and /root/reference is not on the GPU box: this arm times the C "
+                "restatement (oracle/) of the same per-step path on all host threads; the Python reference itself "
+                "measured 4.9e3 env-steps/s on one core (BASELINE.md section 2)",
+        "reward_mean": float(o["reward"].mean()),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tapenv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the tapenv path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    static_h, dynamic_h, size, rt, hm, strat, B, desc, pool = load_workload(args.workload, args.batch, rank)
+    dim = len(size)
+    R = 2 if dim == 2 else 6
+    S = static_h.shape[2]
+    n = S // R
+    macs = strat == "MACS" or "mcs" in rt
+    bytes_step = algorithmic_bytes_per_env_step(n, R, dim, size[0], size[1] if dim == 3 else 1, macs)
+
+    # ring of RING distinct input sets (same instances, rotated) so every episode reads its inputs from HBM,
+    # not from a warm L2: RING * (inputs + ping-pong outputs) >> 126 MB
+    per_set = static_h.nbytes + dynamic_h.nbytes
+    RING = max(2, int(np.ceil(400e6 / (3 * per_set))))
+    env = tapenv.BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=B, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    # record the policy once (untimed): ptr ~ multinomial(current_mask)
+    st0 = torch.from_numpy(static_h).to(dev)
+    dyn0 = torch.from_numpy(dynamic_h).to(dev)
+    cur, mask = env.reset(dyn0)
+    dyn = dyn0
+    ptrs = []
+    for t in range(n):
+        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+        dyn, cur, mask, _, _ = env.step(ptr, st0, dyn, mask)
+        ptrs.append(ptr)
+    ptr_seq0 = torch.stack(ptrs)
+    reward_ref = env.calc_ratio().clone()
+    env.check_flags()
+
+    runners = []
+    for i in range(RING):
+        roll = (i * 131) % B
+        st = torch.roll(st0, roll, 0).contiguous()
+        dy = torch.roll(dyn0, roll, 0).contiguous()
+        pq = torch.roll(ptr_seq0, roll, 1).contiguous()
+        runners.append(tapenv.EpisodeRunner(env, st, dy, pq, use_graph=not args.no_graph, partial_sums=True))
+    sums_total = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def episode(i):
+        r = runners[i % RING]
+        r.run()
+        if world > 1:
+            # end-of-episode reward all-reduce feeding the critic baseline statistics (trainer.py:216-225)
+            dist.all_reduce(r.sums)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        episode(i)
+    barrier()
+    # parity spot check of the replay against the recorded pass (same kernels; the oracle check lives in tests/ and smoke())
+    assert torch.equal(runners[0].run(), reward_ref)
+
+    # ---- timed region 1: `value` -- K episodes, inputs resident in HBM --------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record()
+        episode(k)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # K episodes back to back on one stream: device time from first start to last end
+    span_ms = ev[0][0].elapsed_time(ev[-1][1])
+    tt = torch.tensor([span_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    span_ms_max = float(tt.item())
+    value = world * B * n * args.steps / (span_ms_max * 1e-3)
+    launches = args.steps * runners[0].launches_per_episode
+
+    # ---- timed region 2: roofline of the dominant kernel (the fused step), cold inputs ---------------
+    # M launches back to back, each on a different ring slot (21 MB per launch at c2), events on the launching stream
+    out_bufs = [(torch.empty_like(dyn0), torch.empty(B, S, device=dev), torch.empty(B, S, device=dev),
+                 torch.empty(B, dim, device=dev), torch.empty(B, env.enc_len, device=dev)) for _ in range(RING)]
+    mask1 = torch.ones(B, S, device=dev)
+    M = max(RING * 4, 32)
+    env.reset(dyn0)
+    for i in range(RING):                                  # warm-up (k stays < n: reset in between)
+        env.step(runners[i].ptr_seq[0], runners[i].static, runners[i].dynamic, mask1, out=out_bufs[i])
+    torch.cuda.synchronize(dev)
+    tot_ms, cnt = 0.0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(M // RING):
+        env.clear_container()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for i in range(min(RING, n)):
+            env.step(runners[i].ptr_seq[0], runners[i].static, runners[i].dynamic, mask1, out=out_bufs[i])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tot_ms += e0.elapsed_time(e1)
+        cnt += min(RING, n)
+    step_us = 1e3 * tot_ms / cnt
+    achieved = B * bytes_step / (step_us * 1e-6) / 1e9
+    clocks = sampler.result()
+
+    # ---- timed region 3: e2e -- host buffers in, host reward out, through the public Python API -------
+    st_pin = torch.from_numpy(static_h).pin_memory()
+    dy_pin = torch.from_numpy(dynamic_h).pin_memory()
+    pq_pin = ptr_seq0.cpu().pin_memory()
+    rw_pin = torch.empty(B, dtype=torch.float32).pin_memory()
+    st_d, dy_d, pq_d = torch.empty_like(st0), torch.empty_like(dyn0), torch.empty_like(ptr_seq0)
+    e2e_runner = tapenv.EpisodeRunner(env, st_d, dy_d, pq_d, use_graph=not args.no_graph, partial_sums=True)
+
+    def e2e_episode():
+        st_d.copy_(st_pin, non_blocking=True)
+        dy_d.copy_(dy_pin, non_blocking=True)
+        pq_d.copy_(pq_pin, non_blocking=True)
+        r = e2e_runner.run()
+        if world > 1:
+            dist.all_reduce(e2e_runner.sums)
+        rw_pin.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes the rewards on the host
+        return rw_pin
+
+    for _ in range(3):
+        e2e_episode()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_episode()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * n * args.steps / float(te.item())
+    assert np.array_equal(rw_pin.numpy(), reward_ref.cpu().numpy())
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        ptr_h = ptr_seq0.cpu().numpy()
+        rate, el, reps = cpu_episode_rate(static_h, dynamic_h, ptr_h, size, rt, hm, strat, threads, args.cpu_seconds)
+        from oracle import oracle
+        o = oracle.episode_batch(static_h, dynamic_h, ptr_h, size, rt, hm, strat, nthreads=threads, want=("reward",))
+        parity = bool(np.array_equal(o["reward"], reward_ref.cpu().numpy()))
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d episodes x %d envs x %d steps = %.1f s of oracle/tap_oracle.c on %d pthreads" % (reps, B, n, el, threads),
+               "reward_parity_vs_gpu": parity,
+               "python_reference_1core": "4.9e3 env-steps/s (unmodified tools.py path, build container, BASELINE.md section 2)"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 state + f64 score, f32 tensors", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "blocks": n, "env_steps_per_step": world * B * n,
+                       "step_definition": "one episode = reset + %d fused decode-step launches + reward over the batch" % n,
+                       "l2": "inputs rotate over a ring of %d distinct batches (%.0f MB incl. ping-pong outputs) > 126 MB L2" % (RING, RING * 3 * per_set / 1e6),
+                       "cuda_graph": not args.no_graph,
+                       "inputs": "reference RAND/PPSG generator fixtures (tests/golden), pool of %d tiled" % pool,
+                       "policy": "recorded ptr ~ multinomial(current_mask), seed 1234+rank"},
+            "gpu_launches": launches,
+            "device_ms_sum_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(static_h.nbytes + dynamic_h.nbytes + pq_pin.numel() * 8),
+                    "d2h_bytes_per_step": int(B * 4), "ms_per_step": 1e3 * float(te.item()) / args.steps,
+                    "api": "tapenv.EpisodeRunner.run (BatchedContainers.reset/step/calc_ratio), pinned host buffers"},
+            "roofline": {"bound": "hbm", "kernel": "step (fused update_dynamic+update_mask+add_new_block)",
+                         "achieved": achieved, "peak": peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_env_step": bytes_step, "bytes_per_launch": B * bytes_step,
+                         "launch_us": step_us, "launches_timed": cnt},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="environments per GPU (default: the workload's)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

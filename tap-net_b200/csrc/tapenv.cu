@@ -496,9 +496,9 @@ int tapenv_update_mask(const tapenv_config *cfg, const float *mask, const float 
 
 int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
-    if (!state || !blocks) return TAPENV_EINVAL;
     rc_ = check_strategy_built(cfg);
     if (rc_ != TAPENV_OK) return rc_;
+    if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
     add_blocks_lbg2d_kernel<<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
     return launch_status();
@@ -522,7 +522,7 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
 int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out, double *partial_sums_out, void *stream) {
     int rc_ = check_cfg(cfg);
     if (rc_ != TAPENV_OK) return rc_;
-    if (!state || !reward_out) return TAPENV_EINVAL;
+    if (cfg->batch > 0 && (!state || !reward_out)) return TAPENV_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const DevCfg d = devcfg_of(cfg);
     const StatePtrs st = stateptrs_of(cfg, const_cast<void *>(state));

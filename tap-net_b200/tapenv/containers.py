@@ -1,0 +1,333 @@
+"""Batched packing containers: the B200 replacement of `[tools.Container(...) for _ in range(B)]`
+(model.py:294) and of the per-environment Python loop at model.py:452-453 / :509-510.
+
+`BatchedContainers` owns one opaque HBM state buffer for B environments and drives the kernels through
+the C ABI (include/tapenv.h).  `Container` keeps the reference's per-environment class signature
+(tools.py:3607-3966) as a thin view of one row, so an UNMODIFIED model.py can be pointed at it.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .config import make_config
+from .ops import _dev, _p, _stream
+
+
+class BatchedContainers(object):
+    """B independent containers resident on one GPU.
+
+    Constructor arguments follow tools.Container (tools.py:3611) + batch_size/device.
+    `initial_container_size` / `max_height` are accepted and ignored exactly like the reference ignores
+    them for the strategies built here (they only feed the two-container drawing code)."""
+
+    def __init__(self, container_size, blocks_num, reward_type, heightmap_type="full", initial_container_size=None,
+                 max_height=None, packing_strategy="LB_GREEDY", batch_size=1, device=None, input_type="bot",
+                 allow_rot=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tapenv: a CUDA device is required (no CPU fallback exists)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.container_size = [int(v) for v in container_size]
+        self.block_dim = len(self.container_size)
+        self.blocks_num = int(blocks_num)
+        self.batch_size = int(batch_size)
+        self.reward_type = reward_type
+        self.heightmap_type = heightmap_type
+        self.cfg = make_config(batch_size, blocks_num, container_size, reward_type, heightmap_type, packing_strategy,
+                               input_type, allow_rot)
+        self.packing_strategy = "MACS" if self.cfg.strategy == _capi.MACS else packing_strategy
+        self.S = self.cfg.blocks_num * self.cfg.rotate_types
+        self.enc_len = int(_capi.lib.tapenv_encoded_heightmap_len(C.byref(self.cfg)))
+        lay = _capi.StateLayout()
+        _capi.check(_capi.lib.tapenv_state_get_layout(C.byref(self.cfg), C.byref(lay)), "layout")
+        self._layout = lay
+        self.state = torch.empty(max(int(lay.total), 1), dtype=torch.uint8, device=self.device)
+        self._version = 0
+        self.clear_container()
+
+    # ---- state views (no copies) -------------------------------------------------------
+    def _view(self, off, count, dtype, shape):
+        item = torch.empty((), dtype=dtype).element_size()
+        return self.state[off: off + count * item].view(dtype).view(shape)
+
+    @property
+    def _cells(self):
+        return self.container_size[0] if self.block_dim == 2 else self.container_size[0] * self.container_size[1]
+
+    @property
+    def heightmap(self):
+        """int32 [B,W] or [B,W,L] (tools.py:3630)."""
+        B = self.batch_size
+        shape = (B, self.container_size[0]) if self.block_dim == 2 else (B, self.container_size[0], self.container_size[1])
+        return self._view(self._layout.heightmap, B * self._cells, torch.int32, shape)
+
+    @property
+    def scalars(self):
+        """int32 [B,4]: valid_size, empty_size, number of stable blocks, current_blocks_num."""
+        return self._view(self._layout.scalars, self.batch_size * 4, torch.int32, (self.batch_size, 4))
+
+    @property
+    def valid_size(self):
+        return self.scalars[:, 0]
+
+    @property
+    def empty_size(self):
+        return self.scalars[:, 1]
+
+    @property
+    def current_blocks_num(self):
+        return self.scalars[:, 3]
+
+    @property
+    def positions(self):
+        B, n, d = self.batch_size, self.blocks_num, self.block_dim
+        return self._view(self._layout.positions, B * n * d, torch.int32, (B, n, d))
+
+    @property
+    def blocks(self):
+        B, n, d = self.batch_size, self.blocks_num, self.block_dim
+        return self._view(self._layout.blocks, B * n * d, torch.int32, (B, n, d))
+
+    @property
+    def stable(self):
+        B, n = self.batch_size, self.blocks_num
+        return self._view(self._layout.stable, B * n, torch.uint8, (B, n))
+
+    @property
+    def flags(self):
+        """int32 [B] sticky anomaly bits (1: a stack passed container height -- NumPy would have raised)."""
+        return self._view(self._layout.flags, self.batch_size, torch.int32, (self.batch_size,))
+
+    def _shape_enc(self, t):
+        if self.block_dim == 3:
+            W, L = self.container_size[0], self.container_size[1]
+            return t.view(self.batch_size, 2, W, L) if self.heightmap_type == "diff" else t.view(self.batch_size, W, L)
+        return t
+
+    # ---- operations --------------------------------------------------------------------
+    def clear_container(self):
+        """Container.clear_container for every environment (tools.py:3858-3885)."""
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reset(C.byref(self.cfg), _p(self.state), None, None, None, _stream()), "reset")
+
+    def reset(self, dynamic):
+        """clear + the initial accessibility masks of model.py:297-307 -> (current_mask, mask)."""
+        dynamic = _dev(dynamic, "dynamic", torch.float32)
+        B = self.batch_size
+        if tuple(dynamic.shape) != (B, self.cfg.dyn_rows, self.S):
+            raise _capi.TapEnvError(_capi.ESHAPE, "dynamic %s" % (tuple(dynamic.shape),))
+        cur = torch.empty(B, self.S, dtype=torch.float32, device=self.device)
+        mask = torch.empty_like(cur)
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reset(C.byref(self.cfg), _p(self.state), _p(dynamic), _p(cur), _p(mask),
+                                               _stream()), "reset")
+        return cur, mask
+
+    def add_new_blocks(self, blocks):
+        """Batched Container.add_new_block (tools.py:3663-3744): blocks f32 [B,dim] ->
+        encoded heightmaps f32 [B,enc] (2D) / [B,2,W,L] or [B,W,L] (3D), what model.py:456-463 builds."""
+        blocks = _dev(blocks, "blocks", torch.float32)
+        if tuple(blocks.shape) != (self.batch_size, self.block_dim):
+            raise _capi.TapEnvError(_capi.ESHAPE, "blocks %s" % (tuple(blocks.shape),))
+        out = torch.empty(self.batch_size, self.enc_len, dtype=torch.float32, device=self.device)
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_add_blocks(C.byref(self.cfg), _p(self.state), _p(blocks), _p(out), _stream()),
+                        "add_blocks")
+        return self._shape_enc(out)
+
+    def step(self, ptr, static, dynamic, mask, out=None):
+        """The fused decode-step transition (model.py:376-458 env part) in ONE launch:
+        returns (dynamic', current_mask, mask', decoder_static [B,dim], decoder_dynamic)."""
+        ptr = _dev(ptr, "ptr", torch.int64)
+        static = _dev(static, "static", torch.float32)
+        dynamic = _dev(dynamic, "dynamic", torch.float32)
+        mask = _dev(mask, "mask", torch.float32)
+        B, S = self.batch_size, self.S
+        if tuple(dynamic.shape) != (B, self.cfg.dyn_rows, S) or tuple(static.shape) != (B, self.cfg.static_rows, S) \
+                or tuple(mask.shape) != (B, S) or tuple(ptr.shape) != (B,):
+            raise _capi.TapEnvError(_capi.ESHAPE, "step tensors")
+        if out is None:
+            dyn_out = torch.empty_like(dynamic)
+            cur = torch.empty_like(mask)
+            mask_out = torch.empty_like(mask)
+            dec_static = torch.empty(B, self.cfg.static_rows - 1, dtype=torch.float32, device=self.device)
+            dec_dyn = torch.empty(B, self.enc_len, dtype=torch.float32, device=self.device)
+        else:
+            dyn_out, cur, mask_out, dec_static, dec_dyn = out
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_step(C.byref(self.cfg), _p(self.state), _p(ptr), _p(static), _p(dynamic),
+                                              _p(mask), _p(dyn_out), _p(cur), _p(mask_out), _p(dec_static), _p(dec_dyn),
+                                              _stream()), "step")
+        return dyn_out, cur, mask_out, dec_static, self._shape_enc(dec_dyn)
+
+    def calc_ratio(self, partial_sums=False):
+        """Container.calc_ratio for every environment -> f32 [B] (tools.py:3908-3966, model.py:509-510).
+        partial_sums=True also returns the f64 [3] (sum r, sum r^2, B) operand of the reward all-reduce."""
+        r = torch.empty(self.batch_size, dtype=torch.float32, device=self.device)
+        sums = torch.empty(3, dtype=torch.float64, device=self.device) if partial_sums else None
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reward(C.byref(self.cfg), _p(self.state), _p(r), _p(sums), _stream()), "reward")
+        return (r, sums) if partial_sums else r
+
+    def episode(self, static, dynamic, ptr_seq):
+        """Whole-episode entry: reset + len(ptr_seq) steps + calc_ratio in one launch.
+        ptr_seq int64 [steps,B].  Returns (reward f32 [B], current_mask, mask, decoder_dynamic)."""
+        static = _dev(static, "static", torch.float32)
+        dynamic = _dev(dynamic, "dynamic", torch.float32)
+        ptr_seq = _dev(ptr_seq, "ptr_seq", torch.int64)
+        B, S = self.batch_size, self.S
+        r = torch.empty(B, dtype=torch.float32, device=self.device)
+        cur = torch.empty(B, S, dtype=torch.float32, device=self.device)
+        mask = torch.empty_like(cur)
+        dec_dyn = torch.empty(B, self.enc_len, dtype=torch.float32, device=self.device)
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_episode(C.byref(self.cfg), _p(self.state), _p(static), _p(dynamic), _p(ptr_seq),
+                                                 int(ptr_seq.shape[0]), _p(r), _p(cur), _p(mask), _p(dec_dyn), _stream()),
+                        "episode")
+        return r, cur, mask, self._shape_enc(dec_dyn)
+
+    def check_flags(self):
+        """Raise IndexError if any environment overflowed its container (the reference's NumPy would)."""
+        bad = int((self.flags != 0).sum().item())
+        if bad:
+            raise IndexError("tapenv: %d environment(s) stacked beyond container height / block capacity" % bad)
+
+    # ---- per-environment views -----------------------------------------------------------
+    def __len__(self):
+        return self.batch_size
+
+    def __getitem__(self, b):
+        if not -self.batch_size <= b < self.batch_size:
+            raise IndexError(b)
+        return Container._view_of(self, b % self.batch_size)
+
+    def __iter__(self):
+        return (Container._view_of(self, b) for b in range(self.batch_size))
+
+
+class Container(object):
+    """tools.Container (tools.py:3607) signature.  Stand-alone it is a batch of one; inside a
+    BatchedContainers it is row `b` of the batch.
+
+    Drop-in trick for an unmodified model.py (model.py:452-453 calls add_new_block once per
+    environment with `blocks[b]`, a row VIEW of one [B,dim] ndarray): the call for row 0 launches the
+    step for the whole batch from `block.base`, copies the encoded heightmaps to the host once, and
+    every row call just returns its row."""
+
+    def __init__(self, container_size, blocks_num, reward_type, heightmap_type="full", initial_container_size=None,
+                 max_height=None, packing_strategy="LB_GREEDY", _batch=None, _row=0):
+        if _batch is None:
+            _batch = BatchedContainers(container_size, blocks_num, reward_type, heightmap_type, initial_container_size,
+                                       max_height, packing_strategy, batch_size=1)
+        self._batch = _batch
+        self._row = _row
+        self.container_size = _batch.container_size
+        self.block_dim = _batch.block_dim
+        self.blocks_num = _batch.blocks_num
+        self.reward_type = _batch.reward_type
+        self.heightmap_type = _batch.heightmap_type
+        self.packing_strategy = _batch.packing_strategy
+
+    @classmethod
+    def _view_of(cls, batch, row):
+        views = batch.__dict__.setdefault("_row_views", {})
+        v = views.get(row)
+        if v is None:
+            v = cls(None, None, None, _batch=batch, _row=row)
+            views[row] = v
+        return v
+
+    def _enc_row(self, enc):
+        return enc[self._row].astype(np.int64)
+
+    def add_new_block(self, block, is_rotate=False):
+        bt, b = self._batch, self._row
+        block = np.asarray(block, dtype=np.float32)
+        base = block.base
+        pending = bt.__dict__.get("_pending")
+        if pending is not None and pending["next"] == b and b > 0:
+            pending["next"] = b + 1
+            if not np.array_equal(pending["blocks"][b], block):
+                raise RuntimeError("tapenv: add_new_block rows must come from the batch handed to row 0")
+            if pending["next"] == bt.batch_size:
+                bt.__dict__["_pending"] = None
+            return self._enc_row(pending["enc"])
+        if bt.batch_size > 1:
+            if b != 0 or base is None or base.shape != (bt.batch_size, bt.block_dim):
+                raise RuntimeError("tapenv: in a batch, add_new_block must be called for rows 0..B-1 in order with "
+                                   "rows of one [B,dim] array (model.py:412,452-453); use BatchedContainers.add_new_blocks")
+            blocks = np.ascontiguousarray(base, dtype=np.float32)
+        else:
+            blocks = block.reshape(1, -1)
+        enc = bt.add_new_blocks(torch.from_numpy(blocks).to(bt.device)).cpu().numpy()
+        enc = enc.astype(np.float32)
+        if bt.batch_size > 1:
+            bt.__dict__["_pending"] = {"next": 1, "blocks": blocks, "enc": enc}
+        return self._enc_row(enc)
+
+    def get_heightmap(self, is_full=None):
+        h = self.heightmap
+        if is_full is not None or self.heightmap_type == "full":
+            return h
+        if self.heightmap_type == "zero":
+            return h - h.min()
+        if self.block_dim == 2:
+            return h[1:] - h[:-1]
+        out = np.zeros((2,) + h.shape, dtype=h.dtype)
+        out[0, 1:, :] = h[1:, :] - h[:-1, :]
+        out[1, :, 1:] = h[:, 1:] - h[:, :-1]
+        return out
+
+    def clear_container(self):
+        if self._batch.batch_size != 1:
+            raise RuntimeError("tapenv: clear the whole batch with BatchedContainers.clear_container()")
+        self._batch.clear_container()
+
+    def calc_ratio(self):
+        """One launch + one D2H copy per batch state (cached until the batch changes), then row reads:
+        model.py:509-510 calls this once per environment."""
+        bt = self._batch
+        cache = bt.__dict__.get("_ratio_cache")
+        if cache is None or cache[0] != bt._version:
+            cache = (bt._version, bt.calc_ratio().cpu().numpy())
+            bt.__dict__["_ratio_cache"] = cache
+        return float(cache[1][self._row])
+
+    def calc_CPS(self):
+        v, e, s, k = [int(x) for x in self._batch.scalars[self._row].tolist()]
+        if k == 0:
+            return 0, 0, 0
+        h = int(self.heightmap.max())
+        cells = self._batch._cells
+        return v / (cells * h), v / (e + v), s / k
+
+    # attributes the reference's callers read (rolling.py:640-658, model.py:1175)
+    @property
+    def heightmap(self):
+        return self._batch.heightmap[self._row].cpu().numpy().astype(np.int64)
+
+    @property
+    def positions(self):
+        return self._batch.positions[self._row].cpu().numpy().astype(np.int64)
+
+    @property
+    def stable(self):
+        return [bool(v) for v in self._batch.stable[self._row].tolist()]
+
+    @property
+    def valid_size(self):
+        return int(self._batch.scalars[self._row, 0].item())
+
+    @property
+    def empty_size(self):
+        return int(self._batch.scalars[self._row, 1].item())
+
+    @property
+    def current_blocks_num(self):
+        return int(self._batch.scalars[self._row, 3].item())

@@ -1,0 +1,256 @@
+"""Generate the committed golden fixtures from the UNMODIFIED Python reference.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference);
+the fixtures it writes travel to the GPU box, the reference does not.
+
+    python tests/golden/make_golden.py [--only rand2d,rand3d,ppsg,traj,kat]
+
+Writes next to this file:
+  rand2d_n10.npz   RAND 2D n=10, 4096 samples (BASELINE configs 1/2)       inputs only
+  rand3d_n10.npz   RAND 3D n=10, 2048 samples (config 3)                   inputs only
+  ppsg2d_n20.npz   PPSG 2D n=20 W=7 pool (config 4)                        inputs only
+  traj_*.npz       per-step trajectories of the live reference env path
+                   (pack.update_dynamic + pack.update_mask + tools.Container) under a
+                   seeded random-valid policy: ptr, heightmap, encoded heightmap, masks,
+                   positions, stable, valid/empty, calc_ratio
+  kat.npz          the known-answer vectors G1-G5 of SURVEY.md section 4 re-derived from the reference
+
+Input tensors are stored compactly: `static` as uint8 [B,1+dim,S] (values are small
+integers), `dynamic` (0/1 entries) bit-packed along the flattened [3n*S] axis.
+tests/golden_io.py restores the float32 tensors.
+"""
+import argparse
+import os
+import shutil
+import signal
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+
+def pack_inputs(static, dynamic):
+    static = np.asarray(static)
+    dynamic = np.asarray(dynamic)
+    assert (static == np.round(static)).all() and static.min() >= 0 and static.max() < 256
+    assert np.isin(dynamic, (0.0, 1.0)).all()
+    B = dynamic.shape[0]
+    bits = np.packbits(dynamic.reshape(B, -1).astype(np.uint8), axis=1)
+    return dict(static_u8=static.astype(np.uint8), dynamic_bits=bits, dynamic_shape=np.array(dynamic.shape))
+
+
+def in_scratch(fn):
+    def wrapped(*a, **k):
+        cwd = os.getcwd()
+        d = tempfile.mkdtemp(prefix="tapgold_")
+        os.chdir(d)
+        try:
+            return fn(*a, **k)
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(d, ignore_errors=True)
+    return wrapped
+
+
+@in_scratch
+def make_rand(obj_dim, num, out_name, seed=12345):
+    """pack.create_dataset(10, num, 16, obj_dim, 7, 50, 1, [1,5], seed) + PACKDataset('bot','diff',True,5)
+    -- the scripts/train.sh defaults."""
+    mods = refshim.load(("tools", "generate", "pack"))
+    pack = mods["pack"]
+    t = time.time()
+    train_dir, _ = pack.create_dataset(10, num, 16, obj_dim, 7, 50, 1, [1, 5], seed=seed)
+    ds = pack.PACKDataset(train_dir, 10, num, seed, "bot", "diff", True, 5)
+    static, dynamic = ds.static.numpy(), ds.dynamic.numpy()
+    np.savez_compressed(os.path.join(HERE, out_name), seed=seed, obj_dim=obj_dim, blocks_num=10,
+                        how="pack.create_dataset(10,%d,16,%d,7,50,1,[1,5],seed=%d)" % (num, obj_dim, seed),
+                        **pack_inputs(static, dynamic))
+    print(out_name, static.shape, dynamic.shape, "%.1fs" % (time.time() - t))
+
+
+class _Timeout(Exception):
+    pass
+
+
+def _alarm(signum, frame):
+    raise _Timeout()
+
+
+def _ppsg_worker(args):
+    """One PPSG sample through generate.generate_blocks_with_GT (generate.py:977), with a
+    wall-clock timeout + reseed because the generator's rejection loops are unbounded
+    (SURVEY.md section 6).  DEVIATION from pack.create_dataset_gt: per-sample seeds."""
+    idx, blocks_num, W, H, size_range, per_sample_timeout, prob, key = args
+    mods = refshim.load(("tools", "generate"))
+    generate = mods["generate"]
+    import io
+    import contextlib
+    attempt = 0
+    while True:
+        seed = 12345 + idx * 1000 + attempt
+        np.random.seed(seed)
+        target = [W, int(np.random.choice(key, p=prob))]
+        signal.signal(signal.SIGALRM, _alarm)
+        signal.alarm(per_sample_timeout)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                r = generate.generate_blocks_with_GT(blocks_num, target, [W, H], 1, size_range, "bot", idx,
+                                                     allow_rot=True)
+            signal.alarm(0)
+            return idx, seed, [np.asarray(x) for x in r]
+        except _Timeout:
+            attempt += 1
+        except Exception:
+            signal.alarm(0)
+            attempt += 1
+
+
+@in_scratch
+def make_ppsg(num, out_name, blocks_num=20, W=7, H=50, procs=8):
+    import multiprocessing as mp
+    mods = refshim.load(("tools", "generate", "pack"))
+    pack, generate = mods["pack"], mods["generate"]
+    t = time.time()
+    # generate_height_prob (generate.py:977) reads the RAND valid set of 10-block instances
+    pack.create_dataset(10, 16, 10000, 2, W, H, 1, [1, 5], seed=12345)
+    prob, key = generate.generate_height_prob(2, blocks_num, [1, 5], W, W)
+    with mp.Pool(procs) as pool:
+        res = pool.map(_ppsg_worker, [(i, blocks_num, W, H, [1, 5], 20, prob, key) for i in range(num)], chunksize=1)
+    res.sort(key=lambda r: r[0])
+    d = "./data/gt_2d/pool/"
+    os.makedirs(d)
+    files = {k: open(d + k + ".txt", "w") for k in ("blocks", "pos", "container", "dep_move", "dep_small", "dep_large")}
+
+    def w(f, arr):
+        f.write(" ".join(str(v) for v in np.asarray(arr).reshape(-1)) + "\n")
+    for _, _, (rot_blocks, positions, deps_move, small, large) in res:
+        for bi in range(len(rot_blocks)):
+            w(files["blocks"], rot_blocks[bi]); w(files["dep_small"], small[bi]); w(files["dep_large"], large[bi])
+        w(files["pos"], positions); w(files["dep_move"], deps_move)
+        w(files["container"], np.zeros(blocks_num, dtype=int))
+    for f in files.values():
+        f.close()
+    ds = pack.PACKDataset(d, blocks_num, num, 12345, "bot", "diff", True, W)
+    static, dynamic = ds.static.numpy(), ds.dynamic.numpy()
+    np.savez_compressed(os.path.join(HERE, out_name), seeds=np.array([r[1] for r in res]), obj_dim=2,
+                        blocks_num=blocks_num,
+                        how="generate.generate_blocks_with_GT(20,[7,h~height_prob],[7,50],1,[1,5],'bot') per sample, "
+                            "20 s timeout + reseed", **pack_inputs(static, dynamic))
+    print(out_name, static.shape, dynamic.shape, "%.1fs" % (time.time() - t))
+
+
+def ref_trajectory(static, dynamic, container_size, reward_type, heightmap_type, packing_strategy, seed,
+                   input_type="bot"):
+    """Drive the reference env path exactly as model.py:294-307, :376-458, :509-510 does, with
+    ptr ~ multinomial(current_mask) from a seeded generator."""
+    import torch
+    mods = refshim.load(("tools", "pack"))
+    tools, pack = mods["tools"], mods["pack"]
+    static_t = torch.from_numpy(static)
+    dyn = torch.from_numpy(dynamic)
+    B, _, S = static.shape
+    dim = len(container_size)
+    R = 2 if dim == 2 else 6
+    n = S // R
+    g = torch.Generator().manual_seed(seed)
+    containers = [tools.Container(container_size, n, reward_type, heightmap_type, packing_strategy=packing_strategy)
+                  for _ in range(B)]
+    mask = torch.ones(B, S)
+    move = dyn[:, :n].sum(1); small = dyn[:, n:2 * n].sum(1); large = dyn[:, 2 * n:].sum(1)     # model.py:297-307
+    dm = small * large + move
+    cur = mask.clone(); cur[dm.ne(0)] = 0.0
+    out = dict(ptr=[], heightmap=[], dec_dyn=[], cur_mask=[cur.numpy().copy()], mask=[], valid=[], empty=[])
+    for t in range(n):
+        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+        dyn = pack.update_dynamic(dyn, static_t, ptr, input_type, True)
+        cur, mask = pack.update_mask(mask, dyn, static_t, ptr, input_type, True)
+        blocks = torch.gather(static_t[:, 1:1 + dim], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1)).squeeze(2).numpy()
+        hms = [np.asarray(containers[b].add_new_block(blocks[b], bool(ptr[b] < n))).copy() for b in range(B)]
+        out["ptr"].append(ptr.numpy().copy())
+        out["heightmap"].append(np.stack([np.asarray(c.heightmap).copy() for c in containers]))
+        out["dec_dyn"].append(np.stack(hms).reshape(B, -1))
+        out["cur_mask"].append(cur.numpy().copy()); out["mask"].append(mask.numpy().copy())
+        out["valid"].append(np.array([c.valid_size for c in containers]))
+        out["empty"].append(np.array([c.empty_size for c in containers]))
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["positions"] = np.stack([np.asarray(c.positions) for c in containers])
+    res["stable"] = np.stack([np.asarray(c.stable, dtype=np.uint8) for c in containers])
+    res["ratio"] = np.array([c.calc_ratio() for c in containers], dtype=np.float64)
+    res["dynamic_final"] = np.packbits(dyn.numpy().reshape(B, -1).astype(np.uint8), axis=1)
+    return res
+
+
+def make_traj():
+    from tests.golden_io import load_inputs
+    cases = [
+        ("traj_2d_lbg_soft", "rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 96),
+        ("traj_2d_lbg_hard", "rand2d_n10.npz", [5, 50], "C+P+S-lb-hard", "zero", "LB_GREEDY", 96),
+        ("traj_2d_lbg_w7_full", "rand2d_n10.npz", [7, 50], "C+P-lb-soft", "full", "LB_GREEDY", 48),
+        ("traj_2d_macs_rand", "rand2d_n10.npz", [5, 50], "C+P+S-mcs-soft", "diff", "MACS", 64),
+        ("traj_2d_macs_ppsg", "ppsg2d_n20.npz", [7, 50], "C+P+S-mcs-hard", "diff", "MACS", 48),
+        ("traj_3d_lbg_soft", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 64),
+        ("traj_3d_lbg_hard", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-hard", "full", "LB_GREEDY", 48),
+    ]
+    for name, src, size, rt, hm, strat, num in cases:
+        p = os.path.join(HERE, src)
+        if not os.path.exists(p):
+            print("skip", name, "(no", src, ")")
+            continue
+        t = time.time()
+        static, dynamic = load_inputs(p, num)
+        res = ref_trajectory(static, dynamic, size, rt, hm, strat, seed=2024)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), source=src, container_size=np.array(size),
+                            reward_type=rt, heightmap_type=hm, packing_strategy=strat, num=num, **res)
+        print(name, "%.1fs" % (time.time() - t), "mean ratio %.4f" % res["ratio"].mean())
+
+
+def make_kat():
+    """Known-answer vectors (G1-G4 sequences, doc/data.md, visual/draw_result.py),
+    outputs re-derived here from the live reference."""
+    tools = refshim.load(("tools",))["tools"]
+    seqs = {
+        "G1": ([5, 50], "C+P+S-lb-soft", "LB_GREEDY",
+               [[3, 3], [3, 3], [2, 3], [2, 4], [4, 2], [3, 3], [3, 4], [1, 1], [1, 3], [3, 4]]),
+        "G2": ([5, 50], "C+P+S-lb-hard", "LB_GREEDY",
+               [[4, 1], [2, 3], [4, 2], [1, 1], [3, 3], [4, 4], [2, 2], [1, 4], [3, 1], [2, 1]]),
+        "G3": ([7, 100], "C+P+S-mcs-hard", "MACS",
+               [[3, 2], [1, 4], [4, 3], [2, 1], [3, 2], [1, 2], [1, 4], [2, 3], [2, 3], [3, 2], [4, 3], [4, 4], [3, 4],
+                [1, 2], [1, 2], [2, 2], [3, 2], [2, 3], [1, 3], [1, 4]]),
+        "G4": ([5, 5, 50], "C+P+S-lb-soft", "LB_GREEDY",
+               [[2, 4, 3], [3, 2, 2], [1, 4, 3], [3, 1, 4], [3, 2, 2], [2, 2, 3], [2, 2, 3], [1, 2, 2], [2, 3, 2],
+                [3, 3, 1]]),
+        "DRAW": ([4, 6], "C+P+S-lb-hard", "LB_GREEDY", [[3, 2], [1, 1], [1, 2]]),   # visual/draw_result.py:14-34
+    }
+    out = {}
+    for name, (size, rt, strat, blocks) in seqs.items():
+        c = tools.Container(size, len(blocks), rt, "diff", packing_strategy=strat)
+        hms, encs = [], []
+        for b in blocks:
+            encs.append(np.asarray(c.add_new_block(np.array(b, dtype=np.float32))).reshape(-1).copy())
+            hms.append(np.asarray(c.heightmap).reshape(-1).copy())
+        out[name + "_size"] = np.array(size); out[name + "_reward_type"] = rt; out[name + "_strategy"] = strat
+        out[name + "_blocks"] = np.array(blocks); out[name + "_heightmaps"] = np.stack(hms)
+        out[name + "_enc"] = np.stack(encs); out[name + "_positions"] = np.asarray(c.positions)
+        out[name + "_stable"] = np.asarray(c.stable, dtype=np.uint8)
+        out[name + "_valid"] = c.valid_size; out[name + "_empty"] = c.empty_size; out[name + "_ratio"] = c.calc_ratio()
+    np.savez_compressed(os.path.join(HERE, "kat.npz"), **out)
+    print("kat.npz", {k: float(out[k + "_ratio"]) for k in seqs})
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat")
+    ap.add_argument("--ppsg-num", type=int, default=512)
+    a = ap.parse_args()
+    only = a.only.split(",")
+    if "kat" in only: make_kat()
+    if "rand2d" in only: make_rand(2, 4096, "rand2d_n10.npz")
+    if "rand3d" in only: make_rand(3, 2048, "rand3d_n10.npz")
+    if "ppsg" in only: make_ppsg(a.ppsg_num, "ppsg2d_n20.npz")
+    if "traj" in only: make_traj()

@@ -1,0 +1,33 @@
+"""Loaders for the committed golden fixtures (tests/golden/*.npz, written by make_golden.py)."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_path(name):
+    return name if os.path.isabs(name) else os.path.join(GOLDEN_DIR, name)
+
+
+def unpack_dynamic(bits, shape, num=None):
+    shape = [int(v) for v in shape]
+    if num is not None:
+        bits = bits[:num]
+        shape[0] = bits.shape[0]
+    per = shape[1] * shape[2]
+    d = np.unpackbits(bits, axis=1)[:, :per]
+    return np.ascontiguousarray(d.reshape(shape).astype(np.float32))
+
+
+def load_inputs(name, num=None):
+    """-> (static f32 [B,1+dim,S], dynamic f32 [B,3n,S]) exactly as PACKDataset built them."""
+    z = np.load(golden_path(name))
+    static = z["static_u8"][:num].astype(np.float32)
+    dynamic = unpack_dynamic(z["dynamic_bits"], z["dynamic_shape"], num)
+    return np.ascontiguousarray(static), dynamic
+
+
+def load_traj(name):
+    z = np.load(golden_path(name if name.endswith(".npz") else name + ".npz"))
+    return {k: z[k] for k in z.files}

@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tapenv.h declares; host-side
+configuration logic (no kernels are launched here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tapenv.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tapenv_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tapenv import _capi
+    names = declared_symbols()
+    assert len(names) >= 14
+    raw = C.CDLL(_capi._build.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), "libtapenv.so does not export %s" % n
+        assert n in _capi.SYMBOLS, "%s has no ctypes prototype" % n
+    assert _capi.lib.tapenv_version() == 100 + 0 or _capi.lib.tapenv_version() > 100
+
+
+def test_config_from_reference_option_strings():
+    from tapenv import make_config, _capi
+    c = make_config(4096, 10, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "bot", True)
+    assert (c.dim, c.rotate_types, c.width, c.length, c.height) == (2, 2, 5, 1, 50)
+    assert (c.static_rows, c.dyn_rows, c.update_time) == (3, 30, 3)
+    assert c.reward_flags == 2 | 4 and c.ratio_mode == 4 and c.strategy == _capi.LB_GREEDY
+    c = make_config(8, 10, [5, 5, 50], "C+P+S-lb-hard", "full", "LB_GREEDY", "bot", True)
+    assert (c.dim, c.rotate_types, c.length, c.static_rows, c.dyn_rows) == (3, 6, 5, 4, 30)
+    assert c.reward_flags & 1
+    # tools.py:3617-3620: the reward type overrides the packing strategy
+    c = make_config(8, 20, [7, 50], "C+P+S-mcs-hard", "diff", "LB_GREEDY", "bot", True)
+    assert c.strategy == _capi.MACS and c.reward_flags & 8 and not c.reward_flags & 16
+    # tools.py:3961: C+P-lb-soft -> (C+P)/2 ; no 'S' in the string -> S term off
+    c = make_config(8, 10, [5, 50], "C+P-lb-soft", "zero", "LB_GREEDY", "bot", True)
+    assert c.ratio_mode == 7 and not c.reward_flags & 4
+    c = make_config(8, 10, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "simple", False)
+    assert (c.rotate_types, c.dyn_rows, c.update_time) == (1, 10, 1)
+
+
+@pytest.mark.parametrize("kw,code", [
+    (dict(reward_type="bogus"), -2), (dict(heightmap_type="bogus"), -2), (dict(packing_strategy="bogus"), -2),
+    (dict(input_type="bogus"), -2), (dict(container_size=[64, 50]), -3), (dict(blocks_num=40), -3),
+    (dict(input_type="mul"), -6),
+])
+def test_config_errors(kw, code):
+    from tapenv import make_config, TapEnvError
+    args = dict(batch=4, blocks_num=10, container_size=[5, 50], reward_type="C+P+S-lb-soft", heightmap_type="diff",
+                packing_strategy="LB_GREEDY", input_type="bot", allow_rot=True)
+    args.update(kw)
+    with pytest.raises(TapEnvError) as e:
+        make_config(**args)
+    assert e.value.code == code and isinstance(e.value, ValueError)
+
+
+def test_state_layout_is_disjoint_and_sized():
+    from tapenv import make_config, _capi
+    c = make_config(1000, 10, [5, 5, 50], "C+P+S-lb-soft", "diff")
+    lay = _capi.StateLayout()
+    assert _capi.lib.tapenv_state_get_layout(C.byref(c), C.byref(lay)) == 0
+    offs = [lay.scalars, lay.heightmap, lay.positions, lay.blocks, lay.stable, lay.flags, lay.total]
+    assert offs == sorted(offs) and lay.total == _capi.lib.tapenv_state_bytes(C.byref(c))
+    assert lay.heightmap - lay.scalars >= 1000 * 16 and lay.positions - lay.heightmap >= 1000 * 25 * 4
+    assert _capi.lib.tapenv_encoded_heightmap_len(C.byref(c)) == 50
+    assert all(o % 16 == 0 for o in offs)
+
+
+def test_null_and_cpu_arguments_are_rejected_without_launch():
+    import torch
+    from tapenv import make_config, _capi, update_dynamic
+    c = make_config(4, 10, [5, 50])
+    assert _capi.lib.tapenv_reset(C.byref(c), None, None, None, None, None) == _capi.EINVAL
+    assert _capi.lib.tapenv_step(C.byref(c), None, None, None, None, None, None, None, None, None, None, None) == _capi.EINVAL
+    with pytest.raises(RuntimeError):                       # no CPU fallback
+        update_dynamic(torch.zeros(4, 30, 20), torch.zeros(4, 3, 20), torch.zeros(4, dtype=torch.long), "bot", True)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tap-net_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(d, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(d, f)

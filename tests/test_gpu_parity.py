@@ -1,0 +1,243 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle and the reference-derived
+golden fixtures.  Integer / index / mask outputs must be bit-exact; the reward is compared as float32
+within 1e-6 (north_star tolerance) and is in practice bit-equal."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden_io import load_inputs, load_traj, golden_path
+from tests.rollout import oracle_rollout, random_valid_ptrs
+
+pytestmark = pytest.mark.gpu
+REWARD_TOL = 1e-6
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def gpu_rollout(static, dynamic, ptr_seq, container_size, reward_type, heightmap_type, packing_strategy, fused=True):
+    """Drive BatchedContainers like model.py drives the reference; returns per-step numpy arrays."""
+    torch = _torch()
+    import tapenv
+    dev = torch.device("cuda:0")
+    B, _, S = static.shape
+    dim = len(container_size)
+    n = S // (2 if dim == 2 else 6)
+    st = torch.from_numpy(static).to(dev)
+    dyn = torch.from_numpy(dynamic).to(dev)
+    dyn0 = dyn.clone()
+    env = tapenv.BatchedContainers(container_size, n, reward_type, heightmap_type, packing_strategy=packing_strategy,
+                                   batch_size=B, device=dev)
+    cur, mask = env.reset(dyn)
+    import ctypes
+    if tapenv._capi.lib.tapenv_add_blocks(ctypes.byref(env.cfg), None, None, None, None) == tapenv._capi.EUNSUPPORTED:
+        pytest.skip("strategy not built yet")
+    out = dict(heightmap=[], dec_dyn=[], cur_mask=[cur.cpu().numpy()], mask=[], valid=[], empty=[], dynamic=[], dec_static=[])
+    for t in range(ptr_seq.shape[0]):
+        ptr = torch.from_numpy(ptr_seq[t]).to(dev)
+        if fused:
+            dyn_in = dyn
+            dyn, cur, mask, dec_static, dec_dyn = env.step(ptr, st, dyn_in, mask)
+        else:
+            dyn = tapenv.update_dynamic(dyn, st, ptr, "bot", True)
+            cur, mask = tapenv.update_mask(mask, dyn, st, ptr, "bot", True)
+            dec_static = torch.gather(st[:, 1:1 + dim], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1)).squeeze(2)
+            dec_dyn = env.add_new_blocks(dec_static)
+        out["heightmap"].append(env.heightmap.cpu().numpy().reshape(B, -1))
+        out["dec_dyn"].append(dec_dyn.cpu().numpy().reshape(B, -1)); out["dec_static"].append(dec_static.cpu().numpy())
+        out["cur_mask"].append(cur.cpu().numpy()); out["mask"].append(mask.cpu().numpy())
+        out["valid"].append(env.valid_size.cpu().numpy()); out["empty"].append(env.empty_size.cpu().numpy())
+        out["dynamic"].append(dyn.cpu().numpy())
+    assert torch.equal(dyn0, torch.from_numpy(dynamic).to(dev)), "inputs must never be modified (pack.py:370 clone)"
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["positions"] = env.positions.cpu().numpy()
+    res["stable"] = env.stable.cpu().numpy()
+    res["reward"] = env.calc_ratio().cpu().numpy()
+    res["k"] = env.current_blocks_num.cpu().numpy()
+    res["flags"] = env.flags.cpu().numpy()
+    return res
+
+
+def assert_same(g, r, ptr_seq, static, dim):
+    B = static.shape[0]
+    for k in ("heightmap", "cur_mask", "mask", "valid", "empty", "positions", "stable", "dynamic"):
+        assert np.array_equal(g[k], r[k]), k
+    assert np.array_equal(g["dec_dyn"], r["dec_dyn"].astype(np.float32)), "encoded heightmap"
+    want_static = np.stack([static[np.arange(B)[:, None], 1 + np.arange(dim)[None, :], p[:, None]] for p in ptr_seq])
+    assert np.array_equal(g["dec_static"], want_static)
+    assert np.abs(g["reward"].astype(np.float64) - r["ratio"]).max() <= REWARD_TOL
+    assert np.array_equal(g["reward"], r["ratio"].astype(np.float32))     # and in fact bit-equal after fp64->fp32
+    assert (g["flags"] == 0).all()
+
+
+TRAJ = ["traj_2d_lbg_soft", "traj_2d_lbg_hard", "traj_2d_lbg_w7_full", "traj_2d_macs_rand", "traj_2d_macs_ppsg",
+        "traj_3d_lbg_soft", "traj_3d_lbg_hard"]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", TRAJ)
+def test_reference_trajectories(name, fused):
+    """CUDA vs trajectories recorded from the live Python reference (independent of the C oracle)."""
+    if not os.path.exists(golden_path(name + ".npz")):
+        pytest.skip("fixture not generated")
+    t = load_traj(name)
+    static, dynamic = load_inputs(str(t["source"]), int(t["num"]))
+    size = t["container_size"].tolist()
+    g = gpu_rollout(static, dynamic, t["ptr"], size, str(t["reward_type"]), str(t["heightmap_type"]),
+                    str(t["packing_strategy"]), fused=fused)
+    B = static.shape[0]
+    for k in ("cur_mask", "mask", "valid", "empty", "positions", "stable"):
+        assert np.array_equal(g[k], t[k]), k
+    assert np.array_equal(g["heightmap"], t["heightmap"].reshape(g["heightmap"].shape))
+    assert np.array_equal(g["dec_dyn"], t["dec_dyn"].astype(np.float32))
+    assert np.abs(g["reward"].astype(np.float64) - t["ratio"]).max() <= REWARD_TOL
+    assert np.array_equal(g["reward"], t["ratio"].astype(np.float32))
+
+
+CASES = [
+    # fixture, num, container, reward_type, heightmap_type, strategy
+    ("rand2d_n10.npz", 4096, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY"),     # BASELINE config 2
+    ("rand2d_n10.npz", 1024, [5, 50], "C+P+S-lb-hard", "zero", "LB_GREEDY"),
+    ("rand2d_n10.npz", 515, [4, 50], "C+P+S-lb-hard", "full", "LB_GREEDY"),      # width 4: frequent unplaced blocks
+    ("rand2d_n10.npz", 257, [9, 50], "C+P-lb-soft", "diff", "LB_GREEDY"),
+    ("rand2d_n10.npz", 300, [32, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY"),     # maximum compiled width
+    ("rand2d_n10.npz", 1024, [5, 50], "C+P+S-mcs-soft", "diff", "MACS"),
+    ("rand2d_n10.npz", 512, [5, 50], "C+P+S-mcs-hard", "full", "MACS"),
+    ("ppsg2d_n20.npz", 512, [7, 50], "C+P+S-mcs-hard", "diff", "MACS"),          # BASELINE config 4 (pool)
+    ("rand3d_n10.npz", 2048, [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY"),  # BASELINE config 3
+    ("rand3d_n10.npz", 512, [5, 5, 50], "C+P+S-lb-hard", "zero", "LB_GREEDY"),
+    ("rand3d_n10.npz", 256, [4, 6, 50], "C+P+S-lb-soft", "full", "LB_GREEDY"),   # W != L
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s-%s-%s" % (c[0].split("_")[0], "x".join(map(str, c[2])), c[3], c[4]))
+def test_fused_step_matches_oracle_every_step(case):
+    src, num, size, rt, hm, strat = case
+    if not os.path.exists(golden_path(src)):
+        pytest.skip("fixture not generated")
+    static, dynamic = load_inputs(src, num)
+    r = oracle_rollout(static, dynamic, size, rt, hm, strat, seed=7)
+    g = gpu_rollout(static, dynamic, r["ptr"], size, rt, hm, strat, fused=True)
+    assert_same(g, r, r["ptr"], static, len(size))
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[6], CASES[9]], ids=["2d", "2d-w4-hard", "macs", "3d"])
+def test_unfused_ops_match_oracle_every_step(case):
+    src, num, size, rt, hm, strat = case
+    if not os.path.exists(golden_path(src)):
+        pytest.skip("fixture not generated")
+    static, dynamic = load_inputs(src, min(num, 384))
+    r = oracle_rollout(static, dynamic, size, rt, hm, strat, seed=11)
+    g = gpu_rollout(static, dynamic, r["ptr"], size, rt, hm, strat, fused=False)
+    assert_same(g, r, r["ptr"], static, len(size))
+
+
+@pytest.mark.parametrize("B", [0, 1, 3, 33])
+def test_ragged_batch_sizes(B):
+    torch = _torch()
+    import tapenv
+    static, dynamic = load_inputs("rand2d_n10.npz", max(B, 1))
+    static, dynamic = static[:B], dynamic[:B]
+    if B == 0:
+        env = tapenv.BatchedContainers([5, 50], 10, "C+P+S-lb-soft", "diff", batch_size=0)
+        cur, mask = env.reset(torch.zeros(0, 30, 20, device="cuda"))
+        assert cur.shape == (0, 20) and env.calc_ratio().shape == (0,)
+        return
+    r = oracle_rollout(static, dynamic, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", seed=3)
+    g = gpu_rollout(static, dynamic, r["ptr"], [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY")
+    assert_same(g, r, r["ptr"], static, 2)
+
+
+def test_known_answer_sequences_on_gpu():
+    torch = _torch()
+    import tapenv
+    kat = np.load(golden_path("kat.npz"))
+    for name in ("G1", "G2", "DRAW", "G3", "G4"):
+        size = kat[name + "_size"].tolist()
+        blocks = kat[name + "_blocks"]
+        try:
+            env = tapenv.BatchedContainers(size, len(blocks), str(kat[name + "_reward_type"]), "diff",
+                                           packing_strategy=str(kat[name + "_strategy"]), batch_size=2)
+        except tapenv.TapEnvError as e:
+            if e.code == -6:
+                continue
+            raise
+        for t, b in enumerate(blocks):
+            enc = env.add_new_blocks(torch.tensor(np.stack([b, b]), dtype=torch.float32, device="cuda"))
+            assert np.array_equal(enc.cpu().numpy().reshape(2, -1)[1], kat[name + "_enc"][t].astype(np.float32)), (name, t)
+            assert np.array_equal(env.heightmap.cpu().numpy().reshape(2, -1)[0], kat[name + "_heightmaps"][t]), (name, t)
+        assert np.array_equal(env.positions.cpu().numpy()[1], kat[name + "_positions"])
+        assert np.array_equal(env.stable.cpu().numpy()[0], kat[name + "_stable"])
+        assert abs(float(env.calc_ratio()[0]) - float(kat[name + "_ratio"])) <= REWARD_TOL
+
+
+def test_unplaceable_and_overflow_edge_cases():
+    """Q1: a block wider than the container is not placed, state unchanged, k still advances; more than
+    blocks_num blocks / stacks above container height set the sticky flags instead of raising IndexError."""
+    torch = _torch()
+    import tapenv
+    from oracle import oracle
+    env = tapenv.BatchedContainers([5, 12], 4, "C+P+S-lb-soft", "full", batch_size=1)
+    ref = oracle.Container([5, 12], 4, "C+P+S-lb-soft", "full")
+    for b in ([3, 2], [6, 1], [2, 4]):
+        enc = env.add_new_blocks(torch.tensor([b], dtype=torch.float32, device="cuda"))
+        want = ref.add_new_block(np.array(b, np.float32))
+        assert np.array_equal(enc.cpu().numpy()[0], want.astype(np.float32))
+    assert env.stable.cpu().numpy()[0].tolist() == [int(s) for s in ref.stable]
+    assert env.positions.cpu().numpy()[0].tolist() == ref.positions.tolist()
+    assert int(env.current_blocks_num[0]) == 3 and abs(float(env.calc_ratio()[0]) - ref.calc_ratio()) <= REWARD_TOL
+    assert int(env.flags[0]) == 0
+    env.add_new_blocks(torch.tensor([[5, 4]], dtype=torch.float32, device="cuda"))
+    env.add_new_blocks(torch.tensor([[1, 1]], dtype=torch.float32, device="cuda"))      # 5th block of 4
+    assert int(env.flags[0]) & 2
+    with pytest.raises(IndexError):
+        env.check_flags()
+    env.clear_container()
+    assert int(env.flags[0]) == 0 and int(env.heightmap.sum()) == 0
+    for _ in range(4):
+        env.add_new_blocks(torch.tensor([[5, 4]], dtype=torch.float32, device="cuda"))  # 16 > height 12
+    assert int(env.flags[0]) & 1
+
+
+def test_container_proxy_drop_in_for_unmodified_model_loop():
+    """model.py:294, :452-453, :509-510 verbatim usage pattern against the per-environment views."""
+    torch = _torch()
+    import tapenv
+    static, dynamic = load_inputs("rand2d_n10.npz", 64)
+    B, n, dim = 64, 10, 2
+    r = oracle_rollout(static, dynamic, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", seed=5)
+    containers = tapenv.BatchedContainers([5, 50], n, "C+P+S-lb-soft", "diff", batch_size=B)
+    st = torch.from_numpy(static).cuda()
+    for t in range(n):
+        ptr = torch.from_numpy(r["ptr"][t]).cuda()
+        decoder_static = torch.gather(st[:, 1:1 + dim], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1))
+        blocks = decoder_static.squeeze(2).cpu().numpy()                       # model.py:412
+        is_rotate = (ptr < n).cpu().numpy().astype("bool")
+        heightmaps = []
+        for batch_index in range(B):                                           # model.py:452-453
+            heightmaps.append(containers[batch_index].add_new_block(blocks[batch_index], is_rotate[batch_index]))
+        assert np.array_equal(np.stack(heightmaps), r["dec_dyn"][t])
+    scores = [containers[b].calc_ratio() for b in range(B)]                    # model.py:509-510
+    assert np.abs(np.array(scores) - r["ratio"]).max() <= REWARD_TOL
+    assert containers[3].positions.tolist() == r["positions"][3].tolist()
+    assert containers[5].stable == [bool(v) for v in r["stable"][5]]
+
+
+def test_reward_partial_sums_are_deterministic():
+    torch = _torch()
+    import tapenv
+    static, dynamic = load_inputs("rand2d_n10.npz", 1000)
+    ptrs = random_valid_ptrs(static, dynamic, [5, 50], seed=1)
+    env = tapenv.BatchedContainers([5, 50], 10, "C+P+S-lb-soft", "diff", batch_size=1000)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    cur, mask = env.reset(dyn)
+    for t in range(10):
+        dyn, cur, mask, _, _ = env.step(torch.from_numpy(ptrs[t]).cuda(), st, dyn, mask)
+    r, s = env.calc_ratio(partial_sums=True)
+    r2, s2 = env.calc_ratio(partial_sums=True)
+    assert torch.equal(s, s2) and float(s[2]) == 1000.0
+    r64 = r.double().cpu().numpy()
+    assert abs(float(s[0]) - r64.sum()) < 1e-9 and abs(float(s[1]) - (r64 ** 2).sum()) < 1e-9
