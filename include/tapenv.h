@@ -14,6 +14,7 @@
  *    DEVICE pointers (sm_100a, HBM) unless the name ends in _host.
  *  - the caller owns every buffer (torch allocates them); the library never
  *    allocates, frees or retains memory, has no global state, and is re-entrant.
+ *  - kernels run on the CURRENT CUDA device of the calling thread; pointers must belong to it.
  *  - every function is stream-ordered on `stream` (a cudaStream_t passed as
  *    void*; NULL = legacy default stream) and never synchronises.
  *  - outputs never alias inputs (the reference clones: pack.py:318,323,370).
@@ -88,16 +89,22 @@ typedef struct tapenv_config {
     int32_t static_rows;    /* rows of `static`: 1+dim ('mul-with': 2+dim)                         */
     int32_t dyn_rows;       /* rows of `dynamic`: 3n for 'bot'-like inputs, n for 'simple'/'rot'   */
     int32_t update_time;    /* bands zeroed by update_dynamic: 3 or 1 (pack.py:349)                */
+    int32_t capacity;       /* blocks one container can take: rows of positions/blocks/stable per environment.
+                               tapenv_config_init sets it to blocks_num; rolling inference keeps ONE container for
+                               total_blocks_num blocks while the network window stays at blocks_num
+                               (rolling.py:702-703) -- set it, then re-check with tapenv_config_check.        */
 } tapenv_config;
 
 /* Byte offsets of the arrays inside the opaque per-batch state buffer. */
 typedef struct tapenv_state_layout {
     size_t scalars;    /* i32 [B,4]  valid_size, empty_size, stable count, current_blocks_num (tools.py:3635-3653) */
     size_t heightmap;  /* i32 [B,W] or [B,W,L]                                        (tools.py:3630) */
-    size_t positions;  /* i32 [B,n,dim]                                               (tools.py:3628) */
-    size_t blocks;     /* i32 [B,n,dim]  blocks in arrival order                      (tools.py:3631,3674) */
-    size_t stable;     /* u8  [B,n]                                                   (tools.py:3633) */
-    size_t flags;      /* i32 [B] sticky anomaly bits: 1 = a stack reached container height (NumPy would raise IndexError) */
+    size_t positions;  /* i32 [B,capacity,dim]                                        (tools.py:3628) */
+    size_t blocks;     /* i32 [B,capacity,dim]  blocks in arrival order               (tools.py:3631,3674) */
+    size_t stable;     /* u8  [B,capacity]                                            (tools.py:3633) */
+    size_t flags;      /* i32 [B] sticky anomaly bits (the reference would raise IndexError in each case):
+                          1 = a stack grew above container height, 2 = more than `capacity` blocks were added,
+                          4 = a pointer outside [0,S) was passed to the fused step */
     size_t total;      /* == tapenv_state_bytes() */
 } tapenv_state_layout;
 
@@ -193,10 +200,6 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
                    const int64_t *ptr_seq, int32_t steps, float *reward_out,
                    float *cur_mask_out, float *mask_out, float *dec_dynamic_out, void *stream);
 
-/* Launch-shape tuning knob (does not exist in the reference; never changes results):
- * environments (= warps) per CTA, one of 1, 2, 4, 8; 0 restores the automatic choice
- * (one CTA per environment). */
-void tapenv_set_envs_per_cta(int envs_per_cta);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@ def lib():
         L.tapo_update_mask.argtypes = [p, p, p] + [C.c_int] * 5 + [p, p]
         L.tapo_is_stable_3d_mask.argtypes = [C.c_int, C.c_int, p]
         L.tapo_is_stable_3d_mask.restype = C.c_int
+        L.tapo_is_stable_3d_masks.argtypes = [C.c_int, C.c_int, p, C.c_int, p]
         L.tapo_episode_batch.argtypes = ([C.c_int] * 6 + [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
                                          + [p] * 11 + [C.c_int])
         L.tapo_episode_batch.restype = C.c_int
@@ -272,3 +273,11 @@ def episode_batch(static, dynamic, ptr_seq, container_size, reward_type, heightm
 def is_stable_3d_mask(bx, by, occ):
     occ = np.ascontiguousarray(occ, dtype=np.uint8)
     return bool(lib().tapo_is_stable_3d_mask(bx, by, _ptr(occ)))
+
+
+def is_stable_3d_masks(bx, by, masks):
+    """Bulk tools.is_stable on support bitmasks (bit x*by+y) -> uint8 array."""
+    masks = np.ascontiguousarray(masks, dtype=np.uint32)
+    out = np.zeros(masks.shape[0], dtype=np.uint8)
+    lib().tapo_is_stable_3d_masks(bx, by, _ptr(masks), masks.shape[0], _ptr(out))
+    return out

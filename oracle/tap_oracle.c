@@ -224,6 +224,16 @@ int tapo_is_stable_3d_mask(int bx, int by, const unsigned char *occ /*[bx][by]*/
     return is_stable_3d(&e, bx, by, 0, 0, 1);
 }
 
+/* bulk form for the exhaustive tests of the CUDA-side restatement: out[i] = is_stable for support
+ * bitmask masks[i] (bit x*by+y, x-major) */
+void tapo_is_stable_3d_masks(int bx, int by, const unsigned *masks, int count, unsigned char *out) {
+    unsigned char occ[TAPO_MAXW * TAPO_MAXW];
+    for (int i = 0; i < count; i++) {
+        for (int c = 0; c < bx * by; c++) occ[c] = (masks[i] >> c) & 1u;
+        out[i] = (unsigned char)tapo_is_stable_3d_mask(bx, by, occ);
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* stable (insertion) sort of EMS records by one key -- Python list.sort is stable */
 static void stable_sort_by(int (*rec)[4], int cnt, int key) {

@@ -9,10 +9,14 @@
 
 #include "../../include/tapenv.h"
 #include "tapenv_common.cuh"
-#include "dynmask.cuh"
-#include "lbg2d.cuh"
+#include "dynpass.cuh"
+#include "place_lbg2d.cuh"
+#include "place_lbg3d.cuh"
+#include "place_macs2d.cuh"
 
 namespace tapenv {
+
+enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2 };
 
 // ------------------------------------------------------------------------------------
 // host-side helpers
@@ -28,13 +32,13 @@ static int enc_len_of(const tapenv_config *c) {
 }
 
 static void layout_of(const tapenv_config *c, tapenv_state_layout *L) {
-    const size_t B = (size_t)c->batch, n = (size_t)c->blocks_num, dim = (size_t)c->dim;
+    const size_t B = (size_t)c->batch, cap = (size_t)c->capacity, dim = (size_t)c->dim;
     size_t off = 0;
     L->scalars = off;   off = align_up(off + B * 4 * sizeof(int32_t), 256);
     L->heightmap = off; off = align_up(off + B * (size_t)cells_of(c) * sizeof(int32_t), 256);
-    L->positions = off; off = align_up(off + B * n * dim * sizeof(int32_t), 256);
-    L->blocks = off;    off = align_up(off + B * n * dim * sizeof(int32_t), 256);
-    L->stable = off;    off = align_up(off + B * n, 256);
+    L->positions = off; off = align_up(off + B * cap * dim * sizeof(int32_t), 256);
+    L->blocks = off;    off = align_up(off + B * cap * dim * sizeof(int32_t), 256);
+    L->stable = off;    off = align_up(off + B * cap, 256);
     L->flags = off;     off = align_up(off + B * sizeof(int32_t), 256);
     L->total = off;
 }
@@ -43,9 +47,20 @@ static DevCfg devcfg_of(const tapenv_config *c) {
     DevCfg d;
     d.B = c->batch; d.n = c->blocks_num; d.dim = c->dim; d.R = c->rotate_types;
     d.W = c->width; d.L = c->length; d.H = c->height; d.S = c->blocks_num * c->rotate_types;
+    d.cap = c->capacity;
     d.strategy = c->strategy; d.hm_type = c->heightmap_type; d.flags = c->reward_flags; d.ratio_mode = c->ratio_mode;
     d.static_rows = c->static_rows; d.dyn_rows = c->dyn_rows; d.update_time = c->update_time;
     d.enc_len = enc_len_of(c);
+    // geometry of the 128-bit precedence pass (dynpass.cuh); SV = 1 keeps the divisions defined when S % 4 != 0
+    d.SV = d.S % 4 == 0 && d.S >= 4 ? d.S / 4 : 1;
+    d.RP = 32 / d.SV > 0 ? 32 / d.SV : 1;
+    d.PB = (d.n + d.RP - 1) / d.RP;
+    d.nbands = d.dyn_rows / d.n;
+    d.inv_SV = (65536u + d.SV - 1) / d.SV;
+    d.inv_n = (65536u + d.n - 1) / d.n;
+    d.inv_L = (65536u + d.L - 1) / (d.L > 0 ? d.L : 1);
+    d.dyn_env = (unsigned)(d.dyn_rows * d.S);
+    d.static_env = (unsigned)(d.static_rows * d.S);
     return d;
 }
 
@@ -67,6 +82,7 @@ static int check_cfg(const tapenv_config *c) {
     if (c->batch < 0 || c->blocks_num < 1 || c->width < 1 || c->height < 1) return TAPENV_EINVAL;
     if (c->dim != 2 && c->dim != 3) return TAPENV_EINVAL;
     if (c->dim == 2 && c->length != 1) return TAPENV_ESHAPE;
+    if (c->dim == 3 && c->length < 1) return TAPENV_EINVAL;
     if (c->rotate_types < 1) return TAPENV_EINVAL;
     if (c->strategy != TAPENV_LB_GREEDY && c->strategy != TAPENV_MACS) return TAPENV_EENUM;
     if (c->heightmap_type < 0 || c->heightmap_type > 2) return TAPENV_EENUM;
@@ -75,34 +91,31 @@ static int check_cfg(const tapenv_config *c) {
     if (c->dyn_rows != c->blocks_num && c->dyn_rows != 3 * c->blocks_num) return TAPENV_ESHAPE;
     if (c->update_time != 1 && c->update_time != 3) return TAPENV_ESHAPE;
     if (c->update_time * c->blocks_num > c->dyn_rows) return TAPENV_ESHAPE;
+    if (c->capacity < 1) return TAPENV_ESHAPE;
     if (c->dim == 2 && c->width > kMaxWidth2D) return TAPENV_ELIMIT;
     if (c->dim == 3 && c->width * c->length > kMaxCells3D) return TAPENV_ELIMIT;
     if (c->blocks_num * c->rotate_types > kMaxCandidates) return TAPENV_ELIMIT;
     if (c->blocks_num > kMaxBlocks) return TAPENV_ELIMIT;
-    if ((long long)c->dyn_rows * c->blocks_num * c->rotate_types >= 65536) return TAPENV_ELIMIT;
+    if (c->strategy == TAPENV_MACS && c->capacity > kMaxBlocks) return TAPENV_ELIMIT;
+    if (c->height > (1 << 18)) return TAPENV_ELIMIT;
     return TAPENV_OK;
 }
 
-static int check_strategy_built(const tapenv_config *c) {
-    if (c->strategy == TAPENV_LB_GREEDY && c->dim == 2) return TAPENV_OK;
-    return TAPENV_EUNSUPPORTED;
-}
-
-static int g_envs_per_cta = 0;   // tuning knob only (0 = auto); never changes results
-
-static int pick_epc(int B) {
-    if (g_envs_per_cta > 0) return g_envs_per_cta;
-    return B > 32768 ? 4 : 1;    // one CTA per environment unless the grid would be many waves deep
+static int strategy_kernel(const tapenv_config *c) {
+    if (c->strategy == TAPENV_LB_GREEDY) return c->dim == 2 ? STRAT_LBG2D : STRAT_LBG3D;
+    if (c->strategy == TAPENV_MACS && c->dim == 2) return STRAT_MACS2D;
+    return -1;                                       // MACS 3D: not built (out of scope for v1)
 }
 
 static int launch_status() { return cudaGetLastError() == cudaSuccess ? TAPENV_OK : TAPENV_ECUDA; }
 
 // ------------------------------------------------------------------------------------
-// device: per-environment indexing
+// device: per-environment pieces
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ int env_index(int &lane) {
+__device__ __forceinline__ int env_index(int &lane, int &warp) {
     lane = threadIdx.x & 31;
-    return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    warp = threadIdx.x >> 5;
+    return blockIdx.x * kWarpsPerCta + warp;
 }
 
 __device__ __forceinline__ Scal load_scal(const StatePtrs &st, int b) {
@@ -111,158 +124,190 @@ __device__ __forceinline__ Scal load_scal(const StatePtrs &st, int b) {
     return s;
 }
 
-// Container.add_new_block for one environment (tools.py:3663-3744): placement,
-// commit, k += 1 even when the placement failed (tools.py:3713), heightmap encoding.
-__device__ __forceinline__ void container_add_block_2d(const DevCfg &c, const StatePtrs &st, int b, int lane,
-                                                       int bx, int bz, float *dec_dyn) {
-    int h = lane < c.W ? st.heightmap[(size_t)b * c.W + lane] : 0;
-    Scal sc = load_scal(st, b);
-    if (sc.k >= c.n) {   // the reference raises IndexError (rotate_state[k], tools.py:3677)
-        if (lane == 0) st.flags[b] |= 2;
-    } else {
-        const PlaceResult r = lbg2d_place(c, lane, bx, bz, h, sc);
-        if (lane < c.W) st.heightmap[(size_t)b * c.W + lane] = h;
-        if (lane == 0) {
-            const size_t o = ((size_t)b * c.n + sc.k) * 2;
-            st.blocks[o] = bx; st.blocks[o + 1] = bz;
-            if (r.placed) { st.positions[o] = r.x; st.positions[o + 1] = r.z; }
-            st.stable[(size_t)b * c.n + sc.k] = (unsigned char)r.stable;
-            if (r.placed && r.z + bz > c.H) st.flags[b] |= 1;
-            st.scal[b] = make_int4(sc.valid, sc.empty, sc.nstable, sc.k + 1);
+// Everything a placement needs from the state buffer, loaded up-front so the requests overlap the
+// precedence-tensor traffic.
+template <int STRAT>
+struct EnvRegs {
+    int h, x, y;
+    Scal sc;
+    MacsHist hist;
+
+    __device__ __forceinline__ void load(const DevCfg &c, const StatePtrs &st, int b, int lane) {
+        const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
+        h = lane < cells ? st.heightmap[(size_t)b * cells + lane] : 0;
+        sc = load_scal(st, b);
+        x = 0; y = 0;
+        if (STRAT == STRAT_LBG3D) { x = (int)(((unsigned)lane * c.inv_L) >> 16); y = lane - x * c.L; }
+        if (STRAT == STRAT_MACS2D) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = lane + 32 * s;
+                hist.x[s] = hist.z[s] = hist.xx[s] = hist.zz[s] = 0;
+                if (i < sc.k && i < c.cap) {
+                    const int2 p = *reinterpret_cast<const int2 *>(st.positions + ((size_t)b * c.cap + i) * 2);
+                    const int2 q = *reinterpret_cast<const int2 *>(st.blocks + ((size_t)b * c.cap + i) * 2);
+                    hist.x[s] = p.x; hist.z[s] = p.y; hist.xx[s] = q.x; hist.zz[s] = q.y;
+                }
+            }
         }
     }
-    if (dec_dyn) encode_heightmap_2d(c, lane, h, dec_dyn + (size_t)b * c.enc_len);
+};
+
+// Container.add_new_block for one environment (tools.py:3663-3744): placement, commit,
+// current_blocks_num += 1 even when the placement failed (tools.py:3713), heightmap encoding.
+template <int STRAT>
+__device__ __forceinline__ void container_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane,
+                                                    EnvRegs<STRAT> &e, int bx, int by, int bz, float *dec_dyn,
+                                                    unsigned *ems_keys, int extra_flags) {
+    const int dim = (STRAT == STRAT_LBG3D) ? 3 : 2;
+    const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
+    int anomaly = extra_flags;
+    if (e.sc.k >= c.cap) {       // the reference raises IndexError (rotate_state[k], tools.py:3677)
+        anomaly |= 2;
+    } else {
+        PlaceOut r;
+        if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
+        else if (STRAT == STRAT_LBG3D) r = lbg3d_place(c, lane, e.x, e.y, bx, by, bz, e.h, e.sc);
+        else r = macs2d_place(c, lane, bx, bz, e.h, e.sc, e.hist, ems_keys, anomaly);
+        if (lane < cells) st.heightmap[(size_t)b * cells + lane] = e.h;
+        if (lane == 0) {
+            const size_t o = ((size_t)b * c.cap + e.sc.k) * dim;
+            if (dim == 2) {
+                *reinterpret_cast<int2 *>(st.blocks + o) = make_int2(bx, bz);
+                if (r.placed) *reinterpret_cast<int2 *>(st.positions + o) = make_int2(r.x, r.z);
+            } else {
+                st.blocks[o] = bx; st.blocks[o + 1] = by; st.blocks[o + 2] = bz;
+                if (r.placed) { st.positions[o] = r.x; st.positions[o + 1] = r.y; st.positions[o + 2] = r.z; }
+            }
+            st.stable[(size_t)b * c.cap + e.sc.k] = (unsigned char)r.stable;
+            // a stack above the container: the reference's voxel grid silently clips here and raises
+            // IndexError the next time it touches that column -- flagged instead
+            if (r.placed && r.top > c.H) anomaly |= 1;
+            st.scal[b] = make_int4(e.sc.valid, e.sc.empty, e.sc.nstable, e.sc.k + 1);
+        }
+    }
+    if (anomaly && lane == 0) st.flags[b] |= anomaly;
+    if (dec_dyn) {
+        if (STRAT == STRAT_LBG3D) encode_heightmap_3d(c, lane, e.x, e.y, e.h, dec_dyn + (size_t)b * c.enc_len);
+        else encode_heightmap_2d(c, lane, e.h, dec_dyn + (size_t)b * c.enc_len);
+    }
 }
 
 // ------------------------------------------------------------------------------------
 // K0 reset: Container.__init__ / clear_container + initial accessibility mask
 // ------------------------------------------------------------------------------------
-template <int VW, int CH>
-__global__ void reset_kernel(DevCfg c, StatePtrs st, const float *__restrict__ dynamic,
-                             float *__restrict__ cur_mask, float *__restrict__ mask, unsigned sv_magic) {
-    int lane; const int b = env_index(lane);
+template <bool FAST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+reset_kernel(DevCfg c, StatePtrs st, const float *__restrict__ dynamic, float *__restrict__ cur_mask,
+             float *__restrict__ mask) {
+    typedef Shape<0, 0, 0> SH;
+    int lane, warp; const int b = env_index(lane, warp);
     if (b >= c.B) return;
     const int cells = c.dim == 2 ? c.W : c.W * c.L;
     for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
-    for (int i = lane; i < c.n * c.dim; i += 32) { st.positions[(size_t)b * c.n * c.dim + i] = 0; st.blocks[(size_t)b * c.n * c.dim + i] = 0; }
-    for (int i = lane; i < c.n; i += 32) st.stable[(size_t)b * c.n + i] = 0;
+    for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
+    for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
     if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
     if (dynamic == nullptr) return;
-    const int SV = c.S / VW, total = c.dyn_rows * SV;
-    const float *din = dynamic + (size_t)b * c.dyn_rows * c.S;
-    BandBits bits; bits.clear();
-    DynTile<VW, CH> tile;
-    for (int base = 0; base < total; base += 32 * CH) {
-        tile.load(din, base, lane, total);
-        tile.process(c, sv_magic, SV, nullptr, base, lane, total, -1, bits);
-    }
-    bits.combine(c.S);
-    mask_pass(c, lane, nullptr, -1, bits.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
+    const BandBits bits = dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), nullptr, -1);
+    mask_pass<SH>(c, lane, false, 0.f, 0.f, -1, bits.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
 }
 
 // ------------------------------------------------------------------------------------
 // unfused pieces (signature parity with pack.update_dynamic / pack.update_mask / add_new_block)
 // ------------------------------------------------------------------------------------
-template <int VW, int CH>
-__global__ void update_dynamic_kernel(DevCfg c, const float *__restrict__ dynamic, const float *__restrict__ static_,
-                                      const int64_t *__restrict__ ptr, float *__restrict__ out, unsigned sv_magic) {
-    int lane; const int b = env_index(lane);
+template <bool FAST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+update_dynamic_kernel(DevCfg c, const float *__restrict__ dynamic, const float *__restrict__ static_,
+                      const int64_t *__restrict__ ptr, float *__restrict__ out) {
+    typedef Shape<0, 0, 0> SH;
+    int lane, warp; const int b = env_index(lane, warp);
     if (b >= c.B) return;
-    const int SV = c.S / VW, total = c.dyn_rows * SV;
-    const float *din = dynamic + (size_t)b * c.dyn_rows * c.S;
-    float *dout = out + (size_t)b * c.dyn_rows * c.S;
-    DynTile<VW, CH> tile;
-    tile.load(din, 0, lane, total);
-    const long long p = ptr[b];
-    const int real = (int)static_[(size_t)b * c.static_rows * c.S + p];    // pack.py:347 (.long() truncates)
-    BandBits bits; bits.clear();
-    tile.process(c, sv_magic, SV, dout, 0, lane, total, real, bits);
-    for (int base = 32 * CH; base < total; base += 32 * CH) {
-        tile.load(din, base, lane, total);
-        tile.process(c, sv_magic, SV, dout, base, lane, total, real, bits);
-    }
+    long long p = ptr[b];
+    if (p < 0 || p >= c.S) p = 0;                                          // the reference's index would raise
+    const int real = (int)env_ptr(static_, b, c.static_env)[p];            // pack.py:347 (.long() truncates)
+    dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), env_ptr(out, b, c.dyn_env), real);
 }
 
-template <int VW, int CH>
-__global__ void update_mask_kernel(DevCfg c, const float *__restrict__ mask, const float *__restrict__ dynamic,
-                                   const int64_t *__restrict__ ptr, float *__restrict__ new_mask,
-                                   float *__restrict__ chosen_mask, unsigned sv_magic) {
-    int lane; const int b = env_index(lane);
+template <bool FAST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+update_mask_kernel(DevCfg c, const float *__restrict__ mask, const float *__restrict__ dynamic,
+                   const int64_t *__restrict__ ptr, float *__restrict__ new_mask, float *__restrict__ chosen_mask) {
+    typedef Shape<0, 0, 0> SH;
+    int lane, warp; const int b = env_index(lane, warp);
     if (b >= c.B) return;
-    const int SV = c.S / VW, total = c.dyn_rows * SV;
-    const float *din = dynamic + (size_t)b * c.dyn_rows * c.S;
-    BandBits bits; bits.clear();
-    DynTile<VW, CH> tile;
-    for (int base = 0; base < total; base += 32 * CH) {
-        tile.load(din, base, lane, total);
-        tile.process(c, sv_magic, SV, nullptr, base, lane, total, -1, bits);
-    }
-    bits.combine(c.S);
-    const int realm = (int)(ptr[b] % c.n);                                 // pack.py:314-316
-    mask_pass(c, lane, mask + (size_t)b * c.S, realm, bits.blocked(), new_mask + (size_t)b * c.S,
-              chosen_mask + (size_t)b * c.S);
+    const float m0 = lane < c.S ? mask[(size_t)b * c.S + lane] : 0.f;
+    const float m1 = lane + 32 < c.S ? mask[(size_t)b * c.S + lane + 32] : 0.f;
+    long long p = ptr[b];
+    if (p < 0) p = 0;
+    const BandBits bits = dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), nullptr, -1);
+    const int realm = (int)(p % c.n);                                      // pack.py:314-316
+    mask_pass<SH>(c, lane, true, m0, m1, realm, bits.blocked(), new_mask + (size_t)b * c.S, chosen_mask + (size_t)b * c.S);
 }
 
-__global__ void add_blocks_lbg2d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks,
-                                        float *__restrict__ dec_dyn) {
-    int lane; const int b = env_index(lane);
+template <int STRAT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
     if (b >= c.B) return;
-    const int bx = (int)blocks[(size_t)b * 2], bz = (int)blocks[(size_t)b * 2 + 1];   // .astype(int) tools.py:3689
-    container_add_block_2d(c, st, b, lane, bx, bz, dec_dyn);
+    EnvRegs<STRAT> e; e.load(c, st, b, lane);
+    const float *blk = blocks + (size_t)b * c.dim;
+    const int bx = (int)blk[0];                                            // .astype(int) tools.py:3689
+    const int by = STRAT == STRAT_LBG3D ? (int)blk[1] : 1;
+    const int bz = (int)blk[c.dim - 1];
+    container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
 }
 
 // ------------------------------------------------------------------------------------
-// fused decode-step kernel, LB_GREEDY 2D  (K1 + K2)
+// fused decode-step kernel  (K1 + K2/K3/K4): update_dynamic + update_mask + gather + add_new_block
 // ------------------------------------------------------------------------------------
-template <int VW, int CH>
-__global__ void step_lbg2d_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr,
-                                  const float *__restrict__ static_, const float *__restrict__ dynamic_in,
-                                  const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
-                                  float *__restrict__ cur_mask_out, float *__restrict__ mask_out,
-                                  float *__restrict__ dec_static, float *__restrict__ dec_dyn, unsigned sv_magic) {
-    int lane; const int b = env_index(lane);
+template <int STRAT, bool FAST, int NT, int RT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, STRAT == STRAT_LBG2D ? 8 : 4)
+step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
+            const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
+            float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
+            float *__restrict__ dec_dyn) {
+    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    typedef Shape<NT, RT, DIM> SH;
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
     if (b >= c.B) return;
-    const int SV = c.S / VW, total = c.dyn_rows * SV;
-    const float *din = dynamic_in + (size_t)b * c.dyn_rows * c.S;
-    float *dout = dynamic_out + (size_t)b * c.dyn_rows * c.S;
+    const int S = SH::S(c);
+    const float *srow = env_ptr(static_, b, SH::static_env(c));
+    const float *din = env_ptr(dynamic_in, b, SH::dyn_env(c));
+    float *dout = env_ptr(dynamic_out, b, SH::dyn_env(c));
+    const float *min_ = env_ptr(mask_in, b, (unsigned)S);
 
-    // (1) put the precedence tensor in flight first; everything below up to (3) overlaps with it
-    DynTile<VW, CH> tile;
-    tile.load(din, 0, lane, total);
+    // (1) independent requests first: pointer, the block-id row of `static` (speculative: S floats, so that
+    //     `real` needs no second round trip), the masks and the environment state
+    const long long p64 = ptr[b];
+    const float id0 = lane < S ? srow[lane] : 0.f;
+    const float id1 = (S > 32 && lane + 32 < S) ? srow[lane + 32] : 0.f;
+    const float m0 = lane < S ? min_[lane] : 0.f;
+    const float m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
+    EnvRegs<STRAT> e; e.load(c, st, b, lane);
 
-    // (2) environment transition on the tiny state
-    const long long p = ptr[b];
-    const float *srow = static_ + (size_t)b * c.static_rows * c.S + p;
-    const int real = (int)srow[0];                                         // pack.py:347
-    const float fx = srow[(size_t)c.S], fz = srow[(size_t)2 * c.S];        // model.py:404-406
-    if (dec_static && lane < c.static_rows - 1) dec_static[(size_t)b * (c.static_rows - 1) + lane] = srow[(size_t)(1 + lane) * c.S];
-    const float mval0 = lane < c.S ? mask_in[(size_t)b * c.S + lane] : 0.f;   // early issue; re-read is avoided for S<=32
-    container_add_block_2d(c, st, b, lane, (int)fx, (int)fz, dec_dyn);
+    // (2) the chosen candidate: block id (pack.py:347) and edge lengths (model.py:404-406)
+    const bool badp = p64 < 0 || p64 >= S;           // the reference's gather would raise
+    const int p = badp ? 0 : (int)p64;
+    const int real = (int)__shfl_sync(TAPENV_FULL_MASK, (S > 32 && p >= 32) ? id1 : id0, p & 31);
+    float dimv = 0.f;
+    if (lane < DIM) dimv = srow[(1 + lane) * S + p];
+    if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
 
-    // (3) masked copy + column reductions
-    BandBits bits; bits.clear();
-    tile.process(c, sv_magic, SV, dout, 0, lane, total, real, bits);
-    for (int base = 32 * CH; base < total; base += 32 * CH) {
-        tile.load(din, base, lane, total);
-        tile.process(c, sv_magic, SV, dout, base, lane, total, real, bits);
-    }
-    bits.combine(c.S);
+    // (3) masked copy + column reductions of the precedence tensor
+    const BandBits bits = dynpass<SH, FAST>(c, lane, din, dout, real);
 
-    // (4) masks (pack.py:318-331)
-    const int realm = (int)(p % c.n);
-    const unsigned long long blocked = bits.blocked();
-    if (lane < c.S) {
-        float m = mval0;
-        if ((lane % c.n) == realm) m = 0.f;
-        mask_out[(size_t)b * c.S + lane] = m;
-        cur_mask_out[(size_t)b * c.S + lane] = ((blocked >> lane) & 1ull) ? 0.f : m;
-    }
-    for (int j = lane + 32; j < c.S; j += 32) {
-        float m = mask_in[(size_t)b * c.S + j];
-        if ((j % c.n) == realm) m = 0.f;
-        mask_out[(size_t)b * c.S + j] = m;
-        cur_mask_out[(size_t)b * c.S + j] = ((blocked >> j) & 1ull) ? 0.f : m;
-    }
+    // (4) masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
+    mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
+                  env_ptr(mask_out, b, (unsigned)S));
+
+    // (5) environment transition on the register-resident state
+    const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+    const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+    const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
+    container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -273,26 +318,24 @@ __global__ void reward_kernel(DevCfg c, StatePtrs st, float *__restrict__ reward
     if (b >= c.B) return;
     const int4 s = st.scal[b];
     const int cells = c.dim == 2 ? c.W : c.W * c.L;
-    double ratio;
-    if (s.w == 0) {                                // current_blocks_num == 0 -> C=P=S=0 (tools.py:3888-3889)
-        ratio = 0.0;
-        if (c.ratio_mode == TAPENV_RATIO_CP_HALF) ratio = 0.0 / 2; else ratio = 0.0 / 3;
-    } else {
+    double C = 0.0, P = 0.0, S = 0.0;              // current_blocks_num == 0 -> 0, 0, 0 (tools.py:3888-3889)
+    if (s.w != 0) {
         int height = 0;
         for (int i = 0; i < cells; ++i) height = max(height, st.heightmap[(size_t)b * cells + i]);
-        const double C = (double)s.x / (double)((long long)cells * height);
-        const double P = (double)s.x / (double)(s.y + s.x);
-        const double S = (double)s.z / (double)s.w;
-        switch (c.ratio_mode) {
-            case TAPENV_RATIO_C: ratio = C / 3; break;
-            case TAPENV_RATIO_CS: ratio = (C * S) / 3; break;
-            case TAPENV_RATIO_C_P: ratio = (C + P) / 3; break;
-            case TAPENV_RATIO_CP_S: ratio = ((C + P) * S) / 3; break;
-            case TAPENV_RATIO_2C_SUM: ratio = (2 * C + P + S) / 3; break;
-            case TAPENV_RATIO_CPS: ratio = (C * P * S) / 3; break;
-            case TAPENV_RATIO_CP_HALF: ratio = (C + P) / 2; break;
-            default: ratio = (C + P + S) / 3; break;
-        }
+        C = __ddiv_rn((double)s.x, (double)(cells * height));
+        P = __ddiv_rn((double)s.x, (double)(s.y + s.x));
+        S = __ddiv_rn((double)s.z, (double)s.w);
+    }
+    double ratio;
+    switch (c.ratio_mode) {
+        case TAPENV_RATIO_C: ratio = __ddiv_rn(C, 3.0); break;
+        case TAPENV_RATIO_CS: ratio = __ddiv_rn(__dmul_rn(C, S), 3.0); break;
+        case TAPENV_RATIO_C_P: ratio = __ddiv_rn(__dadd_rn(C, P), 3.0); break;
+        case TAPENV_RATIO_CP_S: ratio = __ddiv_rn(__dmul_rn(__dadd_rn(C, P), S), 3.0); break;
+        case TAPENV_RATIO_2C_SUM: ratio = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, C), P), S), 3.0); break;
+        case TAPENV_RATIO_CPS: ratio = __ddiv_rn(__dmul_rn(__dmul_rn(C, P), S), 3.0); break;
+        case TAPENV_RATIO_CP_HALF: ratio = __ddiv_rn(__dadd_rn(C, P), 2.0); break;
+        default: ratio = __ddiv_rn(__dadd_rn(__dadd_rn(C, P), S), 3.0); break;
     }
     reward[b] = (float)ratio;                      // scores[batch_index] = ... (model.py:510), fp32 tensor
 }
@@ -311,28 +354,11 @@ __global__ void reward_sums_kernel(int B, const float *__restrict__ reward, doub
     if (threadIdx.x == 0) { out[0] = s1[0]; out[1] = s2[0]; out[2] = (double)B; }
 }
 
-// ------------------------------------------------------------------------------------
-// launch helpers
-// ------------------------------------------------------------------------------------
-struct VecPlan { int vw; unsigned sv_magic; };
-
-static VecPlan plan_vec(const DevCfg &d, const void *a, const void *b) {
-    VecPlan p;
+// fast path needs 128-bit rows and 16-byte aligned tensors
+static bool fast_ok(const DevCfg &d, const void *a, const void *b) {
     const uintptr_t al = (uintptr_t)a | (uintptr_t)b;
-    if (d.S % 4 == 0 && al % 16 == 0) p.vw = 4;
-    else if (d.S % 2 == 0 && al % 8 == 0) p.vw = 2;
-    else p.vw = 1;
-    const unsigned SV = (unsigned)(d.S / p.vw);
-    p.sv_magic = (unsigned)((0x100000000ull + SV - 1) / SV);
-    return p;
+    return d.S % 4 == 0 && d.S >= 4 && al % 16 == 0;
 }
-
-#define TAPENV_DISPATCH_VW(plan, KERNEL, grid, block, stream, ...)                                   \
-    do {                                                                                             \
-        if ((plan).vw == 4) KERNEL<4, 5><<<grid, block, 0, stream>>>(__VA_ARGS__, (plan).sv_magic);   \
-        else if ((plan).vw == 2) KERNEL<2, 5><<<grid, block, 0, stream>>>(__VA_ARGS__, (plan).sv_magic); \
-        else KERNEL<1, 5><<<grid, block, 0, stream>>>(__VA_ARGS__, (plan).sv_magic);                  \
-    } while (0)
 
 }  // namespace tapenv
 
@@ -364,8 +390,6 @@ void tapenv_get_limits(tapenv_limits *out) {
     out->max_candidates = kMaxCandidates; out->max_blocks = kMaxBlocks;
 }
 
-void tapenv_set_envs_per_cta(int epc) { g_envs_per_cta = (epc == 1 || epc == 2 || epc == 4 || epc == 8) ? epc : 0; }
-
 static bool str_ends(const char *s, const char *suf) {
     const size_t a = strlen(s), b = strlen(suf);
     return a >= b && strcmp(s + a - b, suf) == 0;
@@ -381,7 +405,7 @@ int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, in
     if (!cfg || !container_size || !reward_type || !packing_strategy || !heightmap_type || !input_type) return TAPENV_EINVAL;
     if (dim != 2 && dim != 3) return TAPENV_EINVAL;
     memset(cfg, 0, sizeof(*cfg));
-    cfg->batch = batch; cfg->blocks_num = blocks_num; cfg->dim = dim;
+    cfg->batch = batch; cfg->blocks_num = blocks_num; cfg->dim = dim; cfg->capacity = blocks_num;
     cfg->rotate_types = allow_rot ? (dim == 2 ? 2 : 6) : 1;              // pack.py:306-309 (dim!)
     cfg->width = container_size[0];
     cfg->length = dim == 3 ? container_size[1] : 1;
@@ -432,7 +456,9 @@ int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, in
     } else if (!strcmp(input_type, "mul") || !strcmp(input_type, "mul-with") || !strcmp(input_type, "rot-old")) {
         return TAPENV_EUNSUPPORTED;   // two-container inputs / legacy layout: out of scope
     } else return TAPENV_EENUM;
-    return check_cfg(cfg);
+    const int rc = check_cfg(cfg);
+    if (rc != TAPENV_OK) return rc;
+    return strategy_kernel(cfg) < 0 ? TAPENV_EUNSUPPORTED : TAPENV_OK;
 }
 
 int tapenv_config_check(const tapenv_config *cfg) { return check_cfg(cfg); }
@@ -459,48 +485,52 @@ int32_t tapenv_encoded_heightmap_len(const tapenv_config *cfg) {
 #define TAPENV_PROLOGUE(cfg)                         \
     int rc_ = check_cfg(cfg);                        \
     if (rc_ != TAPENV_OK) return rc_;                \
-    if ((cfg)->batch == 0) return TAPENV_OK;         \
     const DevCfg d = devcfg_of(cfg);                 \
-    const int epc = pick_epc(d.B);                   \
-    const dim3 block(32 * epc), grid((d.B + epc - 1) / epc); \
+    const dim3 block(32 * kWarpsPerCta), grid((d.B + kWarpsPerCta - 1) / kWarpsPerCta); \
     cudaStream_t s = (cudaStream_t)stream;
 
 int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic, float *cur_mask_out, float *mask_out,
                  void *stream) {
     TAPENV_PROLOGUE(cfg)
+    if (d.B == 0) return TAPENV_OK;
     if (!state) return TAPENV_EINVAL;
     if (dynamic && !cur_mask_out) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    const VecPlan plan = plan_vec(d, dynamic, nullptr);
-    TAPENV_DISPATCH_VW(plan, reset_kernel, grid, block, s, d, st, dynamic, cur_mask_out, mask_out);
+    if (fast_ok(d, dynamic, nullptr)) reset_kernel<true><<<grid, block, 0, s>>>(d, st, dynamic, cur_mask_out, mask_out);
+    else reset_kernel<false><<<grid, block, 0, s>>>(d, st, dynamic, cur_mask_out, mask_out);
     return launch_status();
 }
 
 int tapenv_update_dynamic(const tapenv_config *cfg, const float *dynamic, const float *static_, const int64_t *ptr,
                           float *dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
+    if (d.B == 0) return TAPENV_OK;
     if (!dynamic || !static_ || !ptr || !dynamic_out) return TAPENV_EINVAL;
-    const VecPlan plan = plan_vec(d, dynamic, dynamic_out);
-    TAPENV_DISPATCH_VW(plan, update_dynamic_kernel, grid, block, s, d, dynamic, static_, ptr, dynamic_out);
+    if (fast_ok(d, dynamic, dynamic_out)) update_dynamic_kernel<true><<<grid, block, 0, s>>>(d, dynamic, static_, ptr, dynamic_out);
+    else update_dynamic_kernel<false><<<grid, block, 0, s>>>(d, dynamic, static_, ptr, dynamic_out);
     return launch_status();
 }
 
 int tapenv_update_mask(const tapenv_config *cfg, const float *mask, const float *dynamic, const int64_t *ptr,
                        float *new_mask_out, float *chosen_mask_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
+    if (d.B == 0) return TAPENV_OK;
     if (!mask || !dynamic || !ptr || !new_mask_out || !chosen_mask_out) return TAPENV_EINVAL;
-    const VecPlan plan = plan_vec(d, dynamic, nullptr);
-    TAPENV_DISPATCH_VW(plan, update_mask_kernel, grid, block, s, d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
+    if (fast_ok(d, dynamic, nullptr)) update_mask_kernel<true><<<grid, block, 0, s>>>(d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
+    else update_mask_kernel<false><<<grid, block, 0, s>>>(d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
     return launch_status();
 }
 
 int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
-    rc_ = check_strategy_built(cfg);
-    if (rc_ != TAPENV_OK) return rc_;
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (d.B == 0) return TAPENV_OK;
     if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    add_blocks_lbg2d_kernel<<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
+    if (strat == STRAT_LBG2D) add_blocks_kernel<STRAT_LBG2D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
+    else if (strat == STRAT_LBG3D) add_blocks_kernel<STRAT_LBG3D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
+    else add_blocks_kernel<STRAT_MACS2D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
     return launch_status();
 }
 
@@ -508,14 +538,31 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
                 const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
                 float *mask_out, float *dec_static_out, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (d.B == 0) return TAPENV_OK;
     if (!state || !ptr || !static_ || !dynamic_in || !mask_in || !dynamic_out || !cur_mask_out || !mask_out)
         return TAPENV_EINVAL;
-    rc_ = check_strategy_built(cfg);
-    if (rc_ != TAPENV_OK) return rc_;
     const StatePtrs st = stateptrs_of(cfg, state);
-    const VecPlan plan = plan_vec(d, dynamic_in, dynamic_out);
-    TAPENV_DISPATCH_VW(plan, step_lbg2d_kernel, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in, dynamic_out,
-                       cur_mask_out, mask_out, dec_static_out, dec_dynamic_out);
+    const bool fast = fast_ok(d, dynamic_in, dynamic_out);
+#define TAPENV_STEP_ARGS d, st, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out, dec_dynamic_out
+    // shapes with a fully unrolled instantiation ('bot'-like inputs: 3 bands, all updated); anything else runs generic
+    const bool bot = d.dyn_rows == 3 * d.n && d.update_time == 3 && d.static_rows == 1 + d.dim;
+    if (strat == STRAT_LBG2D) {
+        if (fast && bot && d.n == 10 && d.R == 2) step_kernel<STRAT_LBG2D, true, 10, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else if (fast && bot && d.n == 20 && d.R == 2) step_kernel<STRAT_LBG2D, true, 20, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else if (fast) step_kernel<STRAT_LBG2D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else step_kernel<STRAT_LBG2D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+    } else if (strat == STRAT_LBG3D) {
+        if (fast && bot && d.n == 10 && d.R == 6) step_kernel<STRAT_LBG3D, true, 10, 6><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else if (fast) step_kernel<STRAT_LBG3D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else step_kernel<STRAT_LBG3D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+    } else {
+        if (fast && bot && d.n == 20 && d.R == 2) step_kernel<STRAT_MACS2D, true, 20, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else if (fast && bot && d.n == 10 && d.R == 2) step_kernel<STRAT_MACS2D, true, 10, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else if (fast) step_kernel<STRAT_MACS2D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        else step_kernel<STRAT_MACS2D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+    }
     return launch_status();
 }
 

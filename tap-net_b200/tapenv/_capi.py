@@ -14,7 +14,7 @@ c_void_p, c_int, c_int32, c_size_t, c_char_p = C.c_void_p, C.c_int, C.c_int32, C
 class Config(C.Structure):  # struct tapenv_config
     _fields_ = [(n, c_int32) for n in (
         "batch", "blocks_num", "dim", "rotate_types", "width", "length", "height", "strategy",
-        "heightmap_type", "reward_flags", "ratio_mode", "static_rows", "dyn_rows", "update_time")]
+        "heightmap_type", "reward_flags", "ratio_mode", "static_rows", "dyn_rows", "update_time", "capacity")]
 
 
 class StateLayout(C.Structure):  # struct tapenv_state_layout
@@ -48,7 +48,6 @@ SYMBOLS = {
     "tapenv_step": (c_int, [CFG, P, P, P, P, P, P, P, P, P, P, P]),
     "tapenv_reward": (c_int, [CFG, P, P, P, P]),
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
-    "tapenv_set_envs_per_cta": (None, [c_int]),
 }
 
 
