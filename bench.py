@@ -64,7 +64,7 @@ def load_workload(name, batch, rank):
 # clocks (B200_PROFILING.md: sample DURING the timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.002):
         threading.Thread.__init__(self, daemon=True)
         self.period = period
         self.samples = []
@@ -236,8 +236,8 @@ def run_ours(args):
         r = runners[i % RING]
         r.run()
         if world > 1:
-            # end-of-episode reward all-reduce feeding the critic baseline statistics (trainer.py:216-225)
-            dist.all_reduce(r.sums)
+            # end-of-episode reduction of the reward statistics feeding the critic baseline (trainer.py:216-225)
+            r.total = tapenv.dist.combine_partial_sums(r.sums)
         return r
 
     def barrier():
@@ -301,33 +301,30 @@ def run_ours(args):
             cnt += nl
     step_us = 1e3 * tot_ms / cnt
     achieved = B * bytes_step / (step_us * 1e-6) / 1e9
-    clocks = sampler.result()
 
-    # ---- timed region 3: e2e -- host buffers in, host reward out, through the public Python API -------
+    # ---- timed region 3: e2e -- host buffers in, host rewards out, through the public Python API --------
+    # tapenv.HostPipeline: per episode one H2D upload of (static, dynamic, ptr_seq) from pinned memory on a copy
+    # stream (double-buffered, overlapping the previous episode's kernels), the episode, D2H of rewards + sums.
     st_pin = torch.from_numpy(static_h).pin_memory()
     dy_pin = torch.from_numpy(dynamic_h).pin_memory()
     pq_pin = ptr_seq0.cpu().pin_memory()
-    rw_pin = torch.empty(B, dtype=torch.float32).pin_memory()
-    st_d, dy_d, pq_d = torch.empty_like(st0), torch.empty_like(dyn0), torch.empty_like(ptr_seq0)
-    e2e_runner = tapenv.EpisodeRunner(env, st_d, dy_d, pq_d, use_graph=not args.no_graph, partial_sums=True)
+    pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph)
+    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if world > 1 else None
 
-    def e2e_episode():
-        st_d.copy_(st_pin, non_blocking=True)
-        dy_d.copy_(dy_pin, non_blocking=True)
-        pq_d.copy_(pq_pin, non_blocking=True)
-        r = e2e_runner.run()
-        if world > 1:
-            dist.all_reduce(e2e_runner.sums)
-        rw_pin.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller consumes the rewards on the host
-        return rw_pin
+    def e2e_run(k):
+        last = None
+        for i in range(k):
+            if pipe.inflight == pipe.depth:
+                last = pipe.result()
+            pipe.submit(st_pin, dy_pin, pq_pin, after_episode=after)
+        while pipe.inflight:
+            last = pipe.result()
+        return last
 
-    for _ in range(3):
-        e2e_episode()
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_episode()
+    rw_pin, sums_pin = e2e_run(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -335,6 +332,25 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * n * args.steps / float(te.item())
     assert np.array_equal(rw_pin.numpy(), reward_ref.cpu().numpy())
+
+    clocks = sampler.result()
+
+    # ---- extra: the whole-episode kernel (K7, tapenv_episode): one launch per episode, no intermediate tensors ----
+    k7 = None
+    try:
+        for _ in range(3):
+            rk = env.episode(st0, dyn0, ptr_seq0)[0]
+        assert torch.equal(rk, reward_ref)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            env.episode(runners[_ % RING].static, runners[_ % RING].dynamic, runners[_ % RING].ptr_seq)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        k7 = {"value": B * n * 20 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "ms_per_episode": e0.elapsed_time(e1) / 20,
+              "note": "tapenv_episode: reset + n steps + reward in ONE launch per batch (per GPU), inputs in HBM"}
+    except tapenv.TapEnvError:
+        pass
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
     cpu = None
@@ -370,9 +386,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "device_ms_sum_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(static_h.nbytes + dynamic_h.nbytes + pq_pin.numel() * 8),
-                    "d2h_bytes_per_step": int(B * 4), "ms_per_step": 1e3 * float(te.item()) / args.steps,
-                    "api": "tapenv.EpisodeRunner.run (BatchedContainers.reset/step/calc_ratio), pinned host buffers"},
+                    "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
+                    "api": "tapenv.HostPipeline.submit/result (double-buffered upload + BatchedContainers.reset/step/calc_ratio), pinned host buffers"},
+            "episode_kernel": k7,
             "roofline": {"bound": "hbm", "kernel": "step (fused update_dynamic+update_mask+add_new_block)",
                          "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",

@@ -32,50 +32,66 @@ struct BandBits {   // warp-uniform after combine(): bit j = column j has a non-
 __device__ __forceinline__ unsigned nz_bits(unsigned w) { return (w & 0x7fffffffu) != 0u ? 1u : 0u; }   // -0.0 == 0
 
 // CHP = passes per chunk: all loads of a chunk (CHP * 3 vectors per lane) are issued before the first use.
+// load() and process() are separate so that a kernel can put chunk 0 in flight BEFORE it waits for the
+// pointer / block id it needs to process it.
 template <class SH, int CHP>
 struct DynPassFast {
     uint4 acc[3];
-    int rsub, cv, off0;
+    uint4 v[CHP][3];
+    int rsub, cv;
     bool lane_on;
 
     __device__ __forceinline__ void init(const DevCfg &c, int lane) {
         acc[0] = acc[1] = acc[2] = make_uint4(0u, 0u, 0u, 0u);
         rsub = SH::div_SV(c, lane);
-        cv = lane - rsub * SH::SV(c);
+        cv = lane - rsub * SH::SV(c);              // vector index of (band 0, pass 0) for this lane == lane
         lane_on = rsub < SH::RP(c);
-        off0 = lane;                                   // rsub*SV + cv
+    }
+
+    __device__ __forceinline__ bool on(const DevCfg &c, int p) const {
+        return lane_on && p * SH::RP(c) + rsub < SH::n(c) && p < SH::PB(c);
+    }
+
+    __device__ __forceinline__ void load(const DevCfg &c, const float *din, int lane, int p0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(din) + lane;
+        const int pstride = SH::RP(c) * SH::SV(c), bstride = SH::n(c) * SH::SV(c), nb = SH::nbands(c);
+#pragma unroll
+        for (int i = 0; i < CHP; ++i) {
+            const bool o = on(c, p0 + i);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                v[i][b] = make_uint4(0u, 0u, 0u, 0u);
+                if (o && b < nb) v[i][b] = ldg_stream4(src + (p0 + i) * pstride + b * bstride);
+            }
+        }
     }
 
     // real < 0: no row is zeroed.  dout == nullptr: no copy is written.
-    __device__ __forceinline__ void run(const DevCfg &c, const float *din, float *dout, int real) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(din);
-        uint4 *dst = reinterpret_cast<uint4 *>(dout);
-        const int n = SH::n(c), RP = SH::RP(c), PB = SH::PB(c), nb = SH::nbands(c), ut = SH::update_time(c);
-        const int pstride = RP * SH::SV(c), bstride = n * SH::SV(c);
+    __device__ __forceinline__ void process(const DevCfg &c, float *dout, int lane, int p0, int real) {
+        uint4 *dst = reinterpret_cast<uint4 *>(dout) + lane;
+        const int RP = SH::RP(c), nb = SH::nbands(c), ut = SH::update_time(c);
+        const int pstride = RP * SH::SV(c), bstride = SH::n(c) * SH::SV(c);
         const int zrow = real - rsub;                        // pass p zeroes this lane's row iff p*RP == zrow
 #pragma unroll
-        for (int p0 = 0; p0 < PB; p0 += CHP) {
-            uint4 v[CHP][3];
+        for (int i = 0; i < CHP; ++i) {
+            const bool o = on(c, p0 + i);
+            const bool zero = (p0 + i) * RP == zrow && real >= 0;
 #pragma unroll
-            for (int i = 0; i < CHP; ++i) {
-                const bool on = lane_on && (p0 + i) * RP + rsub < n && (p0 + i) < PB;
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    v[i][b] = make_uint4(0u, 0u, 0u, 0u);
-                    if (on && b < nb) v[i][b] = ldg_stream4(src + off0 + (p0 + i) * pstride + b * bstride);
-                }
+            for (int b = 0; b < 3; ++b) {
+                if (zero && b < ut) v[i][b] = make_uint4(0u, 0u, 0u, 0u);
+                acc[b].x |= v[i][b].x; acc[b].y |= v[i][b].y; acc[b].z |= v[i][b].z; acc[b].w |= v[i][b].w;
+                if (dout && o && b < nb) stg_stream4(dst + (p0 + i) * pstride + b * bstride, v[i][b]);
             }
+        }
+    }
+
+    // chunk 0 must already be loaded
+    __device__ __forceinline__ void finish(const DevCfg &c, const float *din, float *dout, int lane, int real) {
+        process(c, dout, lane, 0, real);
 #pragma unroll
-            for (int i = 0; i < CHP; ++i) {
-                const bool on = lane_on && (p0 + i) * RP + rsub < n && (p0 + i) < PB;
-                const bool zero = (p0 + i) * RP == zrow && real >= 0;
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    if (zero && b < ut) v[i][b] = make_uint4(0u, 0u, 0u, 0u);
-                    acc[b].x |= v[i][b].x; acc[b].y |= v[i][b].y; acc[b].z |= v[i][b].z; acc[b].w |= v[i][b].w;
-                    if (dst && on && b < nb) stg_stream4(dst + off0 + (p0 + i) * pstride + b * bstride, v[i][b]);
-                }
-            }
+        for (int p0 = CHP; p0 < SH::PB(c); p0 += CHP) {
+            load(c, din, lane, p0);
+            process(c, dout, lane, p0, real);
         }
     }
 
@@ -127,7 +143,8 @@ __device__ __forceinline__ BandBits dynpass(const DevCfg &c, int lane, const flo
     if (FAST) {
         DynPassFast<SH, 2> pass;
         pass.init(c, lane);
-        pass.run(c, din, dout, real);
+        pass.load(c, din, lane, 0);
+        pass.finish(c, din, dout, lane, real);
         return pass.combine(c);
     }
     return dynpass_scalar(c, lane, din, dout, real);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/tapenv.h"
 #include "tapenv_common.cuh"
@@ -109,6 +110,32 @@ static int strategy_kernel(const tapenv_config *c) {
 
 static int launch_status() { return cudaGetLastError() == cudaSuccess ? TAPENV_OK : TAPENV_ECUDA; }
 
+// Programmatic dependent launch: every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, waits for its predecessor's memory with
+// griddepcontrol.wait before its first global access and only then lets ITS dependent start launching, so the
+// launch latency and CTA ramp of decode step t+1 overlap the tail of step t (at most one grid is ever parked).
+// TAPENV_PDL=0 in the environment turns the attribute off (plain stream order).
+static bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("TAPENV_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void grid_dependency_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------
 // device: per-environment pieces
 // ------------------------------------------------------------------------------------
@@ -202,6 +229,7 @@ reset_kernel(DevCfg c, StatePtrs st, const float *__restrict__ dynamic, float *_
              float *__restrict__ mask) {
     typedef Shape<0, 0, 0> SH;
     int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
     if (b >= c.B) return;
     const int cells = c.dim == 2 ? c.W : c.W * c.L;
     for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
@@ -222,6 +250,7 @@ update_dynamic_kernel(DevCfg c, const float *__restrict__ dynamic, const float *
                       const int64_t *__restrict__ ptr, float *__restrict__ out) {
     typedef Shape<0, 0, 0> SH;
     int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
     if (b >= c.B) return;
     long long p = ptr[b];
     if (p < 0 || p >= c.S) p = 0;                                          // the reference's index would raise
@@ -235,6 +264,7 @@ update_mask_kernel(DevCfg c, const float *__restrict__ mask, const float *__rest
                    const int64_t *__restrict__ ptr, float *__restrict__ new_mask, float *__restrict__ chosen_mask) {
     typedef Shape<0, 0, 0> SH;
     int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
     if (b >= c.B) return;
     const float m0 = lane < c.S ? mask[(size_t)b * c.S + lane] : 0.f;
     const float m1 = lane + 32 < c.S ? mask[(size_t)b * c.S + lane + 32] : 0.f;
@@ -250,6 +280,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta)
 add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
     __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
     int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
     if (b >= c.B) return;
     EnvRegs<STRAT> e; e.load(c, st, b, lane);
     const float *blk = blocks + (size_t)b * c.dim;
@@ -272,6 +303,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     typedef Shape<NT, RT, DIM> SH;
     __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
     int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
     if (b >= c.B) return;
     const int S = SH::S(c);
     const float *srow = env_ptr(static_, b, SH::static_env(c));
@@ -287,6 +319,8 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     const float m0 = lane < S ? min_[lane] : 0.f;
     const float m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
     EnvRegs<STRAT> e; e.load(c, st, b, lane);
+    DynPassFast<SH, 2> pass;
+    if (FAST) { pass.init(c, lane); pass.load(c, din, lane, 0); }   // first chunk of the precedence tensor in flight
 
     // (2) the chosen candidate: block id (pack.py:347) and edge lengths (model.py:404-406)
     const bool badp = p64 < 0 || p64 >= S;           // the reference's gather would raise
@@ -297,7 +331,9 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
 
     // (3) masked copy + column reductions of the precedence tensor
-    const BandBits bits = dynpass<SH, FAST>(c, lane, din, dout, real);
+    BandBits bits;
+    if (FAST) { pass.finish(c, din, dout, lane, real); bits = pass.combine(c); }
+    else bits = dynpass_scalar(c, lane, din, dout, real);
 
     // (4) masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
     mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
@@ -313,36 +349,157 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
 // ------------------------------------------------------------------------------------
 // K6 reward: Container.calc_CPS / calc_ratio (tools.py:3887-3966), one thread per env
 // ------------------------------------------------------------------------------------
+// Container.calc_CPS + calc_ratio (tools.py:3887-3966) in IEEE fp64, operation for operation
+__device__ __forceinline__ double calc_ratio_dev(const DevCfg &c, int valid, int empty, int nstable, int k, int height) {
+    const int cells = c.dim == 2 ? c.W : c.W * c.L;
+    double C = 0.0, P = 0.0, S = 0.0;              // current_blocks_num == 0 -> 0, 0, 0 (tools.py:3888-3889)
+    if (k != 0) {
+        C = __ddiv_rn((double)valid, (double)(cells * height));
+        P = __ddiv_rn((double)valid, (double)(empty + valid));
+        S = __ddiv_rn((double)nstable, (double)k);
+    }
+    switch (c.ratio_mode) {
+        case TAPENV_RATIO_C: return __ddiv_rn(C, 3.0);
+        case TAPENV_RATIO_CS: return __ddiv_rn(__dmul_rn(C, S), 3.0);
+        case TAPENV_RATIO_C_P: return __ddiv_rn(__dadd_rn(C, P), 3.0);
+        case TAPENV_RATIO_CP_S: return __ddiv_rn(__dmul_rn(__dadd_rn(C, P), S), 3.0);
+        case TAPENV_RATIO_2C_SUM: return __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, C), P), S), 3.0);
+        case TAPENV_RATIO_CPS: return __ddiv_rn(__dmul_rn(__dmul_rn(C, P), S), 3.0);
+        case TAPENV_RATIO_CP_HALF: return __ddiv_rn(__dadd_rn(C, P), 2.0);
+        default: return __ddiv_rn(__dadd_rn(__dadd_rn(C, P), S), 3.0);
+    }
+}
+
 __global__ void reward_kernel(DevCfg c, StatePtrs st, float *__restrict__ reward) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
     if (b >= c.B) return;
     const int4 s = st.scal[b];
     const int cells = c.dim == 2 ? c.W : c.W * c.L;
-    double C = 0.0, P = 0.0, S = 0.0;              // current_blocks_num == 0 -> 0, 0, 0 (tools.py:3888-3889)
-    if (s.w != 0) {
-        int height = 0;
-        for (int i = 0; i < cells; ++i) height = max(height, st.heightmap[(size_t)b * cells + i]);
-        C = __ddiv_rn((double)s.x, (double)(cells * height));
-        P = __ddiv_rn((double)s.x, (double)(s.y + s.x));
-        S = __ddiv_rn((double)s.z, (double)s.w);
+    int height = 0;
+    for (int i = 0; i < cells; ++i) height = max(height, st.heightmap[(size_t)b * cells + i]);
+    reward[b] = (float)calc_ratio_dev(c, s.x, s.y, s.z, s.w, height);   // scores[batch_index] = ... (model.py:510), fp32 tensor
+}
+
+// ------------------------------------------------------------------------------------
+// K7 whole-episode kernel: reset + `steps` decode steps + reward in ONE launch, for a known pointer
+// sequence.  The precedence tensor is read ONCE and kept as bit rows in shared memory (one 64-bit word per
+// band and block row); no intermediate `dynamic` / mask tensor is materialised.
+// (tools.calc_positions_lb_greedy :2393, calc_positions_mcs :3213 and pack.reward pack.py:378 are this loop
+// on the host, one environment at a time.)
+// ------------------------------------------------------------------------------------
+template <int STRAT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const float *__restrict__ dynamic,
+               const int64_t *__restrict__ ptr_seq, int steps, float *__restrict__ reward,
+               float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_dyn) {
+    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    __shared__ unsigned rows[kWarpsPerCta][3][kMaxBlocks][2];          // bit j of (band, row): dynamic[band*n+row][j] != 0
+    __shared__ float stat[kWarpsPerCta][1 + DIM][kMaxCandidates];
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const int S = c.S, n = c.n;
+    const float *din = env_ptr(dynamic, b, c.dyn_env);
+    const float *srow = env_ptr(static_, b, c.static_env);
+
+    // ---- stage the inputs ----
+    for (int i = lane; i < 3 * kMaxBlocks * 2; i += 32) (&rows[warp][0][0][0])[i] = 0u;
+    for (int i = lane; i < (1 + DIM) * S; i += 32) stat[warp][i / S][i % S] = srow[i];
+    __syncwarp();
+    if (c.SV * 4 == S && ((uintptr_t)din & 15) == 0) {               // 128-bit sweep, lane = (row-in-pass, column group)
+        const int rsub = (int)(((unsigned)lane * c.inv_SV) >> 16), cv = lane - rsub * c.SV;
+        const uint4 *src = reinterpret_cast<const uint4 *>(din);
+        if (rsub < c.RP) {
+            for (int row = rsub; row < c.dyn_rows; row += c.RP) {
+                const uint4 v = ldg_stream4(src + row * c.SV + cv);
+                const unsigned nib = nz_bits(v.x) | (nz_bits(v.y) << 1) | (nz_bits(v.z) << 2) | (nz_bits(v.w) << 3);
+                const int band = row / n, rin = row - band * n;
+                if (nib && band < 3) atomicOr(&rows[warp][band][rin][(cv * 4) >> 5], nib << ((cv * 4) & 31));
+            }
+        }
+    } else {
+        for (int q = lane; q < c.dyn_rows * S; q += 32) {
+            const int row = q / S, col = q - row * S;
+            const int band = row / n, rin = row - band * n;
+            if (nz_bits(__float_as_uint(__ldg(din + q))) && band < 3) atomicOr(&rows[warp][band][rin][col >> 5], 1u << (col & 31));
+        }
     }
-    double ratio;
-    switch (c.ratio_mode) {
-        case TAPENV_RATIO_C: ratio = __ddiv_rn(C, 3.0); break;
-        case TAPENV_RATIO_CS: ratio = __ddiv_rn(__dmul_rn(C, S), 3.0); break;
-        case TAPENV_RATIO_C_P: ratio = __ddiv_rn(__dadd_rn(C, P), 3.0); break;
-        case TAPENV_RATIO_CP_S: ratio = __ddiv_rn(__dmul_rn(__dadd_rn(C, P), S), 3.0); break;
-        case TAPENV_RATIO_2C_SUM: ratio = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, C), P), S), 3.0); break;
-        case TAPENV_RATIO_CPS: ratio = __ddiv_rn(__dmul_rn(__dmul_rn(C, P), S), 3.0); break;
-        case TAPENV_RATIO_CP_HALF: ratio = __ddiv_rn(__dadd_rn(C, P), 2.0); break;
-        default: ratio = __ddiv_rn(__dadd_rn(__dadd_rn(C, P), S), 3.0); break;
+    // pointer sequence: lane t (and t+32) keeps the pointer of step t
+    long long pq[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) if (lane + 32 * s < steps) pq[s] = ptr_seq[(size_t)(lane + 32 * s) * c.B + b];
+    __syncwarp();
+
+    // ---- reset (Container.__init__, tools.py:3611-3661) ----
+    const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
+    for (int i = lane; i < c.cap * DIM; i += 32) { st.positions[(size_t)b * c.cap * DIM + i] = 0; st.blocks[(size_t)b * c.cap * DIM + i] = 0; }
+    for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
+    if (lane == 0) st.flags[b] = 0;
+    EnvRegs<STRAT> e;
+    e.h = 0; e.sc.valid = e.sc.empty = e.sc.nstable = e.sc.k = 0;
+    e.x = 0; e.y = 0;
+    if (STRAT == STRAT_LBG3D) { e.x = (int)(((unsigned)lane * c.inv_L) >> 16); e.y = lane - e.x * c.L; }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) e.hist.x[s] = e.hist.z[s] = e.hist.xx[s] = e.hist.zz[s] = 0;
+    if (lane < cells) st.heightmap[(size_t)b * cells + lane] = 0;
+    if (lane == 0) st.scal[b] = make_int4(0, 0, 0, 0);
+
+    unsigned long long mask = S >= 64 ? ~0ull : ((1ull << S) - 1ull);      // model.py:297: ones
+    for (int t = 0; t < steps; ++t) {
+        const long long p64 = __shfl_sync(TAPENV_FULL_MASK, t < 32 ? pq[0] : pq[1], t & 31);
+        const bool badp = p64 < 0 || p64 >= S;
+        const int p = badp ? 0 : (int)p64;
+        const int real = (int)stat[warp][0][p];                             // pack.py:347
+        const int realm = p - (int)(((unsigned)p * c.inv_n) >> 16) * n;     // pack.py:314-316
+        const int bx = (int)stat[warp][1][p];
+        const int by = STRAT == STRAT_LBG3D ? (int)stat[warp][2][p] : 1;
+        const int bz = (int)stat[warp][DIM][p];
+        __syncwarp();
+        if (lane < 3 * 2 && real >= 0 && real < n && (lane >> 1) < c.update_time) rows[warp][lane >> 1][real][lane & 1] = 0u;   // pack.py:370-374
+        for (int r = 0; r < c.R; ++r) mask &= ~(1ull << (realm + n * r));   // pack.py:318-321
+        __syncwarp();
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, t == steps - 1 ? dec_dyn : nullptr,
+                                   ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+        if (e.sc.k < c.cap) e.sc.k += 1;
+        if (STRAT == STRAT_MACS2D) {                                        // refresh the history registers
+            __syncwarp();
+            e.load(c, st, b, lane);
+        }
     }
-    reward[b] = (float)ratio;                      // scores[batch_index] = ... (model.py:510), fp32 tensor
+    // ---- outputs ----
+    // accessibility from the remaining bit rows (pack.py:324-329; model.py:297-307 when steps == 0)
+    __syncwarp();
+    unsigned w[3][2];
+#pragma unroll
+    for (int bd = 0; bd < 3; ++bd) {
+        unsigned lo = 0u, hi = 0u;
+        for (int i = lane; i < n; i += 32) { lo |= rows[warp][bd][i][0]; hi |= rows[warp][bd][i][1]; }
+        w[bd][0] = warp_or(lo); w[bd][1] = S > 32 ? warp_or(hi) : 0u;
+    }
+    const unsigned long long mv = ((unsigned long long)w[0][1] << 32) | w[0][0];
+    const unsigned long long sm = ((unsigned long long)w[1][1] << 32) | w[1][0];
+    const unsigned long long lg = ((unsigned long long)w[2][1] << 32) | w[2][0];
+    const unsigned long long cur = mask & ~(mv | (sm & lg));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = lane + 32 * half;
+        if (j < S) {
+            if (mask_out) mask_out[(size_t)b * S + j] = (float)((mask >> j) & 1ull);
+            if (cur_mask_out) cur_mask_out[(size_t)b * S + j] = (float)((cur >> j) & 1ull);
+        }
+    }
+    if (reward) {
+        const int height = warp_max(lane < cells ? e.h : 0);
+        if (lane == 0) reward[b] = (float)calc_ratio_dev(c, e.sc.valid, e.sc.empty, e.sc.nstable, e.sc.k, height);
+    }
 }
 
 // deterministic (fixed-order) reduction of (sum r, sum r^2, B) in fp64, single CTA
 __global__ void reward_sums_kernel(int B, const float *__restrict__ reward, double *__restrict__ out) {
     __shared__ double s1[1024], s2[1024];
+    grid_dependency_sync();
     double a = 0.0, q = 0.0;
     for (int i = threadIdx.x; i < B; i += blockDim.x) { const double r = (double)reward[i]; a += r; q += r * r; }
     s1[threadIdx.x] = a; s2[threadIdx.x] = q;
@@ -496,8 +653,8 @@ int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic, fl
     if (!state) return TAPENV_EINVAL;
     if (dynamic && !cur_mask_out) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (fast_ok(d, dynamic, nullptr)) reset_kernel<true><<<grid, block, 0, s>>>(d, st, dynamic, cur_mask_out, mask_out);
-    else reset_kernel<false><<<grid, block, 0, s>>>(d, st, dynamic, cur_mask_out, mask_out);
+    if (fast_ok(d, dynamic, nullptr)) launch(reset_kernel<true>, grid, block, s, d, st, dynamic, cur_mask_out, mask_out);
+    else launch(reset_kernel<false>, grid, block, s, d, st, dynamic, cur_mask_out, mask_out);
     return launch_status();
 }
 
@@ -506,8 +663,8 @@ int tapenv_update_dynamic(const tapenv_config *cfg, const float *dynamic, const 
     TAPENV_PROLOGUE(cfg)
     if (d.B == 0) return TAPENV_OK;
     if (!dynamic || !static_ || !ptr || !dynamic_out) return TAPENV_EINVAL;
-    if (fast_ok(d, dynamic, dynamic_out)) update_dynamic_kernel<true><<<grid, block, 0, s>>>(d, dynamic, static_, ptr, dynamic_out);
-    else update_dynamic_kernel<false><<<grid, block, 0, s>>>(d, dynamic, static_, ptr, dynamic_out);
+    if (fast_ok(d, dynamic, dynamic_out)) launch(update_dynamic_kernel<true>, grid, block, s, d, dynamic, static_, ptr, dynamic_out);
+    else launch(update_dynamic_kernel<false>, grid, block, s, d, dynamic, static_, ptr, dynamic_out);
     return launch_status();
 }
 
@@ -516,8 +673,8 @@ int tapenv_update_mask(const tapenv_config *cfg, const float *mask, const float 
     TAPENV_PROLOGUE(cfg)
     if (d.B == 0) return TAPENV_OK;
     if (!mask || !dynamic || !ptr || !new_mask_out || !chosen_mask_out) return TAPENV_EINVAL;
-    if (fast_ok(d, dynamic, nullptr)) update_mask_kernel<true><<<grid, block, 0, s>>>(d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
-    else update_mask_kernel<false><<<grid, block, 0, s>>>(d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
+    if (fast_ok(d, dynamic, nullptr)) launch(update_mask_kernel<true>, grid, block, s, d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
+    else launch(update_mask_kernel<false>, grid, block, s, d, mask, dynamic, ptr, new_mask_out, chosen_mask_out);
     return launch_status();
 }
 
@@ -528,9 +685,9 @@ int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks
     if (d.B == 0) return TAPENV_OK;
     if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (strat == STRAT_LBG2D) add_blocks_kernel<STRAT_LBG2D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
-    else if (strat == STRAT_LBG3D) add_blocks_kernel<STRAT_LBG3D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
-    else add_blocks_kernel<STRAT_MACS2D><<<grid, block, 0, s>>>(d, st, blocks, dec_dynamic_out);
+    if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    else if (strat == STRAT_LBG3D) launch(add_blocks_kernel<STRAT_LBG3D>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    else launch(add_blocks_kernel<STRAT_MACS2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     return launch_status();
 }
 
@@ -549,19 +706,19 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
     // shapes with a fully unrolled instantiation ('bot'-like inputs: 3 bands, all updated); anything else runs generic
     const bool bot = d.dyn_rows == 3 * d.n && d.update_time == 3 && d.static_rows == 1 + d.dim;
     if (strat == STRAT_LBG2D) {
-        if (fast && bot && d.n == 10 && d.R == 2) step_kernel<STRAT_LBG2D, true, 10, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else if (fast && bot && d.n == 20 && d.R == 2) step_kernel<STRAT_LBG2D, true, 20, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else if (fast) step_kernel<STRAT_LBG2D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else step_kernel<STRAT_LBG2D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 10 && d.R == 2) launch(step_kernel<STRAT_LBG2D, true, 10, 2>, grid, block, s, TAPENV_STEP_ARGS);
+        else if (fast && bot && d.n == 20 && d.R == 2) launch(step_kernel<STRAT_LBG2D, true, 20, 2>, grid, block, s, TAPENV_STEP_ARGS);
+        else if (fast) launch(step_kernel<STRAT_LBG2D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        else launch(step_kernel<STRAT_LBG2D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
     } else if (strat == STRAT_LBG3D) {
-        if (fast && bot && d.n == 10 && d.R == 6) step_kernel<STRAT_LBG3D, true, 10, 6><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else if (fast) step_kernel<STRAT_LBG3D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else step_kernel<STRAT_LBG3D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 10 && d.R == 6) launch(step_kernel<STRAT_LBG3D, true, 10, 6>, grid, block, s, TAPENV_STEP_ARGS);
+        else if (fast) launch(step_kernel<STRAT_LBG3D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        else launch(step_kernel<STRAT_LBG3D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
     } else {
-        if (fast && bot && d.n == 20 && d.R == 2) step_kernel<STRAT_MACS2D, true, 20, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else if (fast && bot && d.n == 10 && d.R == 2) step_kernel<STRAT_MACS2D, true, 10, 2><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else if (fast) step_kernel<STRAT_MACS2D, true, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
-        else step_kernel<STRAT_MACS2D, false, 0, 0><<<grid, block, 0, s>>>(TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 20 && d.R == 2) launch(step_kernel<STRAT_MACS2D, true, 20, 2>, grid, block, s, TAPENV_STEP_ARGS);
+        else if (fast && bot && d.n == 10 && d.R == 2) launch(step_kernel<STRAT_MACS2D, true, 10, 2>, grid, block, s, TAPENV_STEP_ARGS);
+        else if (fast) launch(step_kernel<STRAT_MACS2D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        else launch(step_kernel<STRAT_MACS2D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
     }
     return launch_status();
 }
@@ -573,17 +730,25 @@ int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out
     cudaStream_t s = (cudaStream_t)stream;
     const DevCfg d = devcfg_of(cfg);
     const StatePtrs st = stateptrs_of(cfg, const_cast<void *>(state));
-    if (d.B > 0) reward_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(d, st, reward_out);
-    if (partial_sums_out) reward_sums_kernel<<<1, 1024, 0, s>>>(d.B, reward_out, partial_sums_out);
+    if (d.B > 0) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
+    if (partial_sums_out) launch(reward_sums_kernel, 1, 1024, s, d.B, reward_out, partial_sums_out);
     return launch_status();
 }
 
 int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, const float *dynamic,
                    const int64_t *ptr_seq, int32_t steps, float *reward_out, float *cur_mask_out, float *mask_out,
                    float *dec_dynamic_out, void *stream) {
-    (void)cfg; (void)state; (void)static_; (void)dynamic; (void)ptr_seq; (void)steps; (void)reward_out;
-    (void)cur_mask_out; (void)mask_out; (void)dec_dynamic_out; (void)stream;
-    return TAPENV_EUNSUPPORTED;
+    TAPENV_PROLOGUE(cfg)
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (steps < 0 || steps > 64 || steps > cfg->capacity) return TAPENV_ELIMIT;
+    if (d.B == 0) return TAPENV_OK;
+    if (!state || !static_ || !dynamic || (steps > 0 && !ptr_seq)) return TAPENV_EINVAL;
+    const StatePtrs st = stateptrs_of(cfg, state);
+    if (strat == STRAT_LBG2D) launch(episode_kernel<STRAT_LBG2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    else if (strat == STRAT_LBG3D) launch(episode_kernel<STRAT_LBG3D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    else launch(episode_kernel<STRAT_MACS2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    return launch_status();
 }
 
 }  // extern "C"

@@ -12,7 +12,8 @@ from ._capi import TapEnvError
 from .config import make_config, rotate_types
 from .ops import update_dynamic, update_mask
 from .containers import BatchedContainers, Container
-from .runner import EpisodeRunner
+from .runner import EpisodeRunner, HostPipeline
+from . import dist
 
-__all__ = ["update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "make_config", "rotate_types",
+__all__ = ["update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
            "TapEnvError"]

@@ -1,0 +1,61 @@
+"""Multi-GPU: environments are independent, so a batch shards across ranks with NO per-step exchange
+(one process per GPU, torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The only collective of the path is the end-of-episode reduction of the reward statistics that feed the
+critic baseline / advantage normalisation (trainer.py:216-225, :238-240): every rank contributes the
+fp64 triple (sum r, sum r^2, count) produced by tapenv_reward, the triples are all-gathered and summed
+IN RANK ORDER on every rank, so the result is bit-identical on all ranks and independent of the
+collective's internal reduction order.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, world_size, rank):
+    """Contiguous shard [lo, hi) of `total` environments owned by `rank` (remainder spread over the first ranks)."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard(tensor, world_size, rank, dim=0):
+    """This rank's slice of a batch-major tensor."""
+    lo, hi = shard_range(tensor.shape[dim], world_size, rank)
+    return tensor.narrow(dim, lo, hi - lo)
+
+
+def combine_partial_sums(sums, group=None):
+    """sums: f64 [3] = (sum r, sum r^2, count) of THIS rank (any device the group's backend supports).
+    Returns the f64 [3] totals over all ranks, summed in rank order (deterministic, identical on every rank)."""
+    if sums.dtype != torch.float64 or sums.numel() != 3:
+        raise ValueError("partial sums must be a float64 [3] tensor")
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return sums.clone()
+    world = dist.get_world_size(group)
+    gathered = torch.empty(world, 3, dtype=torch.float64, device=sums.device)
+    dist.all_gather_into_tensor(gathered, sums.reshape(1, 3).contiguous(), group=group)
+    total = gathered[0].clone()
+    for r in range(1, world):                      # fixed order: rank 0 + rank 1 + ...
+        total += gathered[r]
+    return total
+
+
+def reward_statistics(sums_total):
+    """(mean, variance, count) of the rewards of the GLOBAL batch from the combined sums."""
+    s1, s2, cnt = [float(v) for v in sums_total.tolist()]
+    if cnt == 0:
+        return 0.0, 0.0, 0
+    mean = s1 / cnt
+    return mean, max(s2 / cnt - mean * mean, 0.0), int(cnt)
+
+
+def gather_rewards(reward, group=None):
+    """All-gather of the per-environment rewards (equal shard sizes) -> f32 [world*B_local], rank-major."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return reward.clone()
+    world = dist.get_world_size(group)
+    out = torch.empty(world * reward.numel(), dtype=reward.dtype, device=reward.device)
+    dist.all_gather_into_tensor(out, reward.contiguous(), group=group)
+    return out

@@ -63,3 +63,70 @@ class EpisodeRunner(object):
         else:
             self._episode()
         return self.reward
+
+
+class HostPipeline(object):
+    """Episodes whose inputs live in HOST memory: double-buffered H2D upload of (static, dynamic, ptr_seq) on a copy
+    stream, episode replay on the compute stream, D2H of the rewards -- upload of episode i+1 overlaps the kernels of
+    episode i.  This is the end-to-end path a trainer's DataLoader drives (trainer.py:189-192: one .cuda() per batch).
+
+        pipe = HostPipeline(env, static_shape, dynamic_shape, steps)
+        pipe.submit(static_pinned, dynamic_pinned, ptr_seq_pinned)     # returns immediately
+        rewards = pipe.result()                                       # pinned f32 [B] of the OLDEST submitted episode
+    """
+
+    def __init__(self, env, steps, depth=2, use_graph=True):
+        self.env = env
+        dev = env.device
+        B, S = env.batch_size, env.S
+        cfg = env.cfg
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(depth):
+            st = torch.empty(B, cfg.static_rows, S, dtype=torch.float32, device=dev)
+            dy = torch.empty(B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
+            pq = torch.zeros(steps, B, dtype=torch.int64, device=dev)
+            runner = EpisodeRunner(env, st, dy, pq, use_graph=use_graph, partial_sums=True)
+            self.slots.append(dict(static=st, dynamic=dy, ptr=pq, runner=runner,
+                                   uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event(),
+                                   reward=torch.empty(B, dtype=torch.float32).pin_memory(),
+                                   sums=torch.empty(3, dtype=torch.float64).pin_memory(), busy=False))
+        self.head = 0      # next slot to submit into
+        self.tail = 0      # oldest slot in flight
+        self.inflight = 0
+        self.h2d_bytes = (B * cfg.static_rows * S + B * cfg.dyn_rows * S) * 4 + steps * B * 8
+        self.d2h_bytes = B * 4 + 24
+
+    def submit(self, static_h, dynamic_h, ptr_h, after_episode=None):
+        if self.inflight == self.depth:
+            raise RuntimeError("pipeline full: call result() first")
+        s = self.slots[self.head]
+        compute = torch.cuda.current_stream(self.env.device)
+        with torch.cuda.stream(self.copy_stream):
+            if s["busy"]:
+                self.copy_stream.wait_event(s["consumed"])       # the slot's previous episode has read its inputs
+            s["static"].copy_(static_h, non_blocking=True)
+            s["dynamic"].copy_(dynamic_h, non_blocking=True)
+            s["ptr"].copy_(ptr_h, non_blocking=True)
+            s["uploaded"].record(self.copy_stream)
+        compute.wait_event(s["uploaded"])
+        r = s["runner"].run()
+        s["consumed"].record(compute)
+        if after_episode is not None:
+            after_episode(s["runner"])                           # e.g. the cross-rank reduction of runner.sums
+        s["reward"].copy_(r, non_blocking=True)
+        s["sums"].copy_(s["runner"].sums, non_blocking=True)
+        s["done"].record(compute)
+        s["busy"] = True
+        self.head = (self.head + 1) % self.depth
+        self.inflight += 1
+
+    def result(self):
+        if self.inflight == 0:
+            raise RuntimeError("nothing in flight")
+        s = self.slots[self.tail]
+        s["done"].synchronize()
+        self.tail = (self.tail + 1) % self.depth
+        self.inflight -= 1
+        return s["reward"], s["sums"]

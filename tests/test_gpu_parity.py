@@ -241,3 +241,37 @@ def test_reward_partial_sums_are_deterministic():
     assert torch.equal(s, s2) and float(s[2]) == 1000.0
     r64 = r.double().cpu().numpy()
     assert abs(float(s[0]) - r64.sum()) < 1e-9 and abs(float(s[1]) - (r64 ** 2).sum()) < 1e-9
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[5], CASES[7], CASES[8], CASES[9]],
+                         ids=["2d-soft", "2d-hard", "2d-w9", "macs-rand", "macs-ppsg", "3d-soft", "3d-hard"])
+def test_whole_episode_kernel_matches_stepwise_oracle(case):
+    """K7 (tapenv_episode): one launch per episode == reset + n steps + calc_ratio of the oracle."""
+    torch = _torch()
+    import tapenv
+    src, num, size, rt, hm, strat = case
+    if not os.path.exists(golden_path(src)):
+        pytest.skip("fixture not generated")
+    static, dynamic = load_inputs(src, min(num, 1024))
+    B = static.shape[0]
+    r = oracle_rollout(static, dynamic, size, rt, hm, strat, seed=21)
+    n = r["ptr"].shape[0]
+    env = tapenv.BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=B)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    for steps in (n, 3, 0):
+        reward, cur, mask, dec_dyn = env.episode(st, dyn, torch.from_numpy(r["ptr"][:steps]).cuda().reshape(steps, B))
+        assert np.array_equal(cur.cpu().numpy(), r["cur_mask"][steps])
+        if steps:
+            assert np.array_equal(mask.cpu().numpy(), r["mask"][steps - 1])
+            assert np.array_equal(env.heightmap.cpu().numpy().reshape(B, -1), r["heightmap"][steps - 1])
+            assert np.array_equal(dec_dyn.cpu().numpy().reshape(B, -1), r["dec_dyn"][steps - 1].astype(np.float32))
+            assert np.array_equal(env.valid_size.cpu().numpy(), r["valid"][steps - 1])
+            assert np.array_equal(env.empty_size.cpu().numpy(), r["empty"][steps - 1])
+        else:
+            assert int(env.heightmap.sum()) == 0 and float(mask.min()) == 1.0
+        if steps == n:
+            assert np.array_equal(reward.cpu().numpy(), r["ratio"].astype(np.float32))
+            assert np.array_equal(env.positions.cpu().numpy(), r["positions"])
+            assert np.array_equal(env.stable.cpu().numpy(), r["stable"])
+        assert (env.flags.cpu().numpy() == 0).all()
+    assert torch.equal(dyn, torch.from_numpy(dynamic).cuda())
