@@ -14,6 +14,10 @@ from .ops import update_dynamic, update_mask
 from .containers import BatchedContainers, Container
 from .runner import EpisodeRunner, HostPipeline
 from . import dist
+from .dataset import PACKDataset
+from .episode import calc_positions_lb_greedy, calc_positions_mcs, reward
+from .dropin import install, uninstall
 
-__all__ = ["update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
+__all__ = ["PACKDataset", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
+           "update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
            "TapEnvError"]

@@ -6,6 +6,7 @@ the C ABI (include/tapenv.h).  `Container` keeps the reference's per-environment
 (tools.py:3607-3966) as a thin view of one row, so an UNMODIFIED model.py can be pointed at it.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -69,14 +70,17 @@ class BatchedContainers(object):
 
     @property
     def valid_size(self):
+        self._bind()
         return self.scalars[:, 0]
 
     @property
     def empty_size(self):
+        self._bind()
         return self.scalars[:, 1]
 
     @property
     def current_blocks_num(self):
+        self._bind()
         return self.scalars[:, 3]
 
     @property
@@ -211,28 +215,78 @@ class BatchedContainers(object):
         return (Container._view_of(self, b) for b in range(self.batch_size))
 
 
-class Container(object):
-    """tools.Container (tools.py:3607) signature.  Stand-alone it is a batch of one; inside a
-    BatchedContainers it is row `b` of the batch.
+class _Group(object):
+    """Containers constructed back to back with identical arguments (model.py:294's list comprehension)."""
 
-    Drop-in trick for an unmodified model.py (model.py:452-453 calls add_new_block once per
-    environment with `blocks[b]`, a row VIEW of one [B,dim] ndarray): the call for row 0 launches the
-    step for the whole batch from `block.base`, copies the encoded heightmaps to the host once, and
-    every row call just returns its row."""
+    def __init__(self, args):
+        self.args = args
+        self.members = []
+        self.batch = None        # None (undecided) | "single" | BatchedContainers
+        self.closed = False
+
+
+_tls = threading.local()
+
+
+class Container(object):
+    """tools.Container (tools.py:3607) signature, usable exactly like the reference class.
+
+    Drop-in behaviour for an UNMODIFIED model.py: `[tools.Container(...) for _ in range(B)]` (model.py:294)
+    creates B of these back to back; they only remember their construction order.  The first
+    `add_new_block` (model.py:452-453 calls it once per environment with `blocks[b]`, a row VIEW of one [B,dim]
+    ndarray) reveals the batch: row 0's call binds all B objects to ONE BatchedContainers, launches the step
+    for the whole batch from `block.base`, copies the encoded heightmaps to the host once, and every later
+    row call just returns its row.  Used any other way (a single object, rows out of order, blocks that are
+    not views of one array) each object becomes its own batch of one -- correct, just not batched."""
 
     def __init__(self, container_size, blocks_num, reward_type, heightmap_type="full", initial_container_size=None,
                  max_height=None, packing_strategy="LB_GREEDY", _batch=None, _row=0):
-        if _batch is None:
-            _batch = BatchedContainers(container_size, blocks_num, reward_type, heightmap_type, initial_container_size,
-                                       max_height, packing_strategy, batch_size=1)
         self._batch = _batch
         self._row = _row
-        self.container_size = _batch.container_size
-        self.block_dim = _batch.block_dim
-        self.blocks_num = _batch.blocks_num
-        self.reward_type = _batch.reward_type
-        self.heightmap_type = _batch.heightmap_type
-        self.packing_strategy = _batch.packing_strategy
+        self._group = None
+        if _batch is not None:
+            self._adopt(_batch)
+            return
+        cfg = make_config(1, blocks_num, container_size, reward_type, heightmap_type, packing_strategy)   # validates the strings
+        self.container_size = [int(v) for v in container_size]
+        self.block_dim = len(self.container_size)
+        self.blocks_num = int(blocks_num)
+        self.reward_type = reward_type
+        self.heightmap_type = heightmap_type
+        self.packing_strategy = "MACS" if cfg.strategy == _capi.MACS else packing_strategy
+        args = (tuple(self.container_size), self.blocks_num, reward_type, heightmap_type, packing_strategy)
+        g = getattr(_tls, "open_group", None)
+        if g is None or g.closed or g.args != args:
+            g = _Group(args)
+            _tls.open_group = g
+        self._group = g
+        self._row = len(g.members)
+        g.members.append(self)
+
+    def _adopt(self, batch):
+        self.container_size = batch.container_size
+        self.block_dim = batch.block_dim
+        self.blocks_num = batch.blocks_num
+        self.reward_type = batch.reward_type
+        self.heightmap_type = batch.heightmap_type
+        self.packing_strategy = batch.packing_strategy
+
+    def _bind(self, batch_hint=None):
+        if self._batch is not None:
+            return
+        g = self._group
+        g.closed = True
+        size, n, rt, hm, strat = g.args
+        if g.batch is None:
+            if batch_hint is not None and batch_hint > 1 and batch_hint == len(g.members) and self._row == 0:
+                g.batch = BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=batch_hint)
+            else:
+                g.batch = "single"
+        if g.batch == "single":
+            self._batch = BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=1)
+            self._row = 0
+        else:
+            self._batch = g.batch
 
     @classmethod
     def _view_of(cls, batch, row):
@@ -247,9 +301,12 @@ class Container(object):
         return enc[self._row].astype(np.int64)
 
     def add_new_block(self, block, is_rotate=False):
-        bt, b = self._batch, self._row
         block = np.asarray(block, dtype=np.float32)
         base = block.base
+        if self._batch is None:
+            hint = base.shape[0] if (base is not None and base.ndim == 2 and base.shape[1] == self.block_dim) else None
+            self._bind(hint)
+        bt, b = self._batch, self._row
         pending = bt.__dict__.get("_pending")
         if pending is not None and pending["next"] == b and b > 0:
             pending["next"] = b + 1
@@ -285,6 +342,7 @@ class Container(object):
         return out
 
     def clear_container(self):
+        self._bind()
         if self._batch.batch_size != 1:
             raise RuntimeError("tapenv: clear the whole batch with BatchedContainers.clear_container()")
         self._batch.clear_container()
@@ -292,6 +350,7 @@ class Container(object):
     def calc_ratio(self):
         """One launch + one D2H copy per batch state (cached until the batch changes), then row reads:
         model.py:509-510 calls this once per environment."""
+        self._bind()
         bt = self._batch
         cache = bt.__dict__.get("_ratio_cache")
         if cache is None or cache[0] != bt._version:
@@ -300,6 +359,7 @@ class Container(object):
         return float(cache[1][self._row])
 
     def calc_CPS(self):
+        self._bind()
         v, e, s, k = [int(x) for x in self._batch.scalars[self._row].tolist()]
         if k == 0:
             return 0, 0, 0
@@ -310,24 +370,30 @@ class Container(object):
     # attributes the reference's callers read (rolling.py:640-658, model.py:1175)
     @property
     def heightmap(self):
+        self._bind()
         return self._batch.heightmap[self._row].cpu().numpy().astype(np.int64)
 
     @property
     def positions(self):
+        self._bind()
         return self._batch.positions[self._row].cpu().numpy().astype(np.int64)
 
     @property
     def stable(self):
+        self._bind()
         return [bool(v) for v in self._batch.stable[self._row].tolist()]
 
     @property
     def valid_size(self):
+        self._bind()
         return int(self._batch.scalars[self._row, 0].item())
 
     @property
     def empty_size(self):
+        self._bind()
         return int(self._batch.scalars[self._row, 1].item())
 
     @property
     def current_blocks_num(self):
+        self._bind()
         return int(self._batch.scalars[self._row, 3].item())

@@ -1,0 +1,78 @@
+"""Whole-episode entries with the reference's signatures: tools.calc_positions_lb_greedy (tools.py:2393-2449),
+tools.calc_positions_mcs (:3213-3315) and pack.reward (pack.py:378-473), batched over environments.
+
+The placement runs in the CUDA kernels (one add_new_block launch per block for the whole batch); the
+C/P/S arithmetic on the resulting integer state is IEEE fp64 division in torch, the same operations the
+reference performs in NumPy."""
+import numpy as np
+import torch
+
+from .containers import BatchedContainers
+from .config import rotate_types
+
+
+def _pack_sequence(blocks, container_size, reward_type, packing_strategy):
+    blocks = torch.as_tensor(blocks)
+    single = blocks.dim() == 2
+    if single:
+        blocks = blocks.unsqueeze(0)
+    if not blocks.is_cuda:
+        blocks = blocks.cuda()
+    blocks = blocks.to(torch.float32)
+    B, n, dim = blocks.shape
+    env = BatchedContainers(container_size, n, reward_type, "full", packing_strategy=packing_strategy, batch_size=B,
+                            device=blocks.device)
+    for i in range(n):
+        env.add_new_blocks(blocks[:, i].contiguous())
+    env.check_flags()
+    return env, single
+
+
+def _result(env, single):
+    sc = env.scalars.to(torch.float64)
+    valid, empty, nstable = sc[:, 0], sc[:, 1], sc[:, 2]
+    hmax = env.heightmap.reshape(env.batch_size, -1).max(dim=1).values
+    cells = env._cells
+    box = hmax.to(torch.float64) * cells
+    n = env.blocks_num
+    ratio = valid / box + valid / (empty + valid) + nstable / n          # C + P + S, NOT divided by 3 (tools.py:2438-2446)
+    scores = torch.stack([sc[:, 0], box, sc[:, 1], sc[:, 2], hmax.to(torch.float64)], 1).to(torch.int64)
+    positions, stable, heightmap = env.positions.clone(), env.stable.bool(), env.heightmap.clone()
+    if single:
+        return (positions[0].cpu().numpy().astype(np.int64), heightmap[0].cpu().numpy().astype(np.int64),
+                [bool(v) for v in stable[0].tolist()], float(ratio[0].item()), [int(v) for v in scores[0].tolist()])
+    return positions, heightmap, stable, ratio, scores
+
+
+def calc_positions_lb_greedy(blocks, container_size, reward_type):
+    """blocks [n,dim] (reference form) or [B,n,dim] (batched).  Returns (positions, heightmap, stable, ratio, scores)
+    with ratio = C+P+S and scores = [valid_size, box_size, empty_size, stable_num, packing_height].
+    The reference returns its voxel `container` in second place; the heightmap carries the same information
+    (cell != 0 <=> z < heightmap) and is what is returned here."""
+    env, single = _pack_sequence(blocks, container_size, reward_type, "LB_GREEDY")
+    return _result(env, single)
+
+
+def calc_positions_mcs(blocks, container_size, reward_type):
+    env, single = _pack_sequence(blocks, container_size, reward_type, "MACS")
+    return _result(env, single)
+
+
+def reward(static, tour_indices, reward_type, input_type, allow_rot, container_width, container_height,
+           packing_strategy="LB_GREEDY"):
+    """pack.reward: re-pack a finished tour and return -(C+P+S) as f32 [B] (pack.py:378-473)."""
+    if input_type in ("mul", "mul-with"):
+        raise NotImplementedError("two-container inputs are outside the accelerated path")
+    static = static.detach()
+    if not static.is_cuda:
+        static = static.cuda()
+    dim = static.shape[1] - 1
+    R = rotate_types(dim, allow_rot)
+    n = static.shape[2] // R
+    size = [container_width, container_height] if dim == 2 else [container_width, container_width, container_height]
+    idx = tour_indices.to(static.device).long()[:, :n]
+    seq = torch.gather(static[:, 1:1 + dim], 2, idx.unsqueeze(1).expand(-1, dim, -1)).transpose(1, 2).contiguous()   # [B,n,dim]
+    strat = "MACS" if packing_strategy in ("MACS", "MUL") else "LB_GREEDY"
+    env, _ = _pack_sequence(seq, size, reward_type, strat)
+    ratio = _result(env, False)[3]
+    return -ratio.to(torch.float32)

@@ -275,3 +275,67 @@ def test_whole_episode_kernel_matches_stepwise_oracle(case):
             assert np.array_equal(env.stable.cpu().numpy(), r["stable"])
         assert (env.flags.cpu().numpy() == 0).all()
     assert torch.equal(dyn, torch.from_numpy(dynamic).cuda())
+
+
+def test_lazy_container_list_as_model_py_builds_it():
+    """`[tools.Container(...) for _ in range(B)]` (model.py:294) with tapenv.Container substituted: the B objects
+    bind to ONE batch on the first add_new_block and behave like the reference objects."""
+    torch = _torch()
+    import tapenv
+    static, dynamic = load_inputs("rand3d_n10.npz", 48)
+    B, n, dim, size = 48, 10, 3, [5, 5, 50]
+    r = oracle_rollout(static, dynamic, size, "C+P+S-lb-soft", "diff", "LB_GREEDY", seed=9)
+    containers = [tapenv.Container(size, n, "C+P+S-lb-soft", "diff", packing_strategy="LB_GREEDY") for _ in range(B)]
+    st = torch.from_numpy(static).cuda()
+    for t in range(n):
+        ptr = torch.from_numpy(r["ptr"][t]).cuda()
+        blocks = torch.gather(st[:, 1:1 + dim], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1)).squeeze(2).cpu().numpy()
+        hms = [containers[b].add_new_block(blocks[b], False) for b in range(B)]
+        assert hms[0].shape == (2, 5, 5)
+        assert np.array_equal(np.stack(hms).reshape(B, -1), r["dec_dyn"][t])
+    assert containers[0]._batch is containers[B - 1]._batch and containers[0]._batch.batch_size == B
+    assert np.abs(np.array([c.calc_ratio() for c in containers]) - r["ratio"]).max() <= REWARD_TOL
+    # a lone object is a batch of one
+    one = tapenv.Container([5, 50], 3, "C+P+S-lb-soft", "diff")
+    kat = np.load(golden_path("kat.npz"))
+    for t, b in enumerate([[3, 3], [3, 3], [2, 3]]):
+        assert np.array_equal(one.add_new_block(np.array(b, np.float32)), kat["G1_enc"][t])
+    assert one.valid_size == 24 and one.current_blocks_num == 3 and one.heightmap.tolist() == [6, 6, 6, 3, 3]
+
+
+def test_whole_episode_wrappers_known_answers():
+    """tools.calc_positions_lb_greedy / pack.reward signatures: visual/draw_result.py:14-34 and SURVEY G1/G3."""
+    torch = _torch()
+    import tapenv
+    pos, hm, stable, ratio, scores = tapenv.calc_positions_lb_greedy(np.array([[3, 2], [1, 1], [1, 2]]), [4, 6], "C+P+S-lb-hard")
+    assert pos.tolist() == [[0, 0], [3, 0], [3, 1]] and stable == [True, True, True]
+    assert ratio == 2.75 and scores == [9, 12, 0, 3, 3] and hm.tolist() == [2, 2, 2, 3]
+    kat = np.load(golden_path("kat.npz"))
+    g1 = torch.tensor(kat["G1_blocks"], dtype=torch.float32).unsqueeze(0).repeat(3, 1, 1)
+    pos, hm, stable, ratio, scores = tapenv.calc_positions_lb_greedy(g1, [5, 50], "C+P+S-lb-soft")
+    assert np.array_equal(pos[2].cpu().numpy(), kat["G1_positions"]) and abs(float(ratio[1]) - 3 * 0.8775) < 1e-12
+    g3 = torch.tensor(kat["G3_blocks"], dtype=torch.float32)
+    pos, hm, stable, ratio, scores = tapenv.calc_positions_mcs(g3, [7, 100], "C+P+S-mcs-hard")
+    assert np.array_equal(pos, kat["G3_positions"]) and abs(ratio - 3 * float(kat["G3_ratio"])) < 1e-12
+    # pack.reward: tour indices into `static`
+    static, dynamic = load_inputs("rand2d_n10.npz", 16)
+    tour = np.stack([np.random.RandomState(i).permutation(10) + 10 * (i % 2) for i in range(16)])
+    rw = tapenv.reward(torch.from_numpy(static), torch.from_numpy(tour), "C+P+S-lb-soft", "bot", True, 5, 50)
+    from oracle import oracle
+    for b in range(16):
+        c = oracle.Container([5, 50], 10, "C+P+S-lb-soft", "full")
+        for j in tour[b]:
+            c.add_new_block(static[b, 1:3, j])
+        assert abs(float(rw[b]) + 3 * c.calc_ratio()) <= 1e-6
+
+
+def test_install_patches_reference_modules():
+    import types
+    import tapenv
+    pack, tools = types.ModuleType("pack"), types.ModuleType("tools")
+    pack.update_dynamic = pack.update_mask = pack.reward = tools.Container = tools.calc_positions_lb_greedy = "orig"
+    names = tapenv.install(pack, tools)
+    assert set(names) == {"update_dynamic", "update_mask", "reward", "Container", "calc_positions_lb_greedy"}
+    assert pack.update_dynamic is tapenv.update_dynamic and tools.Container is tapenv.Container
+    tapenv.uninstall()
+    assert pack.update_mask == "orig" and tools.Container == "orig"

@@ -1,0 +1,99 @@
+"""CPU, build container only (needs /root/reference): live differential checks of the oracle restatement and of
+the host-side dataset loader against the UNMODIFIED Python reference.  Skipped where the reference is absent
+(the GPU box); the committed fixtures under tests/golden/ carry the same pins there."""
+import os
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle, refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refshim.load(("tools", "generate", "pack"))
+
+
+CASES = [
+    (2, [5, 50], 10, "C+P+S-lb-soft", "LB_GREEDY", "diff", 120),
+    (2, [5, 50], 10, "C+P+S-lb-hard", "LB_GREEDY", "zero", 120),
+    (2, [4, 60], 12, "C+P-lb-hard", "LB_GREEDY", "full", 80),
+    (2, [7, 100], 20, "C+P+S-mcs-hard", "MACS", "diff", 60),
+    (2, [5, 50], 10, "C+P+S-mcs-soft", "MACS", "diff", 60),
+    (2, [6, 60], 12, "C+P-mcs-soft", "MACS", "full", 40),
+    (3, [5, 5, 50], 10, "C+P+S-lb-soft", "LB_GREEDY", "diff", 60),
+    (3, [5, 5, 50], 10, "C+P+S-lb-hard", "LB_GREEDY", "zero", 60),
+    (3, [4, 6, 80], 14, "C+P+S-lb-soft", "LB_GREEDY", "full", 30),
+]
+
+
+@pytest.mark.parametrize("dim,size,n,rt,strat,hm,episodes", CASES)
+def test_container_differential(ref, dim, size, n, rt, strat, hm, episodes):
+    tools = ref["tools"]
+    rng = np.random.RandomState(hash((dim, n, rt)) % 2 ** 31)
+    for ep in range(episodes):
+        c = oracle.Container(size, n, rt, hm, packing_strategy=strat)
+        r = tools.Container(size, n, rt, hm, packing_strategy=strat)
+        for k in range(n):
+            b = rng.randint(1, 5, size=dim).astype(np.float32)
+            e = r.add_new_block(b.copy())
+            a = c.add_new_block(b.copy())
+            assert np.array_equal(np.asarray(a), np.asarray(e)), (ep, k)
+            assert np.array_equal(c.heightmap, np.asarray(r.heightmap)) and np.array_equal(c.positions, np.asarray(r.positions))
+            assert c.valid_size == r.valid_size and c.empty_size == r.empty_size
+            assert list(c.stable) == [bool(x) for x in r.stable]
+        assert c.calc_ratio() == r.calc_ratio()
+        assert np.array_equal(c.container, np.asarray(r.container))
+        if strat == "MACS":
+            assert c.level_free_space == [list(map(int, l)) for l in r.level_free_space]
+
+
+def test_mask_and_dynamic_differential(ref):
+    import torch
+    pack = ref["pack"]
+    rng = np.random.RandomState(5)
+    for dim, n in ((2, 10), (3, 10), (2, 20)):
+        R = 2 if dim == 2 else 6
+        S = n * R
+        B = 32
+        static = np.zeros((B, 1 + dim, S), np.float32)
+        static[:, 0] = np.tile(np.arange(n), R)
+        static[:, 1:] = rng.randint(1, 5, size=(B, dim, S))
+        dynamic = (rng.random_sample((B, 3 * n, S)) < 0.1).astype(np.float32)
+        mask = np.ones((B, S), np.float32)
+        dyn_t, mask_t = torch.from_numpy(dynamic), torch.from_numpy(mask)
+        for t in range(n):
+            ptr = rng.randint(0, S, size=B).astype(np.int64)
+            dynamic = oracle.update_dynamic(dynamic, static, ptr)
+            cur, mask = oracle.update_mask(mask, dynamic, static, ptr)
+            dyn_t = pack.update_dynamic(dyn_t, torch.from_numpy(static), torch.from_numpy(ptr), "bot", True)
+            cur_t, mask_t = pack.update_mask(mask_t, dyn_t, torch.from_numpy(static), torch.from_numpy(ptr), "bot", True)
+            assert np.array_equal(dynamic, dyn_t.numpy()) and np.array_equal(cur, cur_t.numpy()) and np.array_equal(mask, mask_t.numpy())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_packdataset_matches_reference_loader(ref, dim):
+    """tapenv.PACKDataset builds the same four tensors as pack.PACKDataset from the same dataset directory."""
+    from tapenv.dataset import PACKDataset
+    pack = ref["pack"]
+    cwd = os.getcwd()
+    d = tempfile.mkdtemp(prefix="tapds_")
+    os.chdir(d)
+    try:
+        train_dir, _ = pack.create_dataset(10, 24, 4, dim, 7, 50, 1, [1, 5], seed=99)
+        for input_type, hm in (("bot", "diff"), ("bot", "full"), ("simple", "zero"), ("bot-rot", "diff")):
+            allow_rot = input_type != "simple"
+            theirs = pack.PACKDataset(train_dir, 10, 24, 7, input_type, hm, True, 5)
+            ours = PACKDataset(train_dir, 10, 24, 7, input_type, hm, True, 5)
+            assert np.array_equal(ours.static.numpy(), theirs.static.numpy())
+            assert np.array_equal(ours.dynamic.numpy(), theirs.dynamic.numpy())
+            assert ours.decoder_static.shape == theirs.decoder_static.shape
+            assert ours.decoder_dynamic.shape == theirs.decoder_dynamic.shape
+            assert len(ours) == len(theirs) and all(np.array_equal(a.detach().numpy(), b.detach().numpy()) for a, b in zip(ours[3], theirs[3]))
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(d, ignore_errors=True)
