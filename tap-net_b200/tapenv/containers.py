@@ -70,17 +70,14 @@ class BatchedContainers(object):
 
     @property
     def valid_size(self):
-        self._bind()
         return self.scalars[:, 0]
 
     @property
     def empty_size(self):
-        self._bind()
         return self.scalars[:, 1]
 
     @property
     def current_blocks_num(self):
-        self._bind()
         return self.scalars[:, 3]
 
     @property
