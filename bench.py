@@ -232,12 +232,17 @@ def run_ours(args):
         runners.append(tapenv.EpisodeRunner(env, st, dy, pq, use_graph=not args.no_graph, partial_sums=True))
     sums_total = torch.zeros(3, dtype=torch.float64, device=dev)
 
+    reducer = tapenv.dist.RewardReducer(dev) if world > 1 else None
+
     def episode(i):
         r = runners[i % RING]
+        if world > 1 and getattr(r, "reduced", None) is not None:
+            torch.cuda.current_stream().wait_event(r.reduced)     # the slot's previous sums have been consumed
         r.run()
         if world > 1:
-            # end-of-episode reduction of the reward statistics feeding the critic baseline (trainer.py:216-225)
-            r.total = tapenv.dist.combine_partial_sums(r.sums)
+            # end-of-episode reduction of the reward statistics feeding the critic baseline (trainer.py:216-225):
+            # all-gather of the per-rank f64 triples on a side stream, overlapping the next episode
+            r.total, r.reduced = reducer.reduce_async(r.sums)
         return r
 
     def barrier():
@@ -309,7 +314,7 @@ def run_ours(args):
     dy_pin = torch.from_numpy(dynamic_h).pin_memory()
     pq_pin = ptr_seq0.cpu().pin_memory()
     pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph)
-    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if world > 1 else None
+    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if world > 1 else None   # in-order here: the host reads the totals
 
     def e2e_run(k):
         last = None

@@ -154,6 +154,12 @@ int32_t tapenv_encoded_heightmap_len(const tapenv_config *cfg);
 int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic,
                  float *cur_mask_out, float *mask_out, void *stream);
 
+/* The initial accessibility mask alone (model.py:297-307 == rolling.py:325-335), without touching any
+ * container state: what a rolling-window driver needs each time the window is refilled while ONE container
+ * keeps filling up (rolling.py:702-703, :607).  cur_mask_out f32 [B,S]; mask_out f32 [B,S] = ones (may be NULL). */
+int tapenv_initial_mask(const tapenv_config *cfg, const float *dynamic, float *cur_mask_out, float *mask_out,
+                        void *stream);
+
 /* pack.update_dynamic(dynamic, static, chosen_idx, input_type, allow_rot) (pack.py:333-376).
  * Out-of-place; block id is read from static[:,0,ptr] (pack.py:347). */
 int tapenv_update_dynamic(const tapenv_config *cfg, const float *dynamic, const float *static_,

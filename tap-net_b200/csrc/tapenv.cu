@@ -225,17 +225,19 @@ __device__ __forceinline__ void container_add_block(const DevCfg &c, const State
 // ------------------------------------------------------------------------------------
 template <bool FAST>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-reset_kernel(DevCfg c, StatePtrs st, const float *__restrict__ dynamic, float *__restrict__ cur_mask,
+reset_kernel(DevCfg c, StatePtrs st, int clear_state, const float *__restrict__ dynamic, float *__restrict__ cur_mask,
              float *__restrict__ mask) {
     typedef Shape<0, 0, 0> SH;
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
-    const int cells = c.dim == 2 ? c.W : c.W * c.L;
-    for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
-    for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
-    for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
-    if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
+    if (clear_state) {
+        const int cells = c.dim == 2 ? c.W : c.W * c.L;
+        for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
+        for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
+        for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
+        if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
+    }
     if (dynamic == nullptr) return;
     const BandBits bits = dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), nullptr, -1);
     mask_pass<SH>(c, lane, false, 0.f, 0.f, -1, bits.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
@@ -293,8 +295,10 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
 // ------------------------------------------------------------------------------------
 // fused decode-step kernel  (K1 + K2/K3/K4): update_dynamic + update_mask + gather + add_new_block
 // ------------------------------------------------------------------------------------
-template <int STRAT, bool FAST, int NT, int RT>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, STRAT == STRAT_LBG2D ? 8 : 4)
+// PLACE_FIRST: run the placement before the precedence pass is consumed (see (3) below) -- chosen when the whole
+// batch is resident in a single wave, where no other warp is left to hide this warp's load latency.
+template <int STRAT, bool FAST, int NT, int RT, bool PLACE_FIRST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, STRAT == STRAT_LBG2D ? 32 / kWarpsPerCta : 16 / kWarpsPerCta)
 step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
             const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
             float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
@@ -330,20 +334,27 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     if (lane < DIM) dimv = srow[(1 + lane) * S + p];
     if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
 
-    // (3) masked copy + column reductions of the precedence tensor
+    // (3) environment transition on the register-resident state.  It only needs the pointer, the block's edge
+    //     lengths and the (tiny) state, all of which arrive long before the precedence tensor has streamed in.
+    //     With a single resident wave (B <= ~4.7k) it runs FIRST so its ~250 warp-instructions overlap the HBM
+    //     read phase; with many waves other warps provide that overlap and the shorter register live range wins.
+    const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+    const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+    const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
+    if (PLACE_FIRST)
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+
+    // (4) masked copy + column reductions of the precedence tensor
     BandBits bits;
     if (FAST) { pass.finish(c, din, dout, lane, real); bits = pass.combine(c); }
     else bits = dynpass_scalar(c, lane, din, dout, real);
 
-    // (4) masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
+    // (5) masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
     mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
                   env_ptr(mask_out, b, (unsigned)S));
 
-    // (5) environment transition on the register-resident state
-    const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
-    const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
-    const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
-    container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+    if (!PLACE_FIRST)
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -653,8 +664,18 @@ int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic, fl
     if (!state) return TAPENV_EINVAL;
     if (dynamic && !cur_mask_out) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (fast_ok(d, dynamic, nullptr)) launch(reset_kernel<true>, grid, block, s, d, st, dynamic, cur_mask_out, mask_out);
-    else launch(reset_kernel<false>, grid, block, s, d, st, dynamic, cur_mask_out, mask_out);
+    if (fast_ok(d, dynamic, nullptr)) launch(reset_kernel<true>, grid, block, s, d, st, 1, dynamic, cur_mask_out, mask_out);
+    else launch(reset_kernel<false>, grid, block, s, d, st, 1, dynamic, cur_mask_out, mask_out);
+    return launch_status();
+}
+
+int tapenv_initial_mask(const tapenv_config *cfg, const float *dynamic, float *cur_mask_out, float *mask_out, void *stream) {
+    TAPENV_PROLOGUE(cfg)
+    if (d.B == 0) return TAPENV_OK;
+    if (!dynamic || !cur_mask_out) return TAPENV_EINVAL;
+    StatePtrs st; memset(&st, 0, sizeof(st));
+    if (fast_ok(d, dynamic, nullptr)) launch(reset_kernel<true>, grid, block, s, d, st, 0, dynamic, cur_mask_out, mask_out);
+    else launch(reset_kernel<false>, grid, block, s, d, st, 0, dynamic, cur_mask_out, mask_out);
     return launch_status();
 }
 
@@ -705,20 +726,27 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
 #define TAPENV_STEP_ARGS d, st, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out, dec_dynamic_out
     // shapes with a fully unrolled instantiation ('bot'-like inputs: 3 bands, all updated); anything else runs generic
     const bool bot = d.dyn_rows == 3 * d.n && d.update_time == 3 && d.static_rows == 1 + d.dim;
+    // one resident wave: 148 SMs x (64 regs -> 32 warps) ; PLACE_FIRST only pays off then (profiles/r01_sweep*.json)
+    const bool pf = d.B <= 148 * 32;
+#define TAPENV_STEP_SHAPE(STRAT, N, R)                                                                     \
+    do {                                                                                                   \
+        if (pf) launch(step_kernel<STRAT, true, N, R, true>, grid, block, s, TAPENV_STEP_ARGS);            \
+        else launch(step_kernel<STRAT, true, N, R, false>, grid, block, s, TAPENV_STEP_ARGS);              \
+    } while (0)
     if (strat == STRAT_LBG2D) {
-        if (fast && bot && d.n == 10 && d.R == 2) launch(step_kernel<STRAT_LBG2D, true, 10, 2>, grid, block, s, TAPENV_STEP_ARGS);
-        else if (fast && bot && d.n == 20 && d.R == 2) launch(step_kernel<STRAT_LBG2D, true, 20, 2>, grid, block, s, TAPENV_STEP_ARGS);
-        else if (fast) launch(step_kernel<STRAT_LBG2D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
-        else launch(step_kernel<STRAT_LBG2D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 10, 2);
+        else if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 20, 2);
+        else if (fast) TAPENV_STEP_SHAPE(STRAT_LBG2D, 0, 0);
+        else launch(step_kernel<STRAT_LBG2D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else if (strat == STRAT_LBG3D) {
-        if (fast && bot && d.n == 10 && d.R == 6) launch(step_kernel<STRAT_LBG3D, true, 10, 6>, grid, block, s, TAPENV_STEP_ARGS);
-        else if (fast) launch(step_kernel<STRAT_LBG3D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
-        else launch(step_kernel<STRAT_LBG3D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 10 && d.R == 6) TAPENV_STEP_SHAPE(STRAT_LBG3D, 10, 6);
+        else if (fast) TAPENV_STEP_SHAPE(STRAT_LBG3D, 0, 0);
+        else launch(step_kernel<STRAT_LBG3D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else {
-        if (fast && bot && d.n == 20 && d.R == 2) launch(step_kernel<STRAT_MACS2D, true, 20, 2>, grid, block, s, TAPENV_STEP_ARGS);
-        else if (fast && bot && d.n == 10 && d.R == 2) launch(step_kernel<STRAT_MACS2D, true, 10, 2>, grid, block, s, TAPENV_STEP_ARGS);
-        else if (fast) launch(step_kernel<STRAT_MACS2D, true, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
-        else launch(step_kernel<STRAT_MACS2D, false, 0, 0>, grid, block, s, TAPENV_STEP_ARGS);
+        if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_MACS2D, 20, 2);
+        else if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_MACS2D, 10, 2);
+        else if (fast) TAPENV_STEP_SHAPE(STRAT_MACS2D, 0, 0);
+        else launch(step_kernel<STRAT_MACS2D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     }
     return launch_status();
 }

@@ -18,7 +18,10 @@ constexpr int kMaxWidth2D = 32;      // one lane per column
 constexpr int kMaxCells3D = 32;      // one lane per heightmap cell
 constexpr int kMaxCandidates = 64;   // S: one 64-bit accessibility word per band
 constexpr int kMaxBlocks = 64;       // n (window) -- two history slots per lane for MACS
-constexpr int kWarpsPerCta = 4;      // environments per CTA
+#ifndef TAPENV_WARPS_PER_CTA
+#define TAPENV_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = TAPENV_WARPS_PER_CTA;      // environments per CTA
 constexpr int kMaxEms = 32 + 2 * kMaxBlocks;   // MACS: list A (<= W) + list B (<= 2 per previous block)
 
 struct DevCfg {  // by-value kernel argument, derived from tapenv_config on the host

@@ -42,6 +42,7 @@ SYMBOLS = {
     "tapenv_state_get_layout": (c_int, [CFG, C.POINTER(StateLayout)]),
     "tapenv_encoded_heightmap_len": (c_int32, [CFG]),
     "tapenv_reset": (c_int, [CFG, P, P, P, P, P]),
+    "tapenv_initial_mask": (c_int, [CFG, P, P, P, P]),
     "tapenv_update_dynamic": (c_int, [CFG, P, P, P, P, P]),
     "tapenv_update_mask": (c_int, [CFG, P, P, P, P, P, P]),
     "tapenv_add_blocks": (c_int, [CFG, P, P, P, P]),
@@ -52,7 +53,7 @@ SYMBOLS = {
 
 
 def _load():
-    path = _build.LIB_PATH
+    path = os.environ.get("TAPENV_LIB") or _build.LIB_PATH      # TAPENV_LIB: a tuning variant built by build.build(out=...)
     if not os.path.exists(path):
         raise ImportError(
             "tapenv: %s is missing -- build it with `python __graft_entry__.py build` "
@@ -66,6 +67,12 @@ def _load():
 
 
 lib = _load()
+
+
+def limits():
+    out = Limits()
+    lib.tapenv_get_limits(C.byref(out))
+    return out
 
 
 class TapEnvError(ValueError):

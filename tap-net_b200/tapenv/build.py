@@ -39,14 +39,16 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into lib/libtapenv.so.  Returns the library path."""
-    if not force and not _stale():
-        return LIB_PATH
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into lib/libtapenv.so.  Returns the library path.
+    `defines` / `out` build tuning variants (e.g. TAPENV_WARPS_PER_CTA=8) next to the default library."""
+    path = LIB_PATH if out is None else os.path.join(LIB_DIR, out)
+    if out is None and not force and not _stale():
+        return path
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", path] + sources()
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return path
 
 
 if __name__ == "__main__":

@@ -14,11 +14,12 @@ def rotate_types(dim, allow_rot=True):
 
 
 def make_config(batch, blocks_num, container_size, reward_type="C+P+S-lb-soft", heightmap_type="diff",
-                packing_strategy="LB_GREEDY", input_type="bot", allow_rot=True):
+                packing_strategy="LB_GREEDY", input_type="bot", allow_rot=True, capacity=None):
     """Returns a validated _capi.Config.  Raises TapEnvError (a ValueError) on unknown enum strings or
     shapes beyond the compiled limits -- the reference would print '... OHHH' and die on a NameError."""
     size = tuple(int(v) for v in container_size)
-    key = (int(batch), int(blocks_num), size, reward_type, heightmap_type, packing_strategy, input_type, bool(allow_rot))
+    key = (int(batch), int(blocks_num), size, reward_type, heightmap_type, packing_strategy, input_type, bool(allow_rot),
+           None if capacity is None else int(capacity))
     cfg = _cache.get(key)
     if cfg is None:
         cfg = _capi.Config()
@@ -26,6 +27,9 @@ def make_config(batch, blocks_num, container_size, reward_type="C+P+S-lb-soft", 
         _capi.check(_capi.lib.tapenv_config_init(C.byref(cfg), key[0], key[1], len(size), 1 if allow_rot else 0, arr,
                                                  reward_type.encode(), packing_strategy.encode(),
                                                  heightmap_type.encode(), input_type.encode()), "config")
+        if capacity is not None:                       # the container outlives the network window (rolling.py:702-703)
+            cfg.capacity = int(capacity)
+            _capi.check(_capi.lib.tapenv_config_check(C.byref(cfg)), "config")
         if len(_cache) > 256:
             _cache.clear()
         _cache[key] = cfg

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .config import make_config
+from .config import make_config, rotate_types
 from .ops import _dev, _p, _stream
 
 
@@ -25,18 +25,25 @@ class BatchedContainers(object):
 
     def __init__(self, container_size, blocks_num, reward_type, heightmap_type="full", initial_container_size=None,
                  max_height=None, packing_strategy="LB_GREEDY", batch_size=1, device=None, input_type="bot",
-                 allow_rot=True):
+                 allow_rot=True, window=None):
         if not torch.cuda.is_available():
             raise RuntimeError("tapenv: a CUDA device is required (no CPU fallback exists)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.container_size = [int(v) for v in container_size]
         self.block_dim = len(self.container_size)
-        self.blocks_num = int(blocks_num)
+        self.blocks_num = int(blocks_num)           # capacity of one container (tools.py:3611 blocks_num)
         self.batch_size = int(batch_size)
         self.reward_type = reward_type
         self.heightmap_type = heightmap_type
-        self.cfg = make_config(batch_size, blocks_num, container_size, reward_type, heightmap_type, packing_strategy,
-                               input_type, allow_rot)
+        # `window`: blocks the NETWORK sees per decode step (rows/columns of static/dynamic/mask).  It equals blocks_num
+        # in training; rolling inference keeps one container of total_blocks_num behind a window of net_blocks_num
+        # (rolling.py:702-703).  A container used without tensors (add_new_blocks only) may exceed the tensor limits.
+        R = rotate_types(len(self.container_size), allow_rot)
+        if window is None:
+            window = self.blocks_num if self.blocks_num * R <= _capi.limits().max_candidates else 1
+        self.window = int(window)
+        self.cfg = make_config(batch_size, self.window, container_size, reward_type, heightmap_type, packing_strategy,
+                               input_type, allow_rot, capacity=self.blocks_num)
         self.packing_strategy = "MACS" if self.cfg.strategy == _capi.MACS else packing_strategy
         self.S = self.cfg.blocks_num * self.cfg.rotate_types
         self.enc_len = int(_capi.lib.tapenv_encoded_heightmap_len(C.byref(self.cfg)))
@@ -125,6 +132,19 @@ class BatchedContainers(object):
         with torch.cuda.device(self.device):
             _capi.check(_capi.lib.tapenv_reset(C.byref(self.cfg), _p(self.state), _p(dynamic), _p(cur), _p(mask),
                                                _stream()), "reset")
+        return cur, mask
+
+    def initial_mask(self, dynamic):
+        """The accessibility masks of a freshly (re)filled window, container untouched (model.py:297-307,
+        rolling.py:325-335) -> (current_mask, mask)."""
+        dynamic = _dev(dynamic, "dynamic", torch.float32)
+        B = self.batch_size
+        if tuple(dynamic.shape) != (B, self.cfg.dyn_rows, self.S):
+            raise _capi.TapEnvError(_capi.ESHAPE, "dynamic %s" % (tuple(dynamic.shape),))
+        cur = torch.empty(B, self.S, dtype=torch.float32, device=self.device)
+        mask = torch.empty_like(cur)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_initial_mask(C.byref(self.cfg), _p(dynamic), _p(cur), _p(mask), _stream()), "initial_mask")
         return cur, mask
 
     def add_new_blocks(self, blocks):
@@ -244,7 +264,10 @@ class Container(object):
         if _batch is not None:
             self._adopt(_batch)
             return
-        cfg = make_config(1, blocks_num, container_size, reward_type, heightmap_type, packing_strategy)   # validates the strings
+        R = rotate_types(len(container_size), True)
+        n_eff = int(blocks_num) if int(blocks_num) * R <= _capi.limits().max_candidates else 1
+        cfg = make_config(1, n_eff, container_size, reward_type, heightmap_type, packing_strategy,
+                          capacity=int(blocks_num))                                                 # validates the strings
         self.container_size = [int(v) for v in container_size]
         self.block_dim = len(self.container_size)
         self.blocks_num = int(blocks_num)

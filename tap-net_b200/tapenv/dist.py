@@ -59,3 +59,29 @@ def gather_rewards(reward, group=None):
     out = torch.empty(world * reward.numel(), dtype=reward.dtype, device=reward.device)
     dist.all_gather_into_tensor(out, reward.contiguous(), group=group)
     return out
+
+
+class RewardReducer(object):
+    """Runs combine_partial_sums on a side stream so the (latency-bound, 24-byte) exchange overlaps the next
+    episode's kernels: nothing on the environment path waits for it -- only the trainer's loss does.
+
+        red = RewardReducer(device)
+        total, done = red.reduce_async(sums)      # sums: f64 [3] produced on the current stream
+        ...                                       # keep stepping environments
+        done.synchronize()  /  torch.cuda.current_stream().wait_event(done)   # before `total` (or `sums`) is reused
+    """
+
+    def __init__(self, device, group=None):
+        self.device = torch.device(device)
+        self.group = group
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def reduce_async(self, sums):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            total = combine_partial_sums(sums, self.group)
+            done.record(self.stream)
+        return total, done

@@ -339,3 +339,43 @@ def test_install_patches_reference_modules():
     assert pack.update_dynamic is tapenv.update_dynamic and tools.Container is tapenv.Container
     tapenv.uninstall()
     assert pack.update_mask == "orig" and tools.Container == "orig"
+
+
+def test_rolling_style_container_outlives_the_window():
+    """rolling.py:702-703 keeps ONE container (blocks_num = total 50, H = 250) while the network window stays at 10:
+    5 windows of 10 RAND-3D blocks, masks re-initialised per window (rolling.py:325-335), state never cleared."""
+    torch = _torch()
+    import tapenv
+    from oracle import oracle
+    B, n, dim, size, total = 96, 10, 3, [5, 5, 250], 50
+    static_all, dynamic_all = load_inputs("rand3d_n10.npz", 5 * B)
+    env = tapenv.BatchedContainers(size, total, "C+P+S-lb-soft", "diff", batch_size=B, window=n)
+    conts = [oracle.Container(size, total, "C+P+S-lb-soft", "diff") for _ in range(B)]
+    rng = np.random.RandomState(4)
+    for w in range(5):
+        static, dynamic = static_all[w * B:(w + 1) * B], dynamic_all[w * B:(w + 1) * B]
+        st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+        cur, mask = env.initial_mask(dyn)
+        cur_o, mask_o, dyn_o = oracle.initial_mask(dynamic, n, 6), np.ones((B, 60), np.float32), dynamic
+        assert np.array_equal(cur.cpu().numpy(), cur_o)
+        for t in range(n):
+            u = rng.random_sample((B, 60)) * (cur_o > 0)
+            ptr = np.argmax(u, axis=1).astype(np.int64)
+            dyn, cur, mask, dec_static, dec_dyn = env.step(torch.from_numpy(ptr).cuda(), st, dyn, mask)
+            dyn_o = oracle.update_dynamic(dyn_o, static, ptr)
+            cur_o, mask_o = oracle.update_mask(mask_o, dyn_o, static, ptr)
+            blocks = static[np.arange(B)[:, None], 1 + np.arange(dim)[None, :], ptr[:, None]]
+            enc = np.stack([conts[b].add_new_block(blocks[b]).reshape(-1) for b in range(B)])
+            assert np.array_equal(dec_dyn.cpu().numpy().reshape(B, -1), enc.astype(np.float32)), (w, t)
+            assert np.array_equal(cur.cpu().numpy(), cur_o) and np.array_equal(mask.cpu().numpy(), mask_o)
+    assert int(env.current_blocks_num.min()) == total and (env.flags.cpu().numpy() == 0).all()
+    assert np.array_equal(env.positions.cpu().numpy(), np.stack([c.positions for c in conts]))
+    assert np.array_equal(env.heightmap.cpu().numpy().reshape(B, -1), np.stack([c.heightmap.reshape(-1) for c in conts]))
+    want = np.array([c.calc_ratio() for c in conts])
+    assert np.array_equal(env.calc_ratio().cpu().numpy(), want.astype(np.float32))
+    # the stand-alone reference-style object with blocks_num = 50 (rolling.py:702)
+    one = tapenv.Container(size, total, "C+P+S-lb-soft", "diff")
+    ref1 = oracle.Container(size, total, "C+P+S-lb-soft", "diff")
+    for i in range(12):
+        blk = static_all[i, 1:4, i % 60]
+        assert np.array_equal(one.add_new_block(blk), ref1.add_new_block(blk))
