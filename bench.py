@@ -38,7 +38,16 @@ WORKLOADS = {
     # reference raises IndexError; placements are identical for any height that is not reached
     "c4": ("ppsg2d_n20.npz", [7, 100], "C+P+S-mcs-hard", "diff", "MACS", 1024,
            "2D PPSG nodes=20 width=7 height=100 MACS C+P+S-mcs-hard batch=8192/8 per GPU (BASELINE configs[3])"),
+    # rolling-style: ONE container [5,5,250] takes 50 blocks while the network window stays at 10 (rolling.py:702-703).
+    # Driven by 5 consecutive 10-block RAND-3D windows per environment (the reference's per-step networkx window refill
+    # is host-side, batch-1 code -- SURVEY.md section 8f N1); masks re-initialised per window, state never cleared.
+    "c5": ("rand3d_n10.npz", [5, 5, 250], "C+P+S-lb-soft", "diff", "LB_GREEDY", 8192,
+           "3D rolling-style total=50 window=10 width=5 height=250 LB_GREEDY batch=65536/8 per GPU (BASELINE configs[4])"),
 }
+WINDOWS = {"c5": 5}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel at the workload's default batch, from the
+# `ncu --set full` captures summarised under profiles/ (writes stay in the 126 MB L2 at these sizes)
+TRAFFIC = {"c2": 11.34e6}
 
 
 def algorithmic_bytes_per_env_step(n, R, dim, W, L, macs):
@@ -51,12 +60,14 @@ def algorithmic_bytes_per_env_step(n, R, dim, W, L, macs):
 
 
 def load_workload(name, batch, rank):
+    """-> static [Wn,B,1+dim,S], dynamic [Wn,B,3n,S] (Wn = windows per episode, 1 except for the rolling-style c5)."""
     from tests.golden_io import load_inputs
     fixture, size, rt, hm, strat, default_b, desc = WORKLOADS[name]
     B = batch or default_b
     static, dynamic = load_inputs(fixture)
     pool = static.shape[0]
-    idx = (np.arange(B) + rank * 977) % pool         # tile the pool; ranks start at different offsets
+    Wn = WINDOWS.get(name, 1)
+    idx = (np.arange(Wn)[:, None] * 389 + np.arange(B)[None, :] + rank * 977) % pool   # tile the pool; ranks / windows start at different offsets
     return np.ascontiguousarray(static[idx]), np.ascontiguousarray(dynamic[idx]), size, rt, hm, strat, B, desc, pool
 
 
@@ -118,27 +129,11 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (the Python reference cannot travel to the GPU box)
 # ----------------------------------------------------------------------------------------------
-def cpu_episode_rate(static, dynamic, ptr_seq, size, rt, hm, strat, threads, min_seconds, max_reps=10000):
-    """Times oracle.episode_batch (update_dynamic + update_mask + add_new_block per env-step, calc_ratio per
-    episode -- model.py:376-453,:509-510 restated in C) over the whole batch, repeated for >= min_seconds."""
-    from oracle import oracle
-    oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        o = oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
-        assert o["status"] == 0
-        reps += 1
-        el = time.perf_counter() - t0
-        if el >= min_seconds or reps >= max_reps:
-            break
-    steps = reps * static.shape[0] * ptr_seq.shape[0]
-    return steps / el, el, reps
-
-
 def host_policy(static, dynamic, size, seed):
-    """Recorded random-valid policy for the CPU arm (checker-side code: uses the oracle's mask functions)."""
+    """Recorded random-valid policy for the CPU arm (checker-side code: uses the oracle's mask functions).
+    static/dynamic carry the window axis; returns ptr_seq [Wn, n, B]."""
     from tests.rollout import random_valid_ptrs
-    return random_valid_ptrs(static, dynamic, size, seed=seed)
+    return np.stack([random_valid_ptrs(static[w], dynamic[w], size, seed=seed + w) for w in range(static.shape[0])])
 
 
 def run_reference(args):
@@ -148,23 +143,24 @@ def run_reference(args):
     static, dynamic, size, rt, hm, strat, B, desc, pool = load_workload(args.workload, args.batch, 0)
     threads = os.cpu_count() or 1
     ptr_seq = host_policy(static, dynamic, size, seed=1234)
-    n = ptr_seq.shape[0]
+    Wn, n = ptr_seq.shape[0], ptr_seq.shape[1]
     from oracle import oracle
+    kw = dict(nthreads=threads, want=("reward",), capacity=Wn * n)
     for _ in range(max(args.warmup, 1)):
-        oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+        oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, **kw)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o = oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, nthreads=threads, want=("reward",))
+        o = oracle.episode_batch(static, dynamic, ptr_seq, size, rt, hm, strat, **kw)
     el = time.perf_counter() - t0
-    value = args.steps * B * n / el
+    value = args.steps * B * n * Wn / el
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32 state + f64 score", "data": "synthetic",
-        "config": {"workload": desc, "batch": B, "blocks": n, "env_steps_per_step": B * n,
+        "config": {"workload": desc, "batch": B, "blocks": n * Wn, "env_steps_per_step": B * n * Wn,
                    "inputs": "reference RAND/PPSG generator fixtures (tests/golden), pool of %d tiled" % pool},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d episodes x %d envs x %d steps, oracle/tap_oracle.c on %d pthreads" % (args.steps, B, n, threads)},
+                         "sample": "%d episodes x %d envs x %d steps, oracle/tap_oracle.c on %d pthreads" % (args.steps, B, n * Wn, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is pure Python/NumPy and /root/reference is not on the GPU box: this arm times the C "
                 "restatement (oracle/) of the same per-step path on all host threads; the Python reference itself "
@@ -195,43 +191,44 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     static_h, dynamic_h, size, rt, hm, strat, B, desc, pool = load_workload(args.workload, args.batch, rank)
+    Wn = static_h.shape[0]
     dim = len(size)
     R = 2 if dim == 2 else 6
-    S = static_h.shape[2]
+    S = static_h.shape[3]
     n = S // R
     macs = strat == "MACS" or "mcs" in rt
     bytes_step = algorithmic_bytes_per_env_step(n, R, dim, size[0], size[1] if dim == 3 else 1, macs)
+    steps_per_episode = Wn * n
 
     # ring of RING distinct input sets (same instances, rotated) so every episode reads its inputs from HBM,
     # not from a warm L2: RING * (inputs + ping-pong outputs) >> 126 MB
     per_set = static_h.nbytes + dynamic_h.nbytes
-    RING = max(2, int(np.ceil(400e6 / (3 * per_set))))
-    env = tapenv.BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=B, device=dev)
+    RING = max(1 if per_set > 300e6 else 2, int(np.ceil(400e6 / (3 * per_set))))
+    env = tapenv.BatchedContainers(size, Wn * n, rt, hm, packing_strategy=strat, batch_size=B, device=dev, window=n)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     # record the policy once (untimed): ptr ~ multinomial(current_mask)
     st0 = torch.from_numpy(static_h).to(dev)
     dyn0 = torch.from_numpy(dynamic_h).to(dev)
-    cur, mask = env.reset(dyn0)
-    dyn = dyn0
     ptrs = []
-    for t in range(n):
-        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
-        dyn, cur, mask, _, _ = env.step(ptr, st0, dyn, mask)
-        ptrs.append(ptr)
-    ptr_seq0 = torch.stack(ptrs)
+    for w in range(Wn):
+        cur, mask = env.reset(dyn0[w]) if w == 0 else env.initial_mask(dyn0[w])
+        dyn = dyn0[w]
+        for t in range(n):
+            ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+            dyn, cur, mask, _, _ = env.step(ptr, st0[w], dyn, mask)
+            ptrs.append(ptr)
+    ptr_seq0 = torch.stack(ptrs).view(Wn, n, B)
     reward_ref = env.calc_ratio().clone()
     env.check_flags()
 
     runners = []
     for i in range(RING):
         roll = (i * 131) % B
-        st = torch.roll(st0, roll, 0).contiguous()
-        dy = torch.roll(dyn0, roll, 0).contiguous()
-        pq = torch.roll(ptr_seq0, roll, 1).contiguous()
+        st = torch.roll(st0, roll, 1).contiguous()
+        dy = torch.roll(dyn0, roll, 1).contiguous()
+        pq = torch.roll(ptr_seq0, roll, 2).contiguous()
         runners.append(tapenv.EpisodeRunner(env, st, dy, pq, use_graph=not args.no_graph, partial_sums=True))
-    sums_total = torch.zeros(3, dtype=torch.float64, device=dev)
-
     reducer = tapenv.dist.RewardReducer(dev) if world > 1 else None
 
     def episode(i):
@@ -275,23 +272,28 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     span_ms_max = float(tt.item())
-    value = world * B * n * args.steps / (span_ms_max * 1e-3)
+    value = world * B * steps_per_episode * args.steps / (span_ms_max * 1e-3)
     launches = args.steps * runners[0].launches_per_episode
 
     # ---- timed region 2: roofline of the dominant kernel (the fused step), cold inputs ---------------
-    # M launches back to back, each on a different ring slot (21 MB per launch at c2), events on the launching stream
-    out_bufs = [(torch.empty_like(dyn0), torch.empty(B, S, device=dev), torch.empty(B, S, device=dev),
-                 torch.empty(B, dim, device=dev), torch.empty(B, env.enc_len, device=dev)) for _ in range(RING)]
+    # graph-replayed launches, each on a different (window, ring slot) input set, events on the launching stream
+    slots = [(r, w) for r in runners for w in range(Wn)]
+    nl = min(len(slots), n)                                # launches per replay (k stays < capacity between clears)
+    out_bufs = [(torch.empty_like(dyn0[0]), torch.empty(B, S, device=dev), torch.empty(B, S, device=dev),
+                 torch.empty(B, dim, device=dev), torch.empty(B, env.enc_len, device=dev)) for _ in range(nl)]
     mask1 = torch.ones(B, S, device=dev)
-    nl = min(RING, n)                                      # launches per replay (k stays < n between clears)
+
+    def roof_launches():
+        for i in range(nl):
+            r, w = slots[i]
+            env.step(r.ptr_seq[w, 0], r.static[w], r.dynamic[w], mask1, out=out_bufs[i])
+
     env.clear_container()
-    for i in range(nl):                                    # warm-up outside capture
-        env.step(runners[i].ptr_seq[0], runners[i].static, runners[i].dynamic, mask1, out=out_bufs[i])
+    roof_launches()                                        # warm-up outside capture
     torch.cuda.synchronize(dev)
     rg = torch.cuda.CUDAGraph()                            # the launches are replayed from a graph so that the
     with torch.cuda.graph(rg):                             # host's per-call overhead is not what gets timed
-        for i in range(nl):
-            env.step(runners[i].ptr_seq[0], runners[i].static, runners[i].dynamic, mask1, out=out_bufs[i])
+        roof_launches()
     tot_ms, cnt = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rep in range(12):
@@ -313,7 +315,7 @@ def run_ours(args):
     st_pin = torch.from_numpy(static_h).pin_memory()
     dy_pin = torch.from_numpy(dynamic_h).pin_memory()
     pq_pin = ptr_seq0.cpu().pin_memory()
-    pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph)
+    pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph, windows=Wn)
     after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if world > 1 else None   # in-order here: the host reads the totals
 
     def e2e_run(k):
@@ -335,39 +337,46 @@ def run_ours(args):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * n * args.steps / float(te.item())
+    e2e_value = world * B * steps_per_episode * args.steps / float(te.item())
     assert np.array_equal(rw_pin.numpy(), reward_ref.cpu().numpy())
-
     clocks = sampler.result()
 
     # ---- extra: the whole-episode kernel (K7, tapenv_episode): one launch per episode, no intermediate tensors ----
     k7 = None
-    try:
+    if Wn == 1:
         for _ in range(3):
-            rk = env.episode(st0, dyn0, ptr_seq0)[0]
+            rk = env.episode(st0[0], dyn0[0], ptr_seq0[0])[0]
         assert torch.equal(rk, reward_ref)
         torch.cuda.synchronize(dev)
         e0.record()
-        for _ in range(20):
-            env.episode(runners[_ % RING].static, runners[_ % RING].dynamic, runners[_ % RING].ptr_seq)
+        for i in range(20):
+            r = runners[i % RING]
+            env.episode(r.static[0], r.dynamic[0], r.ptr_seq[0])
         e1.record()
         torch.cuda.synchronize(dev)
         k7 = {"value": B * n * 20 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "ms_per_episode": e0.elapsed_time(e1) / 20,
-              "note": "tapenv_episode: reset + n steps + reward in ONE launch per batch (per GPU), inputs in HBM"}
-    except tapenv.TapEnvError:
-        pass
+              "note": "tapenv_episode: reset + n steps + reward in ONE launch per batch (per GPU), inputs in HBM, eager launches"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle
         threads = os.cpu_count() or 1
         ptr_h = ptr_seq0.cpu().numpy()
-        rate, el, reps = cpu_episode_rate(static_h, dynamic_h, ptr_h, size, rt, hm, strat, threads, args.cpu_seconds)
-        from oracle import oracle
-        o = oracle.episode_batch(static_h, dynamic_h, ptr_h, size, rt, hm, strat, nthreads=threads, want=("reward",))
+        kw = dict(nthreads=threads, want=("reward",), capacity=Wn * n)
+        oracle.episode_batch(static_h, dynamic_h, ptr_h, size, rt, hm, strat, **kw)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            o = oracle.episode_batch(static_h, dynamic_h, ptr_h, size, rt, hm, strat, **kw)
+            assert o["status"] == 0
+            reps += 1
+            el = time.perf_counter() - t0
+            if el >= args.cpu_seconds or reps >= 10000:
+                break
+        rate = reps * B * steps_per_episode / el
         parity = bool(np.array_equal(o["reward"], reward_ref.cpu().numpy()))
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d episodes x %d envs x %d steps = %.1f s of oracle/tap_oracle.c on %d pthreads" % (reps, B, n, el, threads),
+               "sample": "%d episodes x %d envs x %d steps = %.1f s of oracle/tap_oracle.c on %d pthreads" % (reps, B, steps_per_episode, el, threads),
                "reward_parity_vs_gpu": parity,
                "python_reference_1core": "4.9e3 env-steps/s (unmodified tools.py path, build container, BASELINE.md section 2)"}
 
@@ -382,8 +391,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 state + f64 score, f32 tensors", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "blocks": n, "env_steps_per_step": world * B * n,
-                       "step_definition": "one episode = reset + %d fused decode-step launches + reward over the batch" % n,
+            "config": {"workload": desc, "batch_per_gpu": B, "blocks": steps_per_episode, "env_steps_per_step": world * B * steps_per_episode,
+                       "step_definition": "one episode = reset + %d fused decode-step launches%s + reward over the batch"
+                                          % (steps_per_episode, " (%d windows of %d, masks re-initialised per window)" % (Wn, n) if Wn > 1 else ""),
                        "l2": "inputs rotate over a ring of %d distinct batches (%.0f MB incl. ping-pong outputs) > 126 MB L2" % (RING, RING * 3 * per_set / 1e6),
                        "cuda_graph": not args.no_graph,
                        "inputs": "reference RAND/PPSG generator fixtures (tests/golden), pool of %d tiled" % pool,
@@ -394,10 +404,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
                     "api": "tapenv.HostPipeline.submit/result (double-buffered upload + BatchedContainers.reset/step/calc_ratio), pinned host buffers"},
             "episode_kernel": k7,
-            "roofline": {"bound": "hbm", "kernel": "step (fused update_dynamic+update_mask+add_new_block)",
+            "roofline": {"bound": "hbm", "kernel": "step_kernel (fused update_dynamic+update_mask+add_new_block)",
                          "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC.get(args.workload),
                          "algorithmic_bytes_per_env_step": bytes_step, "bytes_per_launch": B * bytes_step,
                          "launch_us": step_us, "launches_timed": cnt},
             "clocks": clocks,

@@ -66,7 +66,7 @@ def lib():
         L.tapo_is_stable_3d_mask.restype = C.c_int
         L.tapo_is_stable_3d_masks.argtypes = [C.c_int, C.c_int, p, C.c_int, p]
         L.tapo_episode_batch.argtypes = ([C.c_int] * 6 + [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
-                                         + [p] * 11 + [C.c_int])
+                                         + [p] * 11 + [C.c_int, C.c_int, C.c_int])
         L.tapo_episode_batch.restype = C.c_int
         _lib = L
     return _lib
@@ -234,18 +234,23 @@ def initial_mask(dynamic, n, R):
 
 def episode_batch(static, dynamic, ptr_seq, container_size, reward_type, heightmap_type="diff",
                   packing_strategy="LB_GREEDY", nthreads=1, want=("heightmap", "positions", "stable", "reward",
-                                                                  "cur_mask", "mask", "dynamic", "dec_dyn")):
+                                                                  "cur_mask", "mask", "dynamic", "dec_dyn"),
+                  capacity=None):
     """Run whole episodes for a batch on the CPU oracle (the timed CPU baseline).
 
-    static [B,1+dim,S] f32, dynamic [B,3n,S] f32, ptr_seq [steps,B] int64."""
+    static [B,1+dim,S] f32, dynamic [B,3n,S] f32, ptr_seq [steps,B] int64 -- or, rolling-style, the same with a
+    leading window axis ([Wn,B,...], [Wn,B,...], [Wn,steps,B]) and `capacity` blocks per container."""
     static = np.ascontiguousarray(static, dtype=np.float32)
     dynamic = np.ascontiguousarray(dynamic, dtype=np.float32)
     ptr_seq = np.ascontiguousarray(ptr_seq, dtype=np.int64)
-    B, srows, S = static.shape
+    if static.ndim == 3:
+        static, dynamic, ptr_seq = static[None], dynamic[None], ptr_seq[None]
+    nwin, B, srows, S = static.shape
     dim = srows - 1
     R = rotate_types(dim)
     n = S // R
-    steps = ptr_seq.shape[0]
+    steps = ptr_seq.shape[1]
+    cap = int(capacity) if capacity is not None else max(n, nwin * steps)
     W = int(container_size[0])
     Ln = int(container_size[1]) if dim == 3 else 1
     H = int(container_size[-1])
@@ -254,8 +259,8 @@ def episode_batch(static, dynamic, ptr_seq, container_size, reward_type, heightm
     enc = (W - 1 if hm_t == 2 else W) if dim == 2 else (2 * cells if hm_t == 2 else cells)
     o = {}
     if "heightmap" in want: o["heightmap"] = np.zeros((B, cells), np.int32)
-    if "positions" in want: o["positions"] = np.zeros((B, n, dim), np.int32)
-    if "stable" in want: o["stable"] = np.zeros((B, n), np.uint8)
+    if "positions" in want: o["positions"] = np.zeros((B, cap, dim), np.int32)
+    if "stable" in want: o["stable"] = np.zeros((B, cap), np.uint8)
     if "reward" in want: o["reward"] = np.zeros((B,), np.float32)
     if "cur_mask" in want: o["cur_mask"] = np.zeros((B, S), np.float32)
     if "mask" in want: o["mask"] = np.zeros((B, S), np.float32)
@@ -265,7 +270,7 @@ def episode_batch(static, dynamic, ptr_seq, container_size, reward_type, heightm
                                   B, steps, _ptr(static), _ptr(dynamic), _ptr(ptr_seq),
                                   _ptr(o.get("heightmap")), _ptr(o.get("positions")), _ptr(o.get("stable")),
                                   _ptr(o.get("reward")), _ptr(o.get("cur_mask")), _ptr(o.get("mask")),
-                                  _ptr(o.get("dynamic")), _ptr(o.get("dec_dyn")), int(nthreads))
+                                  _ptr(o.get("dynamic")), _ptr(o.get("dec_dyn")), int(nthreads), int(nwin), int(cap))
     o["status"] = st
     return o
 

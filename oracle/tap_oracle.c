@@ -830,6 +830,7 @@ void tapo_update_mask(const float *mask, const float *dynamic, const int64_t *pt
  * Returns 0, or the first non-zero env error. */
 typedef struct {
     int dim, W, L, H, n, R, hm_type, strategy, B, steps, b0, b1, status;
+    int nwin, cap;   /* rolling-style: nwin windows of n blocks into ONE container of capacity cap (rolling.py:702-703) */
     const char *reward_type;
     const float *static_, *dynamic; const int64_t *ptr_seq;
     int *heightmap_out, *pos_out; unsigned char *stable_out; float *reward_out;
@@ -842,29 +843,31 @@ static void *ep_worker(void *arg) {
     const int S = n * R, rows = 3 * n, srows = 1 + dim;
     const int cells = dim == 2 ? W : W * L;
     const int enc = dim == 2 ? (j->hm_type == TAPO_HM_DIFF ? W - 1 : W) : (j->hm_type == TAPO_HM_DIFF ? 2 * W * L : W * L);
-    tapo_env *e = tapo_env_new(dim, W, L, j->H, n, j->reward_type, j->hm_type, j->strategy);
+    tapo_env *e = tapo_env_new(dim, W, L, j->H, j->cap, j->reward_type, j->hm_type, j->strategy);
     if (!e) { j->status = 2; return NULL; }
     float *da = (float *)malloc(sizeof(float) * rows * S), *db = (float *)malloc(sizeof(float) * rows * S);
     float *m = (float *)malloc(sizeof(float) * S), *cm = (float *)malloc(sizeof(float) * S), *nm = (float *)malloc(sizeof(float) * S);
     int *hm = (int *)calloc(2 * cells + 4, sizeof(int));
     for (int b = j->b0; b < j->b1; b++) {
         tapo_env_clear(e);                                           /* model.py:294 */
-        const float *st = j->static_ + (size_t)b * srows * S;
-        memcpy(da, j->dynamic + (size_t)b * rows * S, sizeof(float) * rows * S);
-        tapo_update_mask(NULL, da, NULL, 1, rows, S, n, R, nm, m);  /* model.py:297-307; m = ones */
-        for (int t = 0; t < j->steps; t++) {
-            int64_t p = j->ptr_seq[(size_t)t * B + b];
-            tapo_update_dynamic(da, st, &p, 1, rows, S, srows, n, 3, db);      /* model.py:376 */
-            tapo_update_mask(m, db, &p, 1, rows, S, n, R, nm, cm);             /* model.py:384 */
-            memcpy(m, cm, sizeof(float) * S);
-            float blk[3]; for (int d = 0; d < dim; d++) blk[d] = st[(size_t)(1 + d) * S + p];   /* model.py:404-412 */
-            tapo_env_add_new_block(e, blk, hm);                                /* model.py:453 */
-            float *tsw = da; da = db; db = tsw;
+        for (int w = 0; w < j->nwin; w++) {
+            const float *st = j->static_ + ((size_t)w * B + b) * srows * S;
+            memcpy(da, j->dynamic + ((size_t)w * B + b) * rows * S, sizeof(float) * rows * S);
+            tapo_update_mask(NULL, da, NULL, 1, rows, S, n, R, nm, m);  /* model.py:297-307; m = ones */
+            for (int t = 0; t < j->steps; t++) {
+                int64_t p = j->ptr_seq[((size_t)w * j->steps + t) * B + b];
+                tapo_update_dynamic(da, st, &p, 1, rows, S, srows, n, 3, db);      /* model.py:376 */
+                tapo_update_mask(m, db, &p, 1, rows, S, n, R, nm, cm);             /* model.py:384 */
+                memcpy(m, cm, sizeof(float) * S);
+                float blk[3]; for (int d = 0; d < dim; d++) blk[d] = st[(size_t)(1 + d) * S + p];   /* model.py:404-412 */
+                tapo_env_add_new_block(e, blk, hm);                                /* model.py:453 */
+                float *tsw = da; da = db; db = tsw;
+            }
         }
         if (e->error && !j->status) j->status = e->error;
         if (j->heightmap_out) memcpy(j->heightmap_out + (size_t)b * cells, e->heightmap, sizeof(int) * cells);
-        if (j->pos_out) memcpy(j->pos_out + (size_t)b * n * dim, e->positions, sizeof(int) * n * dim);
-        if (j->stable_out) memcpy(j->stable_out + (size_t)b * n, e->stable, n);
+        if (j->pos_out) memcpy(j->pos_out + (size_t)b * j->cap * dim, e->positions, sizeof(int) * j->cap * dim);
+        if (j->stable_out) memcpy(j->stable_out + (size_t)b * j->cap, e->stable, j->cap);
         if (j->reward_out) j->reward_out[b] = (float)tapo_env_calc_ratio(e);   /* model.py:509-510 */
         if (j->cur_mask_out) memcpy(j->cur_mask_out + (size_t)b * S, nm, sizeof(float) * S);
         if (j->mask_out) memcpy(j->mask_out + (size_t)b * S, m, sizeof(float) * S);
@@ -878,7 +881,10 @@ static void *ep_worker(void *arg) {
 int tapo_episode_batch(int dim, int W, int L, int H, int n, int R, const char *reward_type, int hm_type, int strategy,
                        int B, int steps, const float *static_, const float *dynamic, const int64_t *ptr_seq,
                        int *heightmap_out, int *pos_out, unsigned char *stable_out, float *reward_out,
-                       float *cur_mask_out, float *mask_out, float *dynamic_out, int *dec_dyn_out, int nthreads) {
+                       float *cur_mask_out, float *mask_out, float *dynamic_out, int *dec_dyn_out, int nthreads,
+                       int nwin, int cap) {
+    if (nwin < 1) nwin = 1;
+    if (cap < n) cap = n;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > B) nthreads = B > 0 ? B : 1;
     if (nthreads > 1024) nthreads = 1024;
@@ -888,7 +894,7 @@ int tapo_episode_batch(int dim, int W, int L, int H, int n, int R, const char *r
     for (int t = 0; t < nthreads; t++) {
         ep_job *j = &jobs[t];
         j->dim = dim; j->W = W; j->L = L; j->H = H; j->n = n; j->R = R; j->hm_type = hm_type; j->strategy = strategy;
-        j->B = B; j->steps = steps; j->reward_type = reward_type;
+        j->B = B; j->steps = steps; j->reward_type = reward_type; j->nwin = nwin; j->cap = cap;
         j->b0 = (int)((long long)B * t / nthreads); j->b1 = (int)((long long)B * (t + 1) / nthreads);
         j->static_ = static_; j->dynamic = dynamic; j->ptr_seq = ptr_seq;
         j->heightmap_out = heightmap_out; j->pos_out = pos_out; j->stable_out = stable_out; j->reward_out = reward_out;

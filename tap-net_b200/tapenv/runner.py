@@ -10,17 +10,25 @@ from .containers import BatchedContainers
 
 
 class EpisodeRunner(object):
+    """static [B,rows,S] / dynamic [B,3n,S] / ptr_seq [steps,B]  -- one window per episode (training), or the same
+    tensors with a leading window axis ([Wn,B,...], [Wn,B,...], [Wn,steps,B]) for rolling-style episodes in which ONE
+    container keeps filling while the network window is refilled Wn times (rolling.py:575-658): the container
+    is cleared once, every later window only recomputes the masks (BatchedContainers.initial_mask)."""
+
     def __init__(self, env, static, dynamic, ptr_seq, use_graph=False, partial_sums=True):
         assert isinstance(env, BatchedContainers)
         self.env = env
         dev = env.device
         B, S = env.batch_size, env.S
+        if static.dim() == 3:
+            static, dynamic, ptr_seq = static.unsqueeze(0), dynamic.unsqueeze(0), ptr_seq.unsqueeze(0)
         self.static = static
         self.dynamic = dynamic
-        self.ptr_seq = ptr_seq                        # int64 [steps, B] on device
-        self.steps = int(ptr_seq.shape[0])
+        self.ptr_seq = ptr_seq                        # int64 [Wn, steps, B] on device
+        self.windows = int(ptr_seq.shape[0])
+        self.steps = int(ptr_seq.shape[1])
         f32 = dict(dtype=torch.float32, device=dev)
-        self.dyn_buf = [torch.empty_like(dynamic), torch.empty_like(dynamic)]
+        self.dyn_buf = [torch.empty_like(dynamic[0]), torch.empty_like(dynamic[0])]
         self.cur_buf = [torch.empty(B, S, **f32), torch.empty(B, S, **f32)]
         self.mask_buf = [torch.empty(B, S, **f32), torch.empty(B, S, **f32)]
         self.dec_static = torch.empty(B, env.cfg.static_rows - 1, **f32)
@@ -28,18 +36,19 @@ class EpisodeRunner(object):
         self.reward = None
         self.sums = None
         self.partial_sums = partial_sums
-        self.launches_per_episode = 1 + self.steps + 1 + (1 if partial_sums else 0)
+        self.launches_per_episode = self.windows * (1 + self.steps) + 1 + (1 if partial_sums else 0)
         self.graph = None
         if use_graph:
             self._capture()
 
     def _episode(self):
         env = self.env
-        cur, mask = env.reset(self.dynamic)
-        dyn = self.dynamic
-        for t in range(self.steps):
-            out = (self.dyn_buf[t & 1], self.cur_buf[t & 1], self.mask_buf[t & 1], self.dec_static, self.dec_dyn)
-            dyn, cur, mask, _, _ = env.step(self.ptr_seq[t], self.static, dyn, mask, out=out)
+        for w in range(self.windows):
+            cur, mask = env.reset(self.dynamic[w]) if w == 0 else env.initial_mask(self.dynamic[w])
+            dyn = self.dynamic[w]
+            for t in range(self.steps):
+                out = (self.dyn_buf[t & 1], self.cur_buf[t & 1], self.mask_buf[t & 1], self.dec_static, self.dec_dyn)
+                dyn, cur, mask, _, _ = env.step(self.ptr_seq[w, t], self.static[w], dyn, mask, out=out)
         res = env.calc_ratio(partial_sums=self.partial_sums)
         self.reward, self.sums = res if self.partial_sums else (res, None)
         self.final = (dyn, cur, mask)
@@ -75,7 +84,7 @@ class HostPipeline(object):
         rewards = pipe.result()                                       # pinned f32 [B] of the OLDEST submitted episode
     """
 
-    def __init__(self, env, steps, depth=2, use_graph=True):
+    def __init__(self, env, steps, depth=2, use_graph=True, windows=1):
         self.env = env
         dev = env.device
         B, S = env.batch_size, env.S
@@ -84,9 +93,9 @@ class HostPipeline(object):
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
         for _ in range(depth):
-            st = torch.empty(B, cfg.static_rows, S, dtype=torch.float32, device=dev)
-            dy = torch.empty(B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
-            pq = torch.zeros(steps, B, dtype=torch.int64, device=dev)
+            st = torch.empty(windows, B, cfg.static_rows, S, dtype=torch.float32, device=dev)
+            dy = torch.empty(windows, B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
+            pq = torch.zeros(windows, steps, B, dtype=torch.int64, device=dev)
             runner = EpisodeRunner(env, st, dy, pq, use_graph=use_graph, partial_sums=True)
             self.slots.append(dict(static=st, dynamic=dy, ptr=pq, runner=runner,
                                    uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event(),
@@ -95,7 +104,7 @@ class HostPipeline(object):
         self.head = 0      # next slot to submit into
         self.tail = 0      # oldest slot in flight
         self.inflight = 0
-        self.h2d_bytes = (B * cfg.static_rows * S + B * cfg.dyn_rows * S) * 4 + steps * B * 8
+        self.h2d_bytes = windows * ((B * cfg.static_rows * S + B * cfg.dyn_rows * S) * 4 + steps * B * 8)
         self.d2h_bytes = B * 4 + 24
 
     def submit(self, static_h, dynamic_h, ptr_h, after_episode=None):
@@ -106,9 +115,9 @@ class HostPipeline(object):
         with torch.cuda.stream(self.copy_stream):
             if s["busy"]:
                 self.copy_stream.wait_event(s["consumed"])       # the slot's previous episode has read its inputs
-            s["static"].copy_(static_h, non_blocking=True)
-            s["dynamic"].copy_(dynamic_h, non_blocking=True)
-            s["ptr"].copy_(ptr_h, non_blocking=True)
+            s["static"].copy_(static_h.view_as(s["static"]), non_blocking=True)
+            s["dynamic"].copy_(dynamic_h.view_as(s["dynamic"]), non_blocking=True)
+            s["ptr"].copy_(ptr_h.view_as(s["ptr"]), non_blocking=True)
             s["uploaded"].record(self.copy_stream)
         compute.wait_event(s["uploaded"])
         r = s["runner"].run()
