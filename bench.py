@@ -222,23 +222,35 @@ def run_ours(args):
     reward_ref = env.calc_ratio().clone()
     env.check_flags()
 
+    # multi-GPU: the end-of-episode reduction of the reward statistics feeding the critic baseline (trainer.py:216-225).
+    # Preferred: fused behind the reward kernel over NVLink peer memory (tapenv_reward_allreduce, in the CUDA graph);
+    # otherwise an NCCL all-gather of the f64 triples on a side stream, overlapping the next episode.
+    exchange, reducer, reduction = None, None, "none (single GPU)"
+    if world > 1 and not args.nccl_reduce:
+        try:
+            exchange = tapenv.dist.PeerExchange(dev)
+            reduction = "fused one-shot exchange over NVLink peer memory (tapenv_reward_allreduce), inside the CUDA graph"
+        except Exception as e:                          # no symmetric memory / P2P on this box
+            exchange = None
+            reduction = "PeerExchange unavailable (%s); " % type(e).__name__
+    if world > 1 and exchange is None:
+        reducer = tapenv.dist.RewardReducer(dev)
+        reduction = (reduction if reduction.startswith("PeerExchange") else "") + "NCCL all_gather of the f64 triples on a side stream"
+
     runners = []
     for i in range(RING):
         roll = (i * 131) % B
         st = torch.roll(st0, roll, 1).contiguous()
         dy = torch.roll(dyn0, roll, 1).contiguous()
         pq = torch.roll(ptr_seq0, roll, 2).contiguous()
-        runners.append(tapenv.EpisodeRunner(env, st, dy, pq, use_graph=not args.no_graph, partial_sums=True))
-    reducer = tapenv.dist.RewardReducer(dev) if world > 1 else None
+        runners.append(tapenv.EpisodeRunner(env, st, dy, pq, use_graph=not args.no_graph, partial_sums=True, exchange=exchange))
 
     def episode(i):
         r = runners[i % RING]
-        if world > 1 and getattr(r, "reduced", None) is not None:
+        if reducer is not None and getattr(r, "reduced", None) is not None:
             torch.cuda.current_stream().wait_event(r.reduced)     # the slot's previous sums have been consumed
         r.run()
-        if world > 1:
-            # end-of-episode reduction of the reward statistics feeding the critic baseline (trainer.py:216-225):
-            # all-gather of the per-rank f64 triples on a side stream, overlapping the next episode
+        if reducer is not None:
             r.total, r.reduced = reducer.reduce_async(r.sums)
         return r
 
@@ -315,8 +327,8 @@ def run_ours(args):
     st_pin = torch.from_numpy(static_h).pin_memory()
     dy_pin = torch.from_numpy(dynamic_h).pin_memory()
     pq_pin = ptr_seq0.cpu().pin_memory()
-    pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph, windows=Wn)
-    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if world > 1 else None   # in-order here: the host reads the totals
+    pipe = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph, windows=Wn, exchange=exchange)
+    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if reducer is not None else None   # in-order here: the host reads the totals
 
     def e2e_run(k):
         last = None
@@ -395,7 +407,7 @@ def run_ours(args):
                        "step_definition": "one episode = reset + %d fused decode-step launches%s + reward over the batch"
                                           % (steps_per_episode, " (%d windows of %d, masks re-initialised per window)" % (Wn, n) if Wn > 1 else ""),
                        "l2": "inputs rotate over a ring of %d distinct batches (%.0f MB incl. ping-pong outputs) > 126 MB L2" % (RING, RING * 3 * per_set / 1e6),
-                       "cuda_graph": not args.no_graph,
+                       "cuda_graph": not args.no_graph, "reward_reduction": reduction,
                        "inputs": "reference RAND/PPSG generator fixtures (tests/golden), pool of %d tiled" % pool,
                        "policy": "recorded ptr ~ multinomial(current_mask), seed 1234+rank"},
             "gpu_launches": launches,
@@ -430,6 +442,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="environments per GPU (default: the workload's)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-reduce", action="store_true", help="multi-GPU: reduce the reward statistics with NCCL instead of the fused peer-memory exchange")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -195,6 +195,25 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
 int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out,
                   double *partial_sums_out, void *stream);
 
+/* K6 fused with its collective: Container.calc_ratio for every environment, the deterministic per-rank
+ * (sum r, sum r^2, count) AND the cross-GPU reduction of those triples in the SAME launch sequence, over
+ * NVLink peer memory instead of a separate NCCL call (the statistics feed the critic baseline,
+ * trainer.py:216-225; the reference is single-process and has no collective to cite).
+ *   comm: every rank allocates tapenv_comm_bytes() of zero-initialised, peer-mapped device memory (e.g.
+ *         torch symmetric memory) and passes ALL ranks' base pointers, own rank included, in rank order.
+ *   Each call posts this rank's triple into every peer's buffer (st + fence + sequence flag), waits for
+ *   the triples of all ranks for the same call number and sums them IN RANK ORDER: total_sums_out f64 [3] is
+ *   bit-identical on every rank.  All ranks must issue the same sequence of calls.  Stream-ordered, capturable
+ *   in a CUDA graph (the call counter lives in device memory). */
+#define TAPENV_COMM_MAX_RANKS 8
+typedef struct tapenv_peer_comm {
+    int32_t world, rank;
+    void *peer[TAPENV_COMM_MAX_RANKS];
+} tapenv_peer_comm;
+size_t tapenv_comm_bytes(void);
+int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *reward_out, double *partial_sums_out,
+                            double *total_sums_out, const tapenv_peer_comm *comm, void *stream);
+
 /* Whole-episode entry (tools.calc_positions_lb_greedy tools.py:2393-2449,
  * calc_positions_mcs :3213-3315, pack.reward pack.py:378-473): run `steps` decode steps
  * for a known pointer sequence in ONE launch, without materialising the

@@ -522,6 +522,62 @@ __global__ void reward_sums_kernel(int B, const float *__restrict__ reward, doub
     if (threadIdx.x == 0) { out[0] = s1[0]; out[1] = s2[0]; out[2] = (double)B; }
 }
 
+// ------------------------------------------------------------------------------------
+// K6 + collective: per-rank sums, then a one-shot exchange of the 24-byte triples over NVLink peer memory.
+// Exchange buffer of one rank:  slot[kCommDepth][TAPENV_COMM_MAX_RANKS] {double v[3]; u64 seq;}  + u64 call counter.
+// Rank r writes its triple into slot[seq % depth][r] of EVERY rank (plain stores to peer-mapped addresses travel
+// over NVLink/NVSwitch), fences system-wide, then publishes `seq`; every rank polls its OWN buffer, so the only
+// remote traffic is world x 32 bytes of posted writes.  A slot is reused after kCommDepth calls; a rank can only
+// get that far ahead after every peer has consumed the earlier call (each call waits for all peers), so depth 2
+// would already be safe.
+// ------------------------------------------------------------------------------------
+constexpr int kCommDepth = 4;
+struct CommSlot { double v[3]; unsigned long long seq; };
+struct CommBuf { CommSlot slot[kCommDepth][TAPENV_COMM_MAX_RANKS]; unsigned long long calls; unsigned long long pad[7]; };
+
+__global__ void reward_sums_exchange_kernel(int B, const float *__restrict__ reward, double *__restrict__ out,
+                                            double *__restrict__ total, tapenv_peer_comm comm) {
+    __shared__ double s1[1024], s2[1024];
+    __shared__ unsigned long long seq_sh;
+    grid_dependency_sync();
+    double a = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) { const double r = (double)reward[i]; a += r; q += r * r; }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = q;
+    __syncthreads();
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) { s1[threadIdx.x] += s1[threadIdx.x + w]; s2[threadIdx.x] += s2[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    CommBuf *mine = reinterpret_cast<CommBuf *>(comm.peer[comm.rank]);
+    if (threadIdx.x == 0) {
+        if (out) { out[0] = s1[0]; out[1] = s2[0]; out[2] = (double)B; }
+        seq_sh = ++mine->calls;
+    }
+    __syncthreads();
+    const unsigned long long seq = seq_sh;
+    const int r = threadIdx.x;
+    if (r < comm.world) {
+        // post my triple into peer r's buffer
+        CommSlot *dst = &reinterpret_cast<CommBuf *>(comm.peer[r])->slot[seq % kCommDepth][comm.rank];
+        dst->v[0] = s1[0]; dst->v[1] = s2[0]; dst->v[2] = (double)B;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&dst->seq) = seq;
+        // wait for peer r's triple in MY buffer
+        volatile CommSlot *src = &mine->slot[seq % kCommDepth][r];
+        long long spins = 0;
+        while (src->seq != seq && spins < (1ll << 25)) { __nanosleep(128); ++spins; }   // ~5 s: a peer that never calls must not hang the GPU
+        __threadfence_system();
+        const bool ok = src->seq == seq;
+        s1[32 + r] = ok ? src->v[0] : nan(""); s2[32 + r] = ok ? src->v[1] : nan(""); s1[64 + r] = ok ? src->v[2] : nan("");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && total) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < comm.world; ++k) { t0 += s1[32 + k]; t1 += s2[32 + k]; t2 += s1[64 + k]; }   // rank order
+        total[0] = t0; total[1] = t1; total[2] = t2;
+    }
+}
+
 // fast path needs 128-bit rows and 16-byte aligned tensors
 static bool fast_ok(const DevCfg &d, const void *a, const void *b) {
     const uintptr_t al = (uintptr_t)a | (uintptr_t)b;
@@ -760,6 +816,24 @@ int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out
     const StatePtrs st = stateptrs_of(cfg, const_cast<void *>(state));
     if (d.B > 0) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
     if (partial_sums_out) launch(reward_sums_kernel, 1, 1024, s, d.B, reward_out, partial_sums_out);
+    return launch_status();
+}
+
+size_t tapenv_comm_bytes(void) { return sizeof(CommBuf); }
+
+int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *reward_out, double *partial_sums_out,
+                            double *total_sums_out, const tapenv_peer_comm *comm, void *stream) {
+    int rc_ = check_cfg(cfg);
+    if (rc_ != TAPENV_OK) return rc_;
+    if (!comm || comm->world < 1 || comm->world > TAPENV_COMM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
+        return TAPENV_EINVAL;
+    for (int r = 0; r < comm->world; ++r) if (!comm->peer[r]) return TAPENV_EINVAL;
+    if (!reward_out || !total_sums_out || (cfg->batch > 0 && !state)) return TAPENV_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevCfg d = devcfg_of(cfg);
+    const StatePtrs st = stateptrs_of(cfg, const_cast<void *>(state));
+    if (d.B > 0) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
+    launch(reward_sums_exchange_kernel, 1, 1024, s, d.B, reward_out, partial_sums_out, total_sums_out, *comm);
     return launch_status();
 }
 

@@ -21,6 +21,10 @@ class StateLayout(C.Structure):  # struct tapenv_state_layout
     _fields_ = [(n, c_size_t) for n in ("scalars", "heightmap", "positions", "blocks", "stable", "flags", "total")]
 
 
+class PeerComm(C.Structure):  # struct tapenv_peer_comm
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("peer", c_void_p * 8)]
+
+
 class Limits(C.Structure):  # struct tapenv_limits
     _fields_ = [(n, c_int32) for n in ("max_width_2d", "max_cells_3d", "max_candidates", "max_blocks")]
 
@@ -48,6 +52,8 @@ SYMBOLS = {
     "tapenv_add_blocks": (c_int, [CFG, P, P, P, P]),
     "tapenv_step": (c_int, [CFG, P, P, P, P, P, P, P, P, P, P, P]),
     "tapenv_reward": (c_int, [CFG, P, P, P, P]),
+    "tapenv_comm_bytes": (c_size_t, []),
+    "tapenv_reward_allreduce": (c_int, [CFG, P, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
 }
 

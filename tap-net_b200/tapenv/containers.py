@@ -186,10 +186,19 @@ class BatchedContainers(object):
                                               _stream()), "step")
         return dyn_out, cur, mask_out, dec_static, self._shape_enc(dec_dyn)
 
-    def calc_ratio(self, partial_sums=False):
+    def calc_ratio(self, partial_sums=False, exchange=None):
         """Container.calc_ratio for every environment -> f32 [B] (tools.py:3908-3966, model.py:509-510).
-        partial_sums=True also returns the f64 [3] (sum r, sum r^2, B) operand of the reward all-reduce."""
+        partial_sums=True also returns the f64 [3] (sum r, sum r^2, B) operand of the reward all-reduce.
+        exchange=<tapenv.dist.PeerExchange>: the cross-GPU reduction is fused behind the reward kernel over NVLink
+        peer memory; returns (reward, local sums, global sums) -- the global sums are identical on every rank."""
         r = torch.empty(self.batch_size, dtype=torch.float32, device=self.device)
+        if exchange is not None:
+            sums = torch.empty(3, dtype=torch.float64, device=self.device)
+            total = torch.empty(3, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                _capi.check(_capi.lib.tapenv_reward_allreduce(C.byref(self.cfg), _p(self.state), _p(r), _p(sums), _p(total),
+                                                              C.byref(exchange.comm), _stream()), "reward_allreduce")
+            return r, sums, total
         sums = torch.empty(3, dtype=torch.float64, device=self.device) if partial_sums else None
         with torch.cuda.device(self.device):
             _capi.check(_capi.lib.tapenv_reward(C.byref(self.cfg), _p(self.state), _p(r), _p(sums), _stream()), "reward")

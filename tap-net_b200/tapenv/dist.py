@@ -85,3 +85,31 @@ class RewardReducer(object):
             total = combine_partial_sums(sums, self.group)
             done.record(self.stream)
         return total, done
+
+
+class PeerExchange(object):
+    """Peer-mapped exchange buffers for tapenv_reward_allreduce (the reward-statistics reduction fused behind the
+    reward kernel, over NVLink peer memory).  One per process group; needs torch symmetric memory (CUDA P2P between
+    the ranks' GPUs on one node).  Raises if that is unavailable -- callers then use combine_partial_sums (NCCL)."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _capi
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            raise ValueError("PeerExchange supports up to 8 ranks (one node)")
+        nbytes = int(_capi.lib.tapenv_comm_bytes())
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                # every rank's buffer is zeroed before anyone posts
+        comm = _capi.PeerComm()
+        comm.world, comm.rank = world, rank
+        ptrs = list(self.handle.buffer_ptrs)
+        for r in range(world):
+            comm.peer[r] = C.c_void_p(int(ptrs[r]))
+        self.comm = comm
+        self.world, self.rank = world, rank

@@ -15,9 +15,11 @@ class EpisodeRunner(object):
     container keeps filling while the network window is refilled Wn times (rolling.py:575-658): the container
     is cleared once, every later window only recomputes the masks (BatchedContainers.initial_mask)."""
 
-    def __init__(self, env, static, dynamic, ptr_seq, use_graph=False, partial_sums=True):
+    def __init__(self, env, static, dynamic, ptr_seq, use_graph=False, partial_sums=True, exchange=None):
         assert isinstance(env, BatchedContainers)
         self.env = env
+        self.exchange = exchange                      # tapenv.dist.PeerExchange: fuse the cross-GPU reward reduction
+        self.total = None
         dev = env.device
         B, S = env.batch_size, env.S
         if static.dim() == 3:
@@ -49,8 +51,11 @@ class EpisodeRunner(object):
             for t in range(self.steps):
                 out = (self.dyn_buf[t & 1], self.cur_buf[t & 1], self.mask_buf[t & 1], self.dec_static, self.dec_dyn)
                 dyn, cur, mask, _, _ = env.step(self.ptr_seq[w, t], self.static[w], dyn, mask, out=out)
-        res = env.calc_ratio(partial_sums=self.partial_sums)
-        self.reward, self.sums = res if self.partial_sums else (res, None)
+        if self.exchange is not None:
+            self.reward, self.sums, self.total = env.calc_ratio(exchange=self.exchange)
+        else:
+            res = env.calc_ratio(partial_sums=self.partial_sums)
+            self.reward, self.sums = res if self.partial_sums else (res, None)
         self.final = (dyn, cur, mask)
 
     def _capture(self):
@@ -84,7 +89,7 @@ class HostPipeline(object):
         rewards = pipe.result()                                       # pinned f32 [B] of the OLDEST submitted episode
     """
 
-    def __init__(self, env, steps, depth=2, use_graph=True, windows=1):
+    def __init__(self, env, steps, depth=2, use_graph=True, windows=1, exchange=None):
         self.env = env
         dev = env.device
         B, S = env.batch_size, env.S
@@ -96,7 +101,7 @@ class HostPipeline(object):
             st = torch.empty(windows, B, cfg.static_rows, S, dtype=torch.float32, device=dev)
             dy = torch.empty(windows, B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
             pq = torch.zeros(windows, steps, B, dtype=torch.int64, device=dev)
-            runner = EpisodeRunner(env, st, dy, pq, use_graph=use_graph, partial_sums=True)
+            runner = EpisodeRunner(env, st, dy, pq, use_graph=use_graph, partial_sums=True, exchange=exchange)
             self.slots.append(dict(static=st, dynamic=dy, ptr=pq, runner=runner,
                                    uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event(),
                                    reward=torch.empty(B, dtype=torch.float32).pin_memory(),
@@ -125,7 +130,7 @@ class HostPipeline(object):
         if after_episode is not None:
             after_episode(s["runner"])                           # e.g. the cross-rank reduction of runner.sums
         s["reward"].copy_(r, non_blocking=True)
-        s["sums"].copy_(s["runner"].sums, non_blocking=True)
+        s["sums"].copy_(s["runner"].total if s["runner"].total is not None else s["runner"].sums, non_blocking=True)
         s["done"].record(compute)
         s["busy"] = True
         self.head = (self.head + 1) % self.depth
