@@ -54,6 +54,7 @@ extern "C" {
 /* packing_strategy (tools.py:3607, :3679-3701) */
 #define TAPENV_LB_GREEDY 0
 #define TAPENV_MACS 1
+#define TAPENV_LB 2           /* the older corner-list strategy, tools.py:1602-1914; keeps a voxel grid in the state */
 /* heightmap_type (tools.py:3716-3743) */
 #define TAPENV_HM_FULL 0
 #define TAPENV_HM_ZERO 1
@@ -82,7 +83,7 @@ typedef struct tapenv_config {
     int32_t width;          /* container_size[0]                                                   */
     int32_t length;         /* container_size[1] in 3D, 1 in 2D                                    */
     int32_t height;         /* container_size[-1]                                                  */
-    int32_t strategy;       /* TAPENV_LB_GREEDY | TAPENV_MACS (after the reward-type override, tools.py:3617-3620) */
+    int32_t strategy;       /* TAPENV_LB_GREEDY | TAPENV_MACS | TAPENV_LB (after the reward-type override, tools.py:3617-3620) */
     int32_t heightmap_type; /* TAPENV_HM_*                                                         */
     int32_t reward_flags;   /* TAPENV_RF_* bits                                                    */
     int32_t ratio_mode;     /* TAPENV_RATIO_*                                                      */
@@ -105,6 +106,9 @@ typedef struct tapenv_state_layout {
     size_t flags;      /* i32 [B] sticky anomaly bits (the reference would raise IndexError in each case):
                           1 = a stack grew above container height, 2 = more than `capacity` blocks were added,
                           4 = a pointer outside [0,S) was passed to the fused step */
+    size_t voxels;     /* i16 [B,cells,H]  LB only: 0 empty, -1 empty under a block, k+1 block id   (tools.py:3629) */
+    size_t lists;      /* u8  [B,nlists,capacity+2]  LB only: level_free_space x lists, byte 0 = length (tools.py:3649-3653) */
+    size_t pending;    /* f32 [B,4]  LB only: the gathered block handed from the fused step's tensor pass to the placement pass */
     size_t total;      /* == tapenv_state_bytes() */
 } tapenv_state_layout;
 

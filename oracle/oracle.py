@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libtap_oracle.so")
 
 LB_GREEDY, MACS = 0, 1
 HM_TYPES = {"full": 0, "zero": 1, "diff": 2}
-STRATEGIES = {"LB_GREEDY": 0, "MACS": 1, "MUL": 1}
+STRATEGIES = {"LB_GREEDY": 0, "MACS": 1, "MUL": 1, "LB": 2}
 
 
 def build(force=False):

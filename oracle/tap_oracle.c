@@ -34,10 +34,11 @@
 #define TAPO_MAXW 32   /* container width / length limit of the oracle */
 #define TAPO_MAXN 256  /* blocks per episode limit */
 
-enum { TAPO_LB_GREEDY = 0, TAPO_MACS = 1 };
+enum { TAPO_LB_GREEDY = 0, TAPO_MACS = 1, TAPO_LB = 2 };
 enum { TAPO_HM_FULL = 0, TAPO_HM_ZERO = 1, TAPO_HM_DIFF = 2 };
 
 typedef struct { int len; int v[TAPO_MAXW + 4]; } ilist;
+typedef struct { int len; int v[TAPO_MAXN + 4]; } xlist;   /* LB: per-level x lists grow by appends (tools.py:1745-1749) */
 
 typedef struct tapo_env {
     int dim, W, L, H, n;
@@ -52,6 +53,7 @@ typedef struct tapo_env {
     long long valid, empty; /* tools.py:3635-3636 */
     int k;            /* current_blocks_num tools.py:3653 */
     ilist *lfs;       /* [H] MACS 2D level_free_space tools.py:3641-3643 */
+    xlist *lbl;       /* LB: [H] (2D) or [H][L] (3D) level_free_space tools.py:3649-3653, initial [0] */
     int error;        /* sticky: 1 = numpy would have raised IndexError, 2 = limits */
 } tapo_env;
 
@@ -86,6 +88,10 @@ void tapo_env_clear(tapo_env *e) {
             e->lfs[z].len = 2; e->lfs[z].v[0] = 0; e->lfs[z].v[1] = e->W - 1;
         }
     }
+    if (e->lbl) {
+        int cnt = e->dim == 2 ? e->H : e->H * e->L;
+        for (int i = 0; i < cnt; i++) { e->lbl[i].len = 1; e->lbl[i].v[0] = 0; }
+    }
 }
 
 tapo_env *tapo_env_new(int dim, int W, int L, int H, int n, const char *reward_type,
@@ -108,6 +114,8 @@ tapo_env *tapo_env_new(int dim, int W, int L, int H, int n, const char *reward_t
     e->stable = (unsigned char *)malloc(n);
     e->lfs = NULL;
     if (strategy == TAPO_MACS && dim == 2) e->lfs = (ilist *)malloc(sizeof(ilist) * H);
+    e->lbl = NULL;
+    if (strategy == TAPO_LB) e->lbl = (xlist *)malloc(sizeof(xlist) * (size_t)H * (dim == 2 ? 1 : e->L));
     tapo_env_clear(e);
     return e;
 }
@@ -115,7 +123,7 @@ tapo_env *tapo_env_new(int dim, int W, int L, int H, int n, const char *reward_t
 void tapo_env_free(tapo_env *e) {
     if (!e) return;
     free(e->container); free(e->heightmap); free(e->positions); free(e->blocks);
-    free(e->stable); free(e->lfs); free(e);
+    free(e->stable); free(e->lfs); free(e->lbl); free(e);
 }
 
 /* ------------------------------------------------------------------ */
@@ -699,6 +707,187 @@ static void macs_step_2d(tapo_env *e) {
 }
 
 /* ------------------------------------------------------------------ */
+/* LB ("abandoned" but selectable with packing_strategy='LB'): tools.py:1602-1754 (2D), :1756-1914 (3D).
+ * Driven through Container.add_new_block (:3683-3686), which never stores the returned bounding_box
+ * (`# self.bounding_box = bounding_box`, :3706): every call starts from bounding_box = zeros, so the
+ * compactness of a candidate is valid/((_z+bz)*W) -- THIS block's top, not the packing height. */
+static int xl_has(const xlist *l, int v) { for (int i = 0; i < l->len; i++) if (l->v[i] == v) return 1; return 0; }
+static void xl_remove(xlist *l, int v) { for (int i = 0; i < l->len; i++) if (l->v[i] == v) { for (; i + 1 < l->len; i++) l->v[i] = l->v[i + 1]; l->len--; return; } }
+
+static void lb_step_2d(tapo_env *e) {
+    const int W = e->W, H = e->H, k = e->k;
+    int *h = e->heightmap, *c = e->container;
+    const int bx = e->blocks[k * 2 + 0], bz = e->blocks[k * 2 + 1];
+    /* :1640-1650 first-block initialisation when the container is entirely empty */
+    int allzero = 1; for (int i = 0; i < W * H && allzero; i++) if (c[i] != 0) allzero = 0;
+    if (allzero) { e->valid = 0; e->empty = 0; for (int z = 0; z < H; z++) { e->lbl[z].len = 1; e->lbl[z].v[0] = 0; } memset(h, 0, sizeof(int) * W); }
+    long long valid = e->valid + (long long)bx * bz;          /* :1655 */
+    static __thread int ems[MAX_EMS][4]; int ne = 0;
+    for (int z = 0; z < H; z++) {                              /* :1659-1666 */
+        const xlist *fs = &e->lbl[z];
+        if (z + bz > H) break;
+        else if (z > 0) { int rowzero = 1; for (int x = 0; x < W; x++) if (c[x * H + z - 1] != 0) { rowzero = 0; break; } if (rowzero) break; }
+        for (int i = 0; i < fs->len; i++) {
+            int x = fs->v[i];
+            if (x + bx > W) break;
+            if (z > 0 && xl_has(&e->lbl[z - 1], x)) {
+                int same = 1; for (int q = x; q < W; q++) if (c[q * H + z] != c[q * H + z - 1]) { same = 0; break; }
+                if (same) continue;
+            }
+            if (ne >= MAX_EMS) { e->error = 2; return; }
+            ems[ne][0] = x; ems[ne][1] = z; ne++;
+        }
+    }
+    for (int b = 0; b < k; b++) {                              /* :1668-1677 */
+        int x = e->positions[b * 2], z = e->positions[b * 2 + 1], zz = e->blocks[b * 2 + 1];
+        if (z + zz < H) {
+            if (c[x * H + z + zz] == 0) {
+                int dup = 0; for (int i = 0; i < ne; i++) if (ems[i][0] == x && ems[i][1] == z + zz) { dup = 1; break; }
+                if (!dup) { if (ne >= MAX_EMS) { e->error = 2; return; } ems[ne][0] = x; ems[ne][1] = z + zz; ne++; }
+            }
+        }
+    }
+    static __thread int pos[MAX_EMS][2]; static __thread unsigned char settle[MAX_EMS], stab[MAX_EMS];
+    static __thread double comp[MAX_EMS], pyr[MAX_EMS], stb[MAX_EMS]; static __thread long long empty_ems[MAX_EMS];
+    const int X = W - bx + 1; int nsettled = 0;
+    for (int i = 0; i < ne; i++) {                             /* :1690-1730 */
+        settle[i] = stab[i] = 0; comp[i] = pyr[i] = stb[i] = 0.0; empty_ems[i] = e->empty;
+        int _z = ems[i][1];
+        for (int _x = ems[i][0]; _x < X; _x++) {
+            if (settle[i]) break;
+            int freeall = 1;                                   /* numpy clips the z slice at H */
+            for (int q = _x; q < _x + bx && freeall; q++) for (int zz = _z; zz < _z + bz && zz < H; zz++) if (c[q * H + zz] != 0) { freeall = 0; break; }
+            if (!freeall) continue;
+            if (_z > 0) {
+                if (!is_stable_2d(&c[_x * H + _z - 1], H, bx, _x, bx)) { if (e->hard) continue; }
+                else stab[i] = 1;
+            } else stab[i] = 1;
+            pos[i][0] = _x; pos[i][1] = _z; settle[i] = 1;
+        }
+        if (settle[i]) {
+            nsettled++;
+            int _x = pos[i][0]; _z = pos[i][1];
+            long long bbox = (long long)(_z + bz) * W;         /* bounding_box arrives as zeros: see the note above */
+            comp[i] = (double)valid / (double)bbox;
+            long long cnt = 0; for (int q = _x; q < _x + bx; q++) for (int zz = 0; zz < _z && zz < H; zz++) if (c[q * H + zz] == 0) cnt++;
+            empty_ems[i] += cnt;
+            if (e->useP) pyr[i] = (double)valid / (double)(empty_ems[i] + valid);
+            if (e->useS) { int sn = 0; for (int q = 0; q < k; q++) sn += e->stable[q]; sn += stab[i]; stb[i] = (double)sn / (double)(k + 1); }
+        }
+    }
+    if (nsettled == 0) { e->stable[k] = 0; return; }           /* :1733-1736 */
+    static __thread double ratio[MAX_EMS];
+    for (int i = 0; i < ne; i++) ratio[i] = (comp[i] + pyr[i]) + stb[i];
+    int best = argmax_first(ratio, ne);                        /* the remove-loop at :1741-1743 never runs: unsettled scores are 0.0 */
+    int _x = pos[best][0], _z = pos[best][1];
+    if (_z + bz > H) { e->error = 1; return; }                 /* level_free_space[_z+zz] IndexError below */
+    e->positions[k * 2] = _x; e->positions[k * 2 + 1] = _z;
+    e->stable[k] = stab[best];
+    e->empty = empty_ems[best];
+    for (int q = _x; q < _x + bx; q++) {
+        for (int zz = _z; zz < _z + bz; zz++) c[q * H + zz] = k + 1;
+        for (int zz = 0; zz < _z; zz++) if (c[q * H + zz] == 0) c[q * H + zz] = -1;
+    }
+    for (int zz = 0; zz < bz; zz++) {                          /* :1757-1761 */
+        xlist *fs = &e->lbl[_z + zz];
+        if (xl_has(fs, _x)) xl_remove(fs, _x);
+        if (_x + bx < W && c[(_x + bx) * H + _z + zz] == 0) { if (fs->len >= TAPO_MAXN + 4) { e->error = 2; return; } fs->v[fs->len++] = _x + bx; }
+    }
+    for (int q = _x; q < _x + bx; q++) h[q] = _z + bz;         /* :1764 */
+    e->valid = valid;
+}
+
+static void lb_step_3d(tapo_env *e) {
+    const int W = e->W, L = e->L, H = e->H, k = e->k;
+    int *h = e->heightmap, *c = e->container;
+#define CT(x, y, z) c[((x) * L + (y)) * H + (z)]
+#define LF(z, y) e->lbl[(z) * L + (y)]
+    const int bx = e->blocks[k * 3], by = e->blocks[k * 3 + 1], bz = e->blocks[k * 3 + 2];
+    int allzero = 1; for (int i = 0; i < W * L * H && allzero; i++) if (c[i] != 0) allzero = 0;
+    if (allzero) { e->valid = 0; e->empty = 0; for (int i = 0; i < H * L; i++) { e->lbl[i].len = 1; e->lbl[i].v[0] = 0; } memset(h, 0, sizeof(int) * W * L); }
+    long long valid = e->valid + (long long)bx * by * bz;
+    static __thread int ems[MAX_EMS * 4][4]; int ne = 0;
+    const int EMAX = MAX_EMS * 4;
+    for (int z = 0; z < H; z++) {                              /* :1810-1823 */
+        if (z + bz > H) break;
+        else if (z > 0) { int zero = 1; for (int x = 0; x < W && zero; x++) for (int y = 0; y < L; y++) if (CT(x, y, z - 1) != 0) { zero = 0; break; } if (zero) break; }
+        for (int y = 0; y < L; y++) {
+            const xlist *fs = &LF(z, y);
+            if (y + by > L) break;
+            else if (y > 0 && LF(z, y - 1).len == 1 && LF(z, y - 1).v[0] == 0) continue;   /* free_space_x[y-1] == [0] */
+            for (int i = 0; i < fs->len; i++) {
+                int x = fs->v[i];
+                if (x + bx > W) break;
+                if (y > 0 && xl_has(&LF(z, y - 1), x)) { int same = 1; for (int q = x; q < W; q++) if (CT(q, y, z) != CT(q, y - 1, z)) { same = 0; break; } if (same) continue; }
+                if (z > 0 && xl_has(&LF(z - 1, y), x)) { int same = 1; for (int q = x; q < W && same; q++) for (int r = y; r < L; r++) if (CT(q, r, z) != CT(q, r, z - 1)) { same = 0; break; } if (same) continue; }
+                if (ne >= EMAX) { e->error = 2; return; }
+                ems[ne][0] = x; ems[ne][1] = y; ems[ne][2] = z; ne++;
+            }
+        }
+    }
+    for (int b = 0; b < k; b++) {                              /* :1824-1833 */
+        int x = e->positions[b * 3], y = e->positions[b * 3 + 1], z = e->positions[b * 3 + 2];
+        int yy = e->blocks[b * 3 + 1], zz = e->blocks[b * 3 + 2];
+        if (y + yy < L) {
+            if (CT(x, y + yy, z) == 0) { int dup = 0; for (int i = 0; i < ne; i++) if (ems[i][0] == x && ems[i][1] == y + yy && ems[i][2] == z) { dup = 1; break; }
+                if (!dup) { if (ne >= EMAX) { e->error = 2; return; } ems[ne][0] = x; ems[ne][1] = y + yy; ems[ne][2] = z; ne++; } }
+        }
+        if (z + zz < H) {
+            if (CT(x, y, z + zz) == 0) { int dup = 0; for (int i = 0; i < ne; i++) if (ems[i][0] == x && ems[i][1] == y && ems[i][2] == z + zz) { dup = 1; break; }
+                if (!dup) { if (ne >= EMAX) { e->error = 2; return; } ems[ne][0] = x; ems[ne][1] = y; ems[ne][2] = z + zz; ne++; } }
+        }
+    }
+    static __thread int pos[MAX_EMS * 4][3]; static __thread unsigned char settle[MAX_EMS * 4], stab[MAX_EMS * 4];
+    static __thread double comp[MAX_EMS * 4], pyr[MAX_EMS * 4], stb[MAX_EMS * 4]; static __thread long long empty_ems[MAX_EMS * 4];
+    const int X = W - bx + 1, Y = L - by + 1; int nsettled = 0;
+    for (int i = 0; i < ne; i++) {
+        settle[i] = stab[i] = 0; comp[i] = pyr[i] = stb[i] = 0.0; empty_ems[i] = e->empty;
+        int _z = ems[i][2];
+        for (int _x = ems[i][0]; _x < X && !settle[i]; _x++) for (int _y = ems[i][1]; _y < Y; _y++) {
+            if (settle[i]) break;
+            int freeall = 1;
+            for (int p = _x; p < _x + bx && freeall; p++) for (int q = _y; q < _y + by && freeall; q++) for (int zz = _z; zz < _z + bz && zz < H; zz++) if (CT(p, q, zz) != 0) { freeall = 0; break; }
+            if (!freeall) continue;
+            if (!is_stable_3d(e, bx, by, _x, _y, _z)) { if (e->hard) continue; }
+            else stab[i] = 1;
+            pos[i][0] = _x; pos[i][1] = _y; pos[i][2] = _z; settle[i] = 1;
+        }
+        if (settle[i]) {
+            nsettled++;
+            int _x = pos[i][0], _y = pos[i][1]; _z = pos[i][2];
+            long long bbox = (long long)(_z + bz) * W * L;
+            comp[i] = (double)valid / (double)bbox;
+            long long cnt = 0; for (int p = _x; p < _x + bx; p++) for (int q = _y; q < _y + by; q++) for (int zz = 0; zz < _z && zz < H; zz++) if (CT(p, q, zz) == 0) cnt++;
+            empty_ems[i] += cnt;
+            if (e->useP) pyr[i] = (double)valid / (double)(empty_ems[i] + valid);
+            if (e->useS) { int sn = 0; for (int q = 0; q < k; q++) sn += e->stable[q]; sn += stab[i]; stb[i] = (double)sn / (double)(k + 1); }
+        }
+    }
+    if (nsettled == 0) { e->stable[k] = 0; return; }
+    static __thread double ratio[MAX_EMS * 4];
+    for (int i = 0; i < ne; i++) ratio[i] = (comp[i] + pyr[i]) + stb[i];
+    int best = argmax_first(ratio, ne);
+    int _x = pos[best][0], _y = pos[best][1], _z = pos[best][2];
+    if (_z + bz > H) { e->error = 1; return; }
+    e->positions[k * 3] = _x; e->positions[k * 3 + 1] = _y; e->positions[k * 3 + 2] = _z;
+    e->stable[k] = stab[best];
+    e->empty = empty_ems[best];
+    for (int p = _x; p < _x + bx; p++) for (int q = _y; q < _y + by; q++) {
+        for (int zz = _z; zz < _z + bz; zz++) CT(p, q, zz) = k + 1;
+        for (int zz = 0; zz < _z; zz++) if (CT(p, q, zz) == 0) CT(p, q, zz) = -1;
+    }
+    for (int zz = 0; zz < bz; zz++) for (int yy = 0; yy < by; yy++) {       /* :1905-1909 */
+        xlist *fs = &LF(_z + zz, _y + yy);
+        if (xl_has(fs, _x)) xl_remove(fs, _x);
+        if (_x + bx < W && CT(_x + bx, _y + yy, _z + zz) == 0) { if (fs->len >= TAPO_MAXN + 4) { e->error = 2; return; } fs->v[fs->len++] = _x + bx; }
+    }
+    for (int p = _x; p < _x + bx; p++) for (int q = _y; q < _y + by; q++) h[p * L + q] = _z + bz;
+    e->valid = valid;
+#undef CT
+#undef LF
+}
+
+/* ------------------------------------------------------------------ */
 /* heightmap encodings, tools.py:3716-3743.  Returns number of ints written. */
 int tapo_env_encode_heightmap(const tapo_env *e, int *out) {
     const int W = e->W, L = e->L; const int *h = e->heightmap;
@@ -725,6 +914,8 @@ int tapo_env_add_new_block(tapo_env *e, const float *block, int *hm_out) {
     const int *b = &e->blocks[e->k * e->dim];
     if (e->strategy == TAPO_MACS) {
         if (e->dim == 2) macs_step_2d(e); else { e->error = 2; return -2; }
+    } else if (e->strategy == TAPO_LB) {
+        if (e->dim == 2) lb_step_2d(e); else lb_step_3d(e);
     } else {
         if (e->dim == 2) lbg_step_2d(e, b[0], b[1]); else lbg_step_3d(e, b[0], b[1], b[2]);
     }

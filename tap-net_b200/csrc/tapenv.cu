@@ -14,10 +14,11 @@
 #include "place_lbg2d.cuh"
 #include "place_lbg3d.cuh"
 #include "place_macs2d.cuh"
+#include "place_lb.cuh"
 
 namespace tapenv {
 
-enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2 };
+enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2, STRAT_LB = 3 };
 
 // ------------------------------------------------------------------------------------
 // host-side helpers
@@ -41,6 +42,11 @@ static void layout_of(const tapenv_config *c, tapenv_state_layout *L) {
     L->blocks = off;    off = align_up(off + B * cap * dim * sizeof(int32_t), 256);
     L->stable = off;    off = align_up(off + B * cap, 256);
     L->flags = off;     off = align_up(off + B * sizeof(int32_t), 256);
+    const bool lb = c->strategy == TAPENV_LB;
+    const size_t nlists = (size_t)c->height * (dim == 3 ? (size_t)c->length : 1);
+    L->voxels = off;    off = align_up(off + (lb ? B * (size_t)cells_of(c) * (size_t)c->height * sizeof(int16_t) : 0), 256);
+    L->lists = off;     off = align_up(off + (lb ? B * nlists * (cap + 2) : 0), 256);
+    L->pending = off;   off = align_up(off + (lb ? B * 4 * sizeof(float) : 0), 256);
     L->total = off;
 }
 
@@ -62,6 +68,8 @@ static DevCfg devcfg_of(const tapenv_config *c) {
     d.inv_L = (65536u + d.L - 1) / (d.L > 0 ? d.L : 1);
     d.dyn_env = (unsigned)(d.dyn_rows * d.S);
     d.static_env = (unsigned)(d.static_rows * d.S);
+    d.lcap = c->capacity + 2;
+    d.nlists = c->height * (c->dim == 3 ? c->length : 1);
     return d;
 }
 
@@ -75,6 +83,9 @@ static StatePtrs stateptrs_of(const tapenv_config *c, void *state) {
     s.blocks = (int *)(base + L.blocks);
     s.stable = (unsigned char *)(base + L.stable);
     s.flags = (int *)(base + L.flags);
+    s.voxels = (short *)(base + L.voxels);
+    s.lists = (unsigned char *)(base + L.lists);
+    s.pending = (float *)(base + L.pending);
     return s;
 }
 
@@ -85,7 +96,8 @@ static int check_cfg(const tapenv_config *c) {
     if (c->dim == 2 && c->length != 1) return TAPENV_ESHAPE;
     if (c->dim == 3 && c->length < 1) return TAPENV_EINVAL;
     if (c->rotate_types < 1) return TAPENV_EINVAL;
-    if (c->strategy != TAPENV_LB_GREEDY && c->strategy != TAPENV_MACS) return TAPENV_EENUM;
+    if (c->strategy != TAPENV_LB_GREEDY && c->strategy != TAPENV_MACS && c->strategy != TAPENV_LB) return TAPENV_EENUM;
+    if (c->strategy == TAPENV_LB && (c->capacity > 250 || c->height > 32767)) return TAPENV_ELIMIT;
     if (c->heightmap_type < 0 || c->heightmap_type > 2) return TAPENV_EENUM;
     if (c->ratio_mode < 0 || c->ratio_mode > TAPENV_RATIO_CP_HALF) return TAPENV_EENUM;
     if (c->static_rows < 1 + c->dim) return TAPENV_ESHAPE;
@@ -105,6 +117,7 @@ static int check_cfg(const tapenv_config *c) {
 static int strategy_kernel(const tapenv_config *c) {
     if (c->strategy == TAPENV_LB_GREEDY) return c->dim == 2 ? STRAT_LBG2D : STRAT_LBG3D;
     if (c->strategy == TAPENV_MACS && c->dim == 2) return STRAT_MACS2D;
+    if (c->strategy == TAPENV_LB) return STRAT_LB;
     return -1;                                       // MACS 3D: not built (out of scope for v1)
 }
 
@@ -160,6 +173,7 @@ struct EnvRegs {
     MacsHist hist;
 
     __device__ __forceinline__ void load(const DevCfg &c, const StatePtrs &st, int b, int lane) {
+        if (STRAT == STRAT_LB) return;               // the LB placement runs in its own kernel (lb_kernel)
         const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
         h = lane < cells ? st.heightmap[(size_t)b * cells + lane] : 0;
         sc = load_scal(st, b);
@@ -193,7 +207,9 @@ __device__ __forceinline__ void container_add_block(const DevCfg &c, const State
         anomaly |= 2;
     } else {
         PlaceOut r;
-        if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
+        r.placed = 0; r.x = r.y = r.z = r.stable = r.top = 0;
+        if (STRAT == STRAT_LB) { }
+        else if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
         else if (STRAT == STRAT_LBG3D) r = lbg3d_place(c, lane, e.x, e.y, bx, by, bz, e.h, e.sc);
         else r = macs2d_place(c, lane, bx, bz, e.h, e.sc, e.hist, ems_keys, anomaly);
         if (lane < cells) st.heightmap[(size_t)b * cells + lane] = e.h;
@@ -237,6 +253,12 @@ reset_kernel(DevCfg c, StatePtrs st, int clear_state, const float *__restrict__ 
         for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
         for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
         if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
+        if (c.strategy == TAPENV_LB) {                   // voxel grid zero, every x list = [0] (tools.py:3649-3653)
+            const size_t nv = (size_t)cells * c.H;
+            for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
+            const size_t nl = (size_t)c.nlists * c.lcap;
+            for (size_t i = lane; i < nl; i += 32) st.lists[(size_t)b * nl + i] = (i % c.lcap) == 0 ? 1 : 0;
+        }
     }
     if (dynamic == nullptr) return;
     const BandBits bits = dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), nullptr, -1);
@@ -292,6 +314,63 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
     container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
 }
 
+// LB strategy: one thread per environment (place_lb.cuh).  blocks == nullptr: take the block the fused step's tensor
+// pass left in st.pending.
+template <int DIM>
+__global__ void __launch_bounds__(64)
+lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const int cells = DIM == 2 ? c.W : c.W * c.L;
+    const float *blk = blocks ? blocks + (size_t)b * DIM : st.pending + (size_t)b * 4;
+    const int bx = (int)blk[0], by = DIM == 3 ? (int)blk[1] : 1, bz = (int)blk[DIM - 1];   // .astype(int) tools.py:3675
+    LbState s;
+    s.W = c.W; s.L = DIM == 3 ? c.L : 1; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
+    s.vox = st.voxels + (size_t)b * cells * c.H;
+    s.lists = st.lists + (size_t)b * c.nlists * c.lcap;
+    s.h = st.heightmap + (size_t)b * cells;
+    const int4 sc = st.scal[b];
+    int anomaly = 0;
+    const int k = sc.w;
+    if (k >= c.cap) {
+        anomaly |= 2;
+    } else {
+        int *positions = st.positions + (size_t)b * c.cap * DIM, *blks = st.blocks + (size_t)b * c.cap * DIM;
+        blks[k * DIM] = bx; if (DIM == 3) blks[k * DIM + 1] = by; blks[k * DIM + DIM - 1] = bz;
+        int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
+        unsigned char stable = 0;
+        if (bx >= 1 && by >= 1 && bz >= 1 && bx <= c.W && by <= s.L) {
+            const int vol = bx * by * bz;
+            const LbBest best = lb_place<DIM>(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
+            if (best.any) {
+                lb_commit<DIM>(s, k, best, bx, by, bz, anomaly);
+                if (!(anomaly & 1)) {
+                    positions[k * DIM] = best.x; if (DIM == 3) positions[k * DIM + 1] = best.y; positions[k * DIM + DIM - 1] = best.z;
+                    stable = (unsigned char)best.stable;
+                    out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
+                }
+            }
+        }
+        st.stable[(size_t)b * c.cap + k] = stable;
+        st.scal[b] = out;
+    }
+    if (anomaly) st.flags[b] |= anomaly;
+    if (dec_dyn) {                                   // heightmap encodings (tools.py:3716-3743), serial form
+        float *o = dec_dyn + (size_t)b * c.enc_len;
+        const int *h = s.h;
+        if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
+        else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
+        else if (DIM == 2) { for (int i = 0; i + 1 < c.W; ++i) o[i] = (float)(h[i + 1] - h[i]); }
+        else {
+            for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
+                o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
+                o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // fused decode-step kernel  (K1 + K2/K3/K4): update_dynamic + update_mask + gather + add_new_block
 // ------------------------------------------------------------------------------------
@@ -303,12 +382,13 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
             const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
             float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
             float *__restrict__ dec_dyn) {
-    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
-    typedef Shape<NT, RT, DIM> SH;
+    constexpr int DIMC = STRAT == STRAT_LBG3D ? 3 : 2;
+    typedef Shape<NT, RT, DIMC> SH;
     __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
+    const int DIM = STRAT == STRAT_LB ? c.dim : DIMC;
     const int S = SH::S(c);
     const float *srow = env_ptr(static_, b, SH::static_env(c));
     const float *din = env_ptr(dynamic_in, b, SH::dyn_env(c));
@@ -341,7 +421,11 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
     const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
     const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
-    if (PLACE_FIRST)
+    if (STRAT == STRAT_LB) {                         // hand the gathered block to lb_kernel (launched right behind)
+        if (lane < DIM) st.pending[(size_t)b * 4 + lane] = dimv;
+        if (lane == 0 && badp) st.flags[b] |= 4;
+    }
+    if (PLACE_FIRST && STRAT != STRAT_LB)
         container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
 
     // (4) masked copy + column reductions of the precedence tensor
@@ -353,7 +437,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
                   env_ptr(mask_out, b, (unsigned)S));
 
-    if (!PLACE_FIRST)
+    if (!PLACE_FIRST && STRAT != STRAT_LB)
         container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
 }
 
@@ -638,7 +722,7 @@ int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, in
     // packing strategy, with the reward-type override of tools.py:3617-3620
     if (!strcmp(packing_strategy, "LB_GREEDY")) cfg->strategy = TAPENV_LB_GREEDY;
     else if (!strcmp(packing_strategy, "MACS") || !strcmp(packing_strategy, "MUL")) cfg->strategy = TAPENV_MACS;
-    else if (!strcmp(packing_strategy, "LB")) return TAPENV_EUNSUPPORTED;
+    else if (!strcmp(packing_strategy, "LB")) cfg->strategy = TAPENV_LB;
     else return TAPENV_EENUM;
     static const char *const forces_macs[] = {"C+P+S-mul-soft", "C+P+S-mul-hard", "C+P+S-mcs-soft", "C+P+S-mcs-hard", nullptr};
     if (str_in(reward_type, forces_macs)) cfg->strategy = TAPENV_MACS;
@@ -762,7 +846,10 @@ int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks
     if (d.B == 0) return TAPENV_OK;
     if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    if (strat == STRAT_LB) {
+        if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
+        else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
+    } else if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     else if (strat == STRAT_LBG3D) launch(add_blocks_kernel<STRAT_LBG3D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     else launch(add_blocks_kernel<STRAT_MACS2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     return launch_status();
@@ -789,7 +876,14 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         if (pf) launch(step_kernel<STRAT, true, N, R, true>, grid, block, s, TAPENV_STEP_ARGS);            \
         else launch(step_kernel<STRAT, true, N, R, false>, grid, block, s, TAPENV_STEP_ARGS);              \
     } while (0)
-    if (strat == STRAT_LBG2D) {
+    if (strat == STRAT_LB) {                         // tensor pass (no placement) + the thread-per-environment LB kernel
+        if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
+                         dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
+        else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
+                    dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
+        if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
+        else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
+    } else if (strat == STRAT_LBG2D) {
         if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 10, 2);
         else if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 20, 2);
         else if (fast) TAPENV_STEP_SHAPE(STRAT_LBG2D, 0, 0);
@@ -843,6 +937,7 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
     if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (strat == STRAT_LB) return TAPENV_EUNSUPPORTED;      // LB keeps a voxel grid per environment: stepwise API only
     if (steps < 0 || steps > 64 || steps > cfg->capacity) return TAPENV_ELIMIT;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !static_ || !dynamic || (steps > 0 && !ptr_seq)) return TAPENV_EINVAL;

@@ -34,6 +34,7 @@ struct DevCfg {  // by-value kernel argument, derived from tapenv_config on the 
     int SV, RP, PB, nbands;          // vectors per row, rows per pass, passes per band, bands present
     unsigned inv_SV, inv_n, inv_L;   // ceil(65536/d): q = (x*inv) >> 16 is exact for x < 64, d <= 64
     unsigned dyn_env, static_env;    // elements per environment of `dynamic` / `static`
+    int lcap, nlists;                // LB strategy: bytes per x list (capacity+2) and lists per environment (H or H*L)
 };
 
 // Compile-time problem shape.  NT > 0: blocks_num = NT, rotate_types = RT, 'bot'-like input (3 bands, all
@@ -73,6 +74,9 @@ struct StatePtrs {
     int *blocks;         // [B][cap][dim]
     unsigned char *stable;  // [B][cap]
     int *flags;          // [B]
+    short *voxels;       // LB only: [B][cells][H]
+    unsigned char *lists;   // LB only: [B][nlists][lcap]
+    float *pending;      // LB only: [B][4]
 };
 
 struct Scal { int valid, empty, nstable, k; };

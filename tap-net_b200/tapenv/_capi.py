@@ -18,7 +18,7 @@ class Config(C.Structure):  # struct tapenv_config
 
 
 class StateLayout(C.Structure):  # struct tapenv_state_layout
-    _fields_ = [(n, c_size_t) for n in ("scalars", "heightmap", "positions", "blocks", "stable", "flags", "total")]
+    _fields_ = [(n, c_size_t) for n in ("scalars", "heightmap", "positions", "blocks", "stable", "flags", "voxels", "lists", "pending", "total")]
 
 
 class PeerComm(C.Structure):  # struct tapenv_peer_comm
@@ -30,7 +30,7 @@ class Limits(C.Structure):  # struct tapenv_limits
 
 
 OK, EINVAL, EENUM, ELIMIT, ESHAPE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-LB_GREEDY, MACS = 0, 1
+LB_GREEDY, MACS, LB = 0, 1, 2
 
 # every symbol include/tapenv.h declares: name -> (restype, argtypes)
 P = c_void_p

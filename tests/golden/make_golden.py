@@ -196,7 +196,13 @@ def make_traj():
         ("traj_2d_macs_ppsg", "ppsg2d_n20.npz", [7, 50], "C+P+S-mcs-hard", "diff", "MACS", 48),
         ("traj_3d_lbg_soft", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 64),
         ("traj_3d_lbg_hard", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-hard", "full", "LB_GREEDY", 48),
+        ("traj_2d_lb_soft", "rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB", 64),
+        ("traj_2d_lb_hard", "rand2d_n10.npz", [5, 50], "C+P+S-lb-hard", "full", "LB", 48),
+        ("traj_3d_lb_soft", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB", 48),
     ]
+    only = os.environ.get("TRAJ_ONLY")
+    if only:
+        cases = [c for c in cases if only in c[0]]
     for name, src, size, rt, hm, strat, num in cases:
         p = os.path.join(HERE, src)
         if not os.path.exists(p):

@@ -42,6 +42,11 @@ def test_config_from_reference_option_strings():
     # tools.py:3961: C+P-lb-soft -> (C+P)/2 ; no 'S' in the string -> S term off
     c = make_config(8, 10, [5, 50], "C+P-lb-soft", "zero", "LB_GREEDY", "bot", True)
     assert c.ratio_mode == 7 and not c.reward_flags & 4
+    c = make_config(8, 10, [5, 5, 50], "C+P+S-lb-soft", "diff", "LB", "bot", True)
+    assert c.strategy == _capi.LB
+    lay = _capi.StateLayout()
+    assert _capi.lib.tapenv_state_get_layout(C.byref(c), C.byref(lay)) == 0
+    assert lay.lists - lay.voxels >= 8 * 25 * 50 * 2 and lay.pending - lay.lists >= 8 * 50 * 5 * 12
     c = make_config(8, 10, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "simple", False)
     assert (c.rotate_types, c.dyn_rows, c.update_time) == (1, 10, 1)
 
@@ -66,7 +71,8 @@ def test_state_layout_is_disjoint_and_sized():
     c = make_config(1000, 10, [5, 5, 50], "C+P+S-lb-soft", "diff")
     lay = _capi.StateLayout()
     assert _capi.lib.tapenv_state_get_layout(C.byref(c), C.byref(lay)) == 0
-    offs = [lay.scalars, lay.heightmap, lay.positions, lay.blocks, lay.stable, lay.flags, lay.total]
+    offs = [lay.scalars, lay.heightmap, lay.positions, lay.blocks, lay.stable, lay.flags, lay.voxels, lay.lists, lay.pending, lay.total]
+    assert lay.voxels == lay.lists == lay.pending == lay.total       # LB-only sections are empty for LB_GREEDY
     assert offs == sorted(offs) and lay.total == _capi.lib.tapenv_state_bytes(C.byref(c))
     assert lay.heightmap - lay.scalars >= 1000 * 16 and lay.positions - lay.heightmap >= 1000 * 25 * 4
     assert _capi.lib.tapenv_encoded_heightmap_len(C.byref(c)) == 50

@@ -74,7 +74,7 @@ def assert_same(g, r, ptr_seq, static, dim):
 
 
 TRAJ = ["traj_2d_lbg_soft", "traj_2d_lbg_hard", "traj_2d_lbg_w7_full", "traj_2d_macs_rand", "traj_2d_macs_ppsg",
-        "traj_3d_lbg_soft", "traj_3d_lbg_hard"]
+        "traj_3d_lbg_soft", "traj_3d_lbg_hard", "traj_2d_lb_soft", "traj_2d_lb_hard", "traj_3d_lb_soft"]
 
 
 @pytest.mark.parametrize("fused", [True, False])
@@ -110,6 +110,10 @@ CASES = [
     ("rand3d_n10.npz", 2048, [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY"),  # BASELINE config 3
     ("rand3d_n10.npz", 512, [5, 5, 50], "C+P+S-lb-hard", "zero", "LB_GREEDY"),
     ("rand3d_n10.npz", 256, [4, 6, 50], "C+P+S-lb-soft", "full", "LB_GREEDY"),   # W != L
+    ("rand2d_n10.npz", 1024, [5, 50], "C+P+S-lb-soft", "diff", "LB"),            # the older corner-list strategy (a11)
+    ("rand2d_n10.npz", 512, [6, 50], "C+P+S-lb-hard", "zero", "LB"),
+    ("rand3d_n10.npz", 512, [5, 5, 50], "C+P+S-lb-soft", "diff", "LB"),
+    ("rand3d_n10.npz", 256, [4, 6, 50], "C+P+S-lb-hard", "full", "LB"),
 ]
 
 
@@ -124,7 +128,8 @@ def test_fused_step_matches_oracle_every_step(case):
     assert_same(g, r, r["ptr"], static, len(size))
 
 
-@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[6], CASES[9]], ids=["2d", "2d-w4-hard", "macs", "3d"])
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[6], CASES[9], CASES[11], CASES[13]],
+                         ids=["2d", "2d-w4-hard", "macs", "3d", "lb-2d", "lb-3d"])
 def test_unfused_ops_match_oracle_every_step(case):
     src, num, size, rt, hm, strat = case
     if not os.path.exists(golden_path(src)):

@@ -28,6 +28,10 @@ CASES = [
     (3, [5, 5, 50], 10, "C+P+S-lb-soft", "LB_GREEDY", "diff", 60),
     (3, [5, 5, 50], 10, "C+P+S-lb-hard", "LB_GREEDY", "zero", 60),
     (3, [4, 6, 80], 14, "C+P+S-lb-soft", "LB_GREEDY", "full", 30),
+    (2, [5, 50], 10, "C+P+S-lb-soft", "LB", "diff", 100),
+    (2, [6, 50], 12, "C+P+S-lb-hard", "LB", "zero", 100),
+    (3, [5, 5, 50], 10, "C+P+S-lb-soft", "LB", "diff", 50),
+    (3, [4, 6, 80], 12, "C+P+S-lb-hard", "LB", "full", 30),
 ]
 
 
