@@ -24,8 +24,8 @@ STRATEGIES = {"LB_GREEDY": 0, "MACS": 1, "MUL": 1, "LB": 2}
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "tap_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("tap_oracle.c", "win_oracle.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _LIB_PATH
 
@@ -68,6 +68,22 @@ def lib():
         L.tapo_episode_batch.argtypes = ([C.c_int] * 6 + [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
                                          + [p] * 11 + [C.c_int, C.c_int, C.c_int])
         L.tapo_episode_batch.restype = C.c_int
+        L.tapo_pyset_order.argtypes = [p, C.c_int, p]
+        L.tapo_pyset_order.restype = C.c_int
+        L.tapo_win_new.argtypes = [C.c_int, C.c_int, C.c_int, p, p, C.c_int]
+        L.tapo_win_new.restype = p
+        L.tapo_win_free.argtypes = [p]
+        L.tapo_win_convert_to_input.argtypes = [p, p, p]
+        L.tapo_win_convert_to_input.restype = C.c_int
+        L.tapo_win_remove_block.argtypes = [p, C.c_int]
+        L.tapo_win_is_last_graph.argtypes = [p]
+        L.tapo_win_is_last_graph.restype = C.c_int
+        L.tapo_win_nodes.argtypes = [p, p]
+        L.tapo_win_nodes.restype = C.c_int
+        L.tapo_win_error.argtypes = [p]
+        L.tapo_win_error.restype = C.c_int
+        L.tapo_rolling_batch.argtypes = ([C.c_int] * 6 + [C.c_char_p] + [C.c_int] * 4 + [p] * 5 + [C.c_int])
+        L.tapo_rolling_batch.restype = C.c_int
         _lib = L
     return _lib
 
@@ -286,3 +302,82 @@ def is_stable_3d_masks(bx, by, masks):
     out = np.zeros(masks.shape[0], dtype=np.uint8)
     lib().tapo_is_stable_3d_masks(bx, by, _ptr(masks), masks.shape[0], _ptr(out))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# rolling window (generate.InitialContainer, generate.py:1589-1825) -- win_oracle.c
+# ----------------------------------------------------------------------------------------------
+WINDOW_ORDER_REFERENCE, WINDOW_ORDER_SORTED = 0, 1
+
+
+def pyset_order(keys):
+    """Iteration order of set(keys) for small non-negative ints, restated from CPython's setobject.c."""
+    keys = np.ascontiguousarray(keys, dtype=np.int32)
+    out = np.zeros(max(len(keys), 1), np.int32)
+    cnt = lib().tapo_pyset_order(_ptr(keys), len(keys), _ptr(out))
+    assert cnt >= 0
+    return out[:cnt].tolist()
+
+
+class InitialContainer(object):
+    """generate.InitialContainer restricted to what rolling.validate drives: convert_to_input / remove_block /
+    is_last_graph / sub_graph_nodes.  Built from the five precedence graphs as [5,T,T] 0/1 matrices
+    (adj[g,u,v] = edge u -> v: move, left, right, forward, backward) and the [R*T,dim] rotation-major blocks."""
+
+    def __init__(self, adj, blocks, blocks_num, child_graph_size, block_dim, order=WINDOW_ORDER_REFERENCE):
+        adj = np.ascontiguousarray(adj, dtype=np.uint8)
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+        self.T, self.n, self.dim = int(blocks_num), int(child_graph_size), int(block_dim)
+        self.R = rotate_types(self.dim)
+        assert adj.shape == (5, self.T, self.T) and blocks.shape == (self.R * self.T, self.dim)
+        self._h = lib().tapo_win_new(self.T, self.n, self.dim, _ptr(adj), _ptr(blocks), int(order))
+        if not self._h:
+            raise ValueError("window oracle limits")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().tapo_win_free(self._h)
+            self._h = None
+
+    def convert_to_input(self):
+        S = self.n * self.R
+        static = np.zeros((1 + self.dim, S), np.float32)
+        dynamic = np.zeros((3 * self.n, S), np.float32)
+        rc = lib().tapo_win_convert_to_input(self._h, _ptr(static), _ptr(dynamic))
+        if rc:
+            raise ValueError("window cannot be filled (the reference raises in np.concatenate)")
+        return static, dynamic
+
+    def remove_block(self, block_id):
+        lib().tapo_win_remove_block(self._h, int(block_id))
+
+    def is_last_graph(self):
+        return bool(lib().tapo_win_is_last_graph(self._h))
+
+    @property
+    def sub_graph_nodes(self):
+        out = np.zeros(self.T, np.int32)
+        k = lib().tapo_win_nodes(self._h, _ptr(out))
+        return out[:k].tolist()
+
+    @property
+    def error(self):
+        return lib().tapo_win_error(self._h)
+
+
+def rolling_batch(adj, blocks, ptr_seq, container_size, window, reward_type, heightmap_type="diff",
+                  packing_strategy="LB_GREEDY", order=WINDOW_ORDER_REFERENCE, nthreads=1):
+    """rolling.validate's loop (rolling.py:575-640) for a batch, network replaced by the recorded ptr_seq [T,B]:
+    adj [B,5,T,T] u8, blocks [B,R*T,dim] i32.  -> dict(reward f32 [B], heightmap i32 [B,cells], status)."""
+    adj = np.ascontiguousarray(adj, dtype=np.uint8)
+    blocks = np.ascontiguousarray(blocks, dtype=np.int32)
+    ptr_seq = np.ascontiguousarray(ptr_seq, dtype=np.int64)
+    B, _, T, _ = adj.shape
+    dim = blocks.shape[2]
+    W = int(container_size[0]); Ln = int(container_size[1]) if dim == 3 else 1; H = int(container_size[-1])
+    reward = np.zeros(B, np.float32)
+    hm = np.zeros((B, W * Ln), np.int32)
+    st = lib().tapo_rolling_batch(dim, W, Ln, H, T, int(window), reward_type.encode(), HM_TYPES[heightmap_type],
+                                  STRATEGIES[packing_strategy], int(order), B, _ptr(adj), _ptr(blocks), _ptr(ptr_seq),
+                                  _ptr(reward), _ptr(hm), int(nthreads))
+    return dict(reward=reward, heightmap=hm, status=st)

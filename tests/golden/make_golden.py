@@ -14,6 +14,11 @@ Writes next to this file:
                    seeded random-valid policy: ptr, heightmap, encoded heightmap, masks,
                    positions, stable, valid/empty, calc_ratio
   kat.npz          the known-answer vectors G1-G5 of SURVEY.md section 4 re-derived from the reference
+  rolling{2,3}d_t50.npz   rolling.get_dataset(50, ...) + rolling.RollingDataset: per instance the five precedence
+                   graphs of generate.InitialContainer (bit-packed adjacency) + rotation-major blocks + positions
+  traj_rolling_*.npz      rolling.validate's loop (rolling.py:575-640) on the live reference, network replaced by a
+                   seeded random-valid policy: every window's static/dynamic/sub_graph_nodes, every step's
+                   ptr / heightmap / returned encoding, final positions / stable / calc_ratio
 
 Input tensors are stored compactly: `static` as uint8 [B,1+dim,S] (values are small
 integers), `dynamic` (0/1 entries) bit-packed along the flattened [3n*S] axis.
@@ -216,6 +221,95 @@ def make_traj():
         print(name, "%.1fs" % (time.time() - t), "mean ratio %.4f" % res["ratio"].mean())
 
 
+def ic_adjacency(ic):
+    """[5,T,T] 0/1: adj[g,u,v] = edge u -> v of generate.InitialContainer's G_move/G_left/G_right/G_forward/G_backward."""
+    T = ic.blocks_num
+    adj = np.zeros((5, T, T), np.uint8)
+    for g, G in enumerate((ic.G_move, ic.G_left, ic.G_right, ic.G_forward, ic.G_backward)):
+        for u, v in G.edges():
+            adj[g, int(u), int(v)] = 1
+    return adj
+
+
+@in_scratch
+def make_rolling(obj_dim, num, out_name, T=50, n=10, seed=12345):
+    """rolling.get_dataset(T, num, 4, obj_dim, 7, 250, 1, [1,5], seed) (rolling.py:20-84, the rolling.py CLI defaults)
+    + rolling.RollingDataset (rolling.py:462-534) -> the InitialContainers the rolling driver consumes."""
+    mods = refshim.load(("tools", "generate", "rolling"))
+    rolling = mods["rolling"]
+    t = time.time()
+    os.makedirs("./data/rand_%dd" % obj_dim)
+    train_dir, _ = rolling.get_dataset(T, num, 4, obj_dim, 7, 250, 1, [1, 5], seed=seed)
+    ds = rolling.RollingDataset(train_dir, T, n, num, obj_dim, seed, "bot", "diff", True, 5, 7, 250)
+    adj = np.stack([ic_adjacency(ic) for ic in ds.initial_containers])
+    blocks = np.stack([np.asarray(ic.blocks) for ic in ds.initial_containers])
+    positions = np.stack([np.asarray(ic.positions) for ic in ds.initial_containers])
+    assert blocks.min() >= 0 and blocks.max() < 256
+    np.savez_compressed(os.path.join(HERE, out_name), seed=seed, obj_dim=obj_dim, total_blocks_num=T,
+                        how="rolling.get_dataset(%d,%d,4,%d,7,250,1,[1,5],seed=%d) + rolling.RollingDataset" % (T, num, obj_dim, seed),
+                        adj_bits=np.packbits(adj.reshape(num, -1), axis=1), adj_shape=np.array(adj.shape),
+                        blocks_u8=blocks.astype(np.uint8), positions=positions.astype(np.int16))
+    print(out_name, adj.shape, blocks.shape, "%.1fs" % (time.time() - t))
+
+
+def ref_rolling_trajectory(adj_src, num, container_size, n, reward_type, heightmap_type, packing_strategy, seed):
+    """rolling.validate's loop (rolling.py:575-640) + the env section of rolling.DRL.forward (:325-335, :404-436)."""
+    import torch
+    from tests.golden_io import load_rolling
+    mods = refshim.load(("tools", "generate", "pack"))
+    tools, generate, pack = mods["tools"], mods["generate"], mods["pack"]
+    z = load_rolling(adj_src, num)
+    T, dim = z["T"], z["dim"]
+    ics = [7, 250] if dim == 2 else [7, 7, 250]
+    g = torch.Generator().manual_seed(seed)
+    out = dict(static=[], dynamic_bits=[], nodes=[], ptr=[], heightmap=[], dec_dyn=[], positions=[], stable=[], ratio=[])
+    for b in range(num):
+        ic = generate.InitialContainer(z["blocks"][b], z["positions"][b], T, ics, True, n, "bot")
+        assert np.array_equal(ic_adjacency(ic), z["adj"][b])
+        cont = tools.Container(container_size, T, reward_type, heightmap_type, ics, packing_strategy=packing_strategy)
+        rec = dict(static=[], dynamic_bits=[], nodes=[], ptr=[], heightmap=[], dec_dyn=[])
+        one_step = True
+        while one_step:
+            static, dynamic = ic.convert_to_input()
+            rec["static"].append(static.astype(np.uint8)); rec["nodes"].append(np.array(ic.sub_graph_nodes))
+            rec["dynamic_bits"].append(np.packbits(dynamic.reshape(-1).astype(np.uint8)))
+            if ic.is_last_graph():
+                one_step = False
+            st = torch.FloatTensor(static).unsqueeze(0); dyn = torch.FloatTensor(dynamic).unsqueeze(0)
+            S = st.shape[2]
+            mask = torch.ones(1, S)
+            dm = dyn[:, n:2 * n].sum(1) * dyn[:, 2 * n:].sum(1) + dyn[:, :n].sum(1)
+            cur = mask.clone(); cur[dm.ne(0)] = 0.0
+            for _ in range(1 if one_step else n):
+                ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+                dyn = pack.update_dynamic(dyn, st, ptr, "bot", True)
+                cur, mask = pack.update_mask(mask, dyn, st, ptr, "bot", True)
+                blk = st[0, 1:, int(ptr)].numpy()
+                enc = np.asarray(cont.add_new_block(blk, bool(ptr < n))).reshape(-1).copy()
+                rec["ptr"].append(int(ptr)); rec["heightmap"].append(np.asarray(cont.heightmap).reshape(-1).copy())
+                rec["dec_dyn"].append(enc)
+            p = int(ptr)
+            while p >= n:
+                p -= n
+            ic.remove_block(ic.sub_graph_nodes[p])
+        for k in rec:
+            out[k].append(np.stack(rec[k]))
+        out["positions"].append(np.asarray(cont.positions)); out["stable"].append(np.asarray(cont.stable, dtype=np.uint8))
+        out["ratio"].append(cont.calc_ratio())
+    return {k: np.stack(v) for k, v in out.items()}
+
+
+def make_rolling_traj():
+    cases = [("traj_rolling_3d", "rolling3d_t50.npz", 16, [5, 5, 250], "C+P+S-lb-soft", "diff", "LB_GREEDY"),
+             ("traj_rolling_2d", "rolling2d_t50.npz", 24, [5, 250], "C+P+S-lb-hard", "diff", "LB_GREEDY")]
+    for name, src, num, size, rt, hm, strat in cases:
+        t = time.time()
+        res = ref_rolling_trajectory(src, num, size, 10, rt, hm, strat, seed=2025)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), source=src, container_size=np.array(size), window=10,
+                            reward_type=rt, heightmap_type=hm, packing_strategy=strat, num=num, **res)
+        print(name, "%.1fs" % (time.time() - t), "mean ratio %.4f" % res["ratio"].mean())
+
+
 def make_kat():
     """Known-answer vectors (G1-G4 sequences, doc/data.md, visual/draw_result.py),
     outputs re-derived here from the live reference."""
@@ -251,7 +345,7 @@ def make_kat():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat")
+    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj")
     ap.add_argument("--ppsg-num", type=int, default=512)
     a = ap.parse_args()
     only = a.only.split(",")
@@ -260,3 +354,7 @@ if __name__ == "__main__":
     if "rand3d" in only: make_rand(3, 2048, "rand3d_n10.npz")
     if "ppsg" in only: make_ppsg(a.ppsg_num, "ppsg2d_n20.npz")
     if "traj" in only: make_traj()
+    if "rolling" in only:
+        make_rolling(3, 512, "rolling3d_t50.npz")
+        make_rolling(2, 256, "rolling2d_t50.npz")
+    if "rolltraj" in only: make_rolling_traj()

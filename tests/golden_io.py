@@ -31,3 +31,16 @@ def load_inputs(name, num=None):
 def load_traj(name):
     z = np.load(golden_path(name if name.endswith(".npz") else name + ".npz"))
     return {k: z[k] for k in z.files}
+
+
+def load_rolling(name, num=None):
+    """-> dict(adj u8 [B,5,T,T] (adj[b,g,u,v] = edge u -> v), blocks i32 [B,R*T,dim], positions i32 [B,T,dim], T, dim)
+    exactly as rolling.RollingDataset / generate.InitialContainer built them."""
+    z = np.load(golden_path(name))
+    shape = [int(v) for v in z["adj_shape"]]
+    bits = z["adj_bits"][:num]
+    shape[0] = bits.shape[0]
+    per = shape[1] * shape[2] * shape[3]
+    adj = np.unpackbits(bits, axis=1)[:, :per].reshape(shape)
+    return dict(adj=np.ascontiguousarray(adj), blocks=z["blocks_u8"][:num].astype(np.int32),
+                positions=z["positions"][:num].astype(np.int32), T=int(z["total_blocks_num"]), dim=int(z["obj_dim"]))
