@@ -38,13 +38,13 @@ WORKLOADS = {
     # reference raises IndexError; placements are identical for any height that is not reached
     "c4": ("ppsg2d_n20.npz", [7, 100], "C+P+S-mcs-hard", "diff", "MACS", 1024,
            "2D PPSG nodes=20 width=7 height=100 MACS C+P+S-mcs-hard batch=8192/8 per GPU (BASELINE configs[3])"),
-    # rolling-style: ONE container [5,5,250] takes 50 blocks while the network window stays at 10 (rolling.py:702-703).
-    # Driven by 5 consecutive 10-block RAND-3D windows per environment (the reference's per-step networkx window refill
-    # is host-side, batch-1 code -- SURVEY.md section 8f N1); masks re-initialised per window, state never cleared.
-    "c5": ("rand3d_n10.npz", [5, 5, 250], "C+P+S-lb-soft", "diff", "LB_GREEDY", 8192,
-           "3D rolling-style total=50 window=10 width=5 height=250 LB_GREEDY batch=65536/8 per GPU (BASELINE configs[4])"),
+    # rolling inference (rolling.py:575-640): ONE container [5,5,250] takes 50 blocks while the network window stays at 10;
+    # the window is rebuilt before every decode step by generate.InitialContainer -> tapenv_rolling_step (see run_rolling)
+    "c5": ("rolling3d_t50.npz", [5, 5, 250], "C+P+S-lb-soft", "diff", "LB_GREEDY", 8192,
+           "3D rolling total=50 window=10 width=5 height=250 LB_GREEDY batch=65536/8 per GPU (BASELINE configs[4])"),
 }
-WINDOWS = {"c5": 5}
+WINDOWS = {}
+ROLLING = {"c5": (50, 10)}          # workload -> (total_blocks_num, network window)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel at the workload's default batch, from the
 # `ncu --set full` captures summarised under profiles/ (writes stay in the 126 MB L2 at these sizes)
 TRAFFIC = {"c2": 11.34e6}
@@ -170,6 +170,283 @@ def run_reference(args):
     print(json.dumps(line))
     return 0
 
+
+
+# ----------------------------------------------------------------------------------------------
+# rolling workload (BASELINE configs[4]): generate.InitialContainer window + one container per instance
+# ----------------------------------------------------------------------------------------------
+def rolling_bytes_per_env_step(T, n, dim, W, L):
+    """Algorithmic HBM bytes of ONE fused rolling decode step (tapenv_rolling_step) per instance: the tensors the next
+    network call consumes (static, dynamic, two masks) are written, the instance graphs / blocks / states are read."""
+    R = 2 if dim == 2 else 6
+    S = n * R
+    cells = W if dim == 2 else W * L
+    dec_dyn = (W - 1) if dim == 2 else 2 * W * L
+    out = (1 + dim) * S * 4 + 3 * n * S * 4 + 2 * S * 4 + n * 4 + 4 + 4 * dim + 4 * dec_dyn
+    graphs = T * 8 + (2 if dim == 2 else 4) * n * 8           # movement predecessors of every node + rotation graphs of the window
+    blocks = S * dim * 4
+    state = 2 * 64 + 2 * 4 * cells + 2 * 16 + 2 * 4 * dim + 1  # window state r/w, heightmap r/w, scalars r/w, position/block/stable
+    return out + graphs + blocks + state + 8
+
+
+def load_rolling_workload(name, batch, rank):
+    from tests.golden_io import load_rolling
+    fixture, size, rt, hm, strat, default_b, desc = WORKLOADS[name]
+    T, n = ROLLING[name]
+    B = batch or default_b
+    z = load_rolling(fixture)
+    pool = z["adj"].shape[0]
+    idx = (np.arange(B) + rank * 977) % pool
+    return z["adj"][idx], np.ascontiguousarray(z["blocks"][idx]), size, rt, hm, strat, B, desc, pool, T, n, z["dim"]
+
+
+def rolling_host_policy(adj, blocks, T, n, dim, seed):
+    """Recorded random-valid policy for the CPU arm (checker-side code: drives the oracle's window)."""
+    from oracle import oracle
+    B = adj.shape[0]
+    R = 2 if dim == 2 else 6
+    rng = np.random.RandomState(seed)
+    ptr_seq = np.zeros((T, B), np.int64)
+    for b in range(B):
+        ic = oracle.InitialContainer(adj[b], blocks[b], T, n, dim)
+        t = 0
+        while t < T:
+            static, dynamic = ic.convert_to_input()
+            last = ic.is_last_graph()
+            mask = np.ones((1, n * R), np.float32)
+            cur = oracle.initial_mask(dynamic[None], n, R)
+            dyn = dynamic[None]
+            for _ in range(n if last else 1):
+                ok = np.nonzero(cur[0] > 0)[0]
+                p = int(rng.choice(ok))
+                ptr_seq[t, b] = p
+                t += 1
+                if last:
+                    pa = np.array([p], np.int64)
+                    dyn = oracle.update_dynamic(dyn, static[None], pa)
+                    cur, mask = oracle.update_mask(mask, dyn, static[None], pa)
+            ic.remove_block(ic.sub_graph_nodes[p % n])
+    return ptr_seq
+
+
+def run_rolling_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    adj, blocks, size, rt, hm, strat, B, desc, pool, T, n, dim = load_rolling_workload(args.workload, args.batch, 0)
+    threads = os.cpu_count() or 1
+    Bs = min(B, 1024)                                     # bounded sample: the policy is recorded on the host (slow Python loop)
+    adj, blocks = adj[:Bs], blocks[:Bs]
+    ptr_seq = rolling_host_policy(adj, blocks, T, n, dim, seed=1234)
+    kw = dict(nthreads=threads)
+    for _ in range(max(args.warmup, 1)):
+        oracle.rolling_batch(adj, blocks, ptr_seq, size, n, rt, hm, strat, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = oracle.rolling_batch(adj, blocks, ptr_seq, size, n, rt, hm, strat, **kw)
+    el = time.perf_counter() - t0
+    value = args.steps * Bs * T / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 state + f64 score", "data": "synthetic",
+        "config": {"workload": desc, "batch": Bs, "blocks": T, "env_steps_per_step": Bs * T,
+                   "inputs": "reference rolling.get_dataset fixtures (tests/golden), pool of %d tiled" % pool},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d episodes x %d instances x %d steps, oracle/win_oracle.c + tap_oracle.c on %d pthreads" % (args.steps, Bs, T, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C restatement (oracle/) of rolling.validate's loop on all host threads; the reference itself is Python + networkx",
+        "reward_mean": float(o["reward"].mean()),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_rolling(args):
+    import torch
+    import torch.distributed as dist
+    import tapenv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the tapenv path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    adj, blocks_h, size, rt, hm, strat, B, desc, pool, T, n, dim = load_rolling_workload(args.workload, args.batch, rank)
+    graphs_h = tapenv.pack_graphs(adj)
+    bytes_step = rolling_bytes_per_env_step(T, n, dim, size[0], size[1] if dim == 3 else 1)
+    env = tapenv.BatchedContainers(size, T, rt, hm, packing_strategy=strat, batch_size=B, device=dev, window=n)
+
+    exchange, reduction = None, "none (single GPU)"
+    if world > 1:
+        exchange = tapenv.dist.PeerExchange(dev)
+        reduction = "fused one-shot exchange over NVLink peer memory (tapenv_reward_allreduce), inside the CUDA graph"
+
+    # record the policy once (untimed): ptr ~ multinomial(current_mask of the live window)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    win0 = tapenv.BatchedInitialContainers(graphs_h, blocks_h, T, n, dim, device=dev)
+    rec = tapenv.RollingRunner(env, win0)
+    static, dynamic, cur = rec.begin()
+    ptrs = []
+    for t in range(T):
+        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+        ptrs.append(ptr)
+        static, dynamic, cur, _, _ = rec.step(ptr)
+    ptr_seq0 = torch.stack(ptrs)
+    reward_ref = env.calc_ratio().clone()
+    env.check_flags(); win0.check_flags()
+
+    RING = 2                                               # one episode's ping-pong outputs alone exceed the 126 MB L2
+    runners = []
+    for i in range(RING):
+        roll = (i * 131) % B
+        win = tapenv.BatchedInitialContainers(torch.roll(win0.graphs, roll, 0), torch.roll(win0.blocks, roll, 0), T, n, dim, device=dev)
+        runners.append(tapenv.RollingRunner(env, win, ptr_seq=torch.roll(ptr_seq0, roll, 1).contiguous(),
+                                            use_graph=not args.no_graph, partial_sums=True, exchange=exchange))
+    per_episode_bytes = sum(t.numel() * 4 for t in runners[0].static + runners[0].dynamic + runners[0].cur + runners[0].mask)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        runners[i % RING].run()
+    barrier()
+    assert torch.equal(runners[0].run(), reward_ref)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    for k in range(args.steps):
+        runners[k % RING].run()
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    span_ms_max = float(tt.item())
+    value = world * B * T * args.steps / (span_ms_max * 1e-3)
+    launches = args.steps * runners[0].launches_per_episode
+
+    # roofline of the dominant kernel: the T-n fused rolling steps of one episode, replayed from a graph
+    rr = tapenv.RollingRunner(env, win0, ptr_seq=ptr_seq0)
+    nl = T - n
+
+    def roll_steps():
+        for t in range(nl):
+            rr.step(ptr_seq0[t])
+
+    rr.begin(); roll_steps()
+    torch.cuda.synchronize(dev)
+    rr.begin()
+    rg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(rg):
+        roll_steps()
+    tot_ms, cnt = 0.0, 0
+    for rep in range(8):
+        rr.begin()
+        torch.cuda.synchronize(dev)
+        e0.record(); rg.replay(); e1.record()
+        torch.cuda.synchronize(dev)
+        if rep >= 2:
+            tot_ms += e0.elapsed_time(e1); cnt += nl
+    step_us = 1e3 * tot_ms / cnt
+    achieved = B * bytes_step / (step_us * 1e-6) / 1e9
+
+    # e2e: host graphs / blocks / pointers in, host rewards out
+    gr_pin = torch.from_numpy(graphs_h).pin_memory()
+    bl_pin = torch.from_numpy(blocks_h).pin_memory()
+    pq_pin = ptr_seq0.cpu().pin_memory()
+    pipe = tapenv.RollingHostPipeline(env, T, n, depth=2, use_graph=not args.no_graph, exchange=exchange)
+
+    def e2e_run(k):
+        last = None
+        for i in range(k):
+            if pipe.inflight == pipe.depth:
+                last = pipe.result()
+            pipe.submit(gr_pin, bl_pin, pq_pin)
+        while pipe.inflight:
+            last = pipe.result()
+        return last
+
+    e2e_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    rw_pin, sums_pin = e2e_run(args.steps)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * args.steps / float(te.item())
+    assert np.array_equal(rw_pin.numpy(), reward_ref.cpu().numpy())
+    clocks = sampler.result()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle
+        threads = os.cpu_count() or 1
+        ptr_h = ptr_seq0.cpu().numpy()
+        oracle.rolling_batch(adj, blocks_h, ptr_h, size, n, rt, hm, strat, nthreads=threads)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            o = oracle.rolling_batch(adj, blocks_h, ptr_h, size, n, rt, hm, strat, nthreads=threads)
+            assert o["status"] == 0
+            reps += 1
+            el = time.perf_counter() - t0
+            if el >= args.cpu_seconds or reps >= 10000:
+                break
+        cpu = {"value": reps * B * T / el, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d episodes x %d instances x %d steps = %.1f s of oracle/win_oracle.c + tap_oracle.c on %d pthreads" % (reps, B, T, el, threads),
+               "reward_parity_vs_gpu": bool(np.array_equal(o["reward"], reward_ref.cpu().numpy()))}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 state + f64 score, f32 tensors, u64 graph masks", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "blocks": T, "window": n, "env_steps_per_step": world * B * T,
+                       "step_definition": "one episode = clear + window reset + first window + %d fused rolling steps (place + remove_block + "
+                                          "convert_to_input) + %d fused decode steps in the last window + reward over the batch" % (T - n, n),
+                       "l2": "%.0f MB of ping-pong window tensors per episode > 126 MB L2; %d instance sets alternate" % (per_episode_bytes / 1e6, RING),
+                       "cuda_graph": not args.no_graph, "reward_reduction": reduction,
+                       "inputs": "reference rolling.get_dataset fixtures (tests/golden), pool of %d tiled" % pool,
+                       "policy": "recorded ptr ~ multinomial(current_mask), seed 1234+rank",
+                       "node_order": "reference (networkx FilterAtlas / CPython set order)"},
+            "gpu_launches": launches, "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+                    "ms_per_step": 1e3 * float(te.item()) / args.steps,
+                    "api": "tapenv.RollingHostPipeline.submit/result (graphs + blocks + pointers from pinned host memory), rewards to pinned host memory"},
+            "roofline": {"bound": "hbm", "kernel": "window_kernel (fused add_new_block + remove_block + convert_to_input)",
+                         "achieved": achieved, "peak": peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC.get(args.workload),
+                         "algorithmic_bytes_per_env_step": bytes_step, "bytes_per_launch": B * bytes_step,
+                         "launch_us": step_us, "launches_timed": cnt},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
@@ -445,6 +722,8 @@ def main():
     ap.add_argument("--nccl-reduce", action="store_true", help="multi-GPU: reduce the reward statistics with NCCL instead of the fused peer-memory exchange")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
+    if args.workload in ROLLING:
+        return run_rolling_reference(args) if args.impl == "reference" else run_rolling(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TAPENV_VERSION 100
+#define TAPENV_VERSION 101
 
 /* error codes */
 #define TAPENV_OK 0
@@ -228,6 +228,54 @@ int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *
 int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, const float *dynamic,
                    const int64_t *ptr_seq, int32_t steps, float *reward_out,
                    float *cur_mask_out, float *mask_out, float *dec_dynamic_out, void *stream);
+
+
+/* ---- rolling window --------------------------------------------------------------------------------------------
+ * generate.InitialContainer (generate.py:1589-1825) for B instances: the window of `window` (= child_graph_size) nodes
+ * the network sees while ONE container takes all `total_blocks` blocks (rolling.py:575-640, :702-703).
+ *   pred    u64 [B,5,T]: bit u of pred[b,g,v] <=> edge u -> v in G_move / G_left / G_right / G_forward / G_backward
+ *           (generate.py:1621-1664: deps_g[u,v] == True).  T = total_blocks <= 64.
+ *   blocks  i32 [B,R*T,dim]: self.blocks, rotation-major (rolling.py:483-485, generate.py:1615).
+ *   wstate  tapenv_window_state_bytes() bytes, 64 per instance: the InitialContainer fields that change
+ *           (gm's node set, after_nodes_list, sub_graph_nodes).  u32 words per instance: [0:2) removed-from-gm mask,
+ *           [2:4) after_nodes_list mask, [4:12) sub_graph_nodes as bytes (0xff = unused), [12] len, [13] sticky flags:
+ *           1 = no in-degree-0 node (the reference would loop forever), 2 = window not full at convert_to_input (the
+ *           reference raises in np.concatenate), 4 = pointer outside the window.
+ * node_order: how the induced sub-graphs enumerate their nodes (this decides which row/column of `dynamic` a dependency
+ *   lands in).  REFERENCE reproduces what the reference does under networkx >= 2 / CPython 3: networkx's subgraph view
+ *   iterates the Python *set* of the window nodes when 2*window < total_blocks (coreviews.FilterAtlas.__iter__), so the
+ *   order is CPython's set layout (Objects/setobject.c) -- while `static` uses the sorted node list.  SORTED uses the
+ *   ascending order everywhere (the evident intent). */
+#define TAPENV_WINDOW_ORDER_REFERENCE 0
+#define TAPENV_WINDOW_ORDER_SORTED 1
+typedef struct tapenv_window_config {
+    int32_t batch;          /* B */
+    int32_t total_blocks;   /* T: InitialContainer blocks_num        (generate.py:1590) */
+    int32_t window;         /* n: child_graph_size                   (generate.py:1590) */
+    int32_t dim;            /* 2 or 3 */
+    int32_t rotate_types;   /* factorial(dim)                        (generate.py:1610) */
+    int32_t node_order;     /* TAPENV_WINDOW_ORDER_* */
+} tapenv_window_config;
+size_t tapenv_window_state_bytes(const tapenv_window_config *wcfg);
+/* InitialContainer.__init__ tail (generate.py:1666-1673): nothing removed, every node in after_nodes_list, empty window. */
+int tapenv_window_reset(const tapenv_window_config *wcfg, void *wstate, void *stream);
+/* [remove_block(sub_graph_nodes[prev_ptr mod n]) when prev_ptr != NULL (rolling.py:636-640, generate.py:1810-1822)] +
+ * convert_to_input() (generate.py:1770-1808, 'bot' input) + is_last_graph() (:1824) for every instance.
+ *   static_out f32 [B,1+dim,S], dynamic_out f32 [B,3n,S];
+ *   cur_mask_out / mask_out f32 [B,S] (may be NULL): the initial masks rolling.DRL.forward derives (rolling.py:325-335);
+ *   nodes_out i32 [B,n] (may be NULL): sub_graph_nodes (sorted; -1 = unused);
+ *   remaining_out i32 [B] (may be NULL): len(after_nodes_list); is_last_graph() <=> 0. */
+int tapenv_window_next(const tapenv_window_config *wcfg, void *wstate, const uint64_t *pred, const int32_t *blocks,
+                       const int64_t *prev_ptr, float *static_out, float *dynamic_out, float *cur_mask_out,
+                       float *mask_out, int32_t *nodes_out, int32_t *remaining_out, void *stream);
+/* One rolling decode step in ONE launch: the block the pointer selects in the CURRENT window (rolling.py:417-431) goes
+ * into the container (add_new_block, :436), then tapenv_window_next(prev_ptr = ptr).  update_dynamic / update_mask are
+ * not evaluated: with one_step=True their results never leave rolling.DRL.forward (rolling.py:404-412, :449-453).
+ *   dec_static_out f32 [B,dim] (may be NULL), dec_dynamic_out f32 [B,enc] (may be NULL); other outputs as above. */
+int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_window_config *wcfg, void *wstate,
+                        const uint64_t *pred, const int32_t *blocks, const int64_t *ptr, float *dec_static_out,
+                        float *dec_dynamic_out, float *static_out, float *dynamic_out, float *cur_mask_out,
+                        float *mask_out, int32_t *nodes_out, int32_t *remaining_out, void *stream);
 
 
 #ifdef __cplusplus

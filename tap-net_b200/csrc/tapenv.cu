@@ -15,6 +15,7 @@
 #include "place_lbg3d.cuh"
 #include "place_macs2d.cuh"
 #include "place_lb.cuh"
+#include "window.cuh"
 
 namespace tapenv {
 
@@ -662,6 +663,79 @@ __global__ void reward_sums_exchange_kernel(int B, const float *__restrict__ rew
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Rolling window (generate.InitialContainer, window.cuh) -- alone, or fused behind the placement of the block chosen
+// from the PREVIOUS window: ONE launch per rolling decode step.  In rolling.DRL.forward(one_step=True) the outputs of
+// update_dynamic / update_mask are locals that are never returned (rolling.py:404-412, :449-453), so the fused rolling
+// step performs gather + add_new_block + remove_block + convert_to_input only.
+// ------------------------------------------------------------------------------------
+__global__ void window_reset_kernel(int B, int T, unsigned *wstate) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (q >= B * kWinStateWords) return;
+    const int word = q % kWinStateWords;
+    const unsigned long long after = T >= 64 ? ~0ull : ((1ull << T) - 1ull);           // generate.py:1672-1673
+    unsigned v = 0u;
+    if (word == 2) v = (unsigned)after;
+    else if (word == 3) v = (unsigned)(after >> 32);
+    else if (word >= 4 && word < 12) v = 0xffffffffu;
+    wstate[q] = v;
+}
+
+template <int STRAT, bool FAST>                      // STRAT < 0: window only
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, const unsigned long long *__restrict__ pred,
+              const int *__restrict__ blocks, const int64_t *__restrict__ ptr, float *__restrict__ dec_static,
+              float *__restrict__ dec_dyn, float *__restrict__ static_out, float *__restrict__ dynamic_out,
+              float *__restrict__ cur_mask, float *__restrict__ mask_out, int *__restrict__ nodes_out,
+              int *__restrict__ remaining_out) {
+    constexpr int ES = STRAT < 0 ? STRAT_LBG2D : STRAT;
+    __shared__ WinShared shs[kWarpsPerCta];
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
+    if (b >= w.B) return;
+    WinShared &sh = shs[warp];
+    unsigned *ws = wstate + (size_t)b * kWinStateWords;
+    const unsigned word = lane < kWinStateWords ? ws[lane] : 0u;
+    const unsigned long long *pe = pred + (size_t)b * 5 * w.T;
+    const unsigned long long pm0 = lane < w.T ? pe[lane] : 0ull;
+    const unsigned long long pm1 = lane + 32 < w.T ? pe[lane + 32] : 0ull;
+    const long long p64 = ptr ? ptr[b] : -1;
+    EnvRegs<ES> e;
+    if (STRAT >= 0) e.load(c, st, b, lane);
+    const unsigned long long gone = (unsigned long long)__shfl_sync(TAPENV_FULL_MASK, word, 0) |
+                                    ((unsigned long long)__shfl_sync(TAPENV_FULL_MASK, word, 1) << 32);
+    const unsigned long long after = (unsigned long long)__shfl_sync(TAPENV_FULL_MASK, word, 2) |
+                                     ((unsigned long long)__shfl_sync(TAPENV_FULL_MASK, word, 3) << 32);
+    const int len = (int)__shfl_sync(TAPENV_FULL_MASK, word, 12);
+    int flags = (int)__shfl_sync(TAPENV_FULL_MASK, word, 13);
+    sh.list[lane] = (unsigned char)(__shfl_sync(TAPENV_FULL_MASK, word, 4 + (lane >> 2)) >> (8 * (lane & 3)));
+    __syncwarp();
+    const int *blk = blocks + (size_t)b * w.blocks_env;
+    int rm = -1;
+    if (ptr) {
+        const bool badp = p64 < 0 || p64 >= w.S;      // the reference's gather / list index would raise
+        const int p = badp ? 0 : (int)p64;
+        const int r = (int)(((unsigned)p * w.inv_n) >> 16), idx = p - r * w.n;     // rolling.py:637-638
+        if (badp || idx >= len) flags |= 4; else rm = idx;
+        if (STRAT >= 0) {
+            const int node = rm >= 0 ? (int)sh.list[idx] : -1;
+            float dimv = 0.f;
+            if (lane < w.dim && node >= 0) dimv = (float)blk[(node + r * w.T) * w.dim + lane];     // == static[:,1:,ptr] of the previous window
+            if (dec_static && lane < w.dim) dec_static[(size_t)b * w.dim + lane] = dimv;
+            const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+            const int by = ES == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+            const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, w.dim - 1);
+            if (node >= 0)
+                container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+        }
+    }
+    window_advance<FAST>(w, sh, b, lane, gone, after, len, flags, rm, ws, pe, pm0, pm1, blk, static_out, dynamic_out,
+                         cur_mask, mask_out, nodes_out, remaining_out);
+}
+
 // fast path needs 128-bit rows and 16-byte aligned tensors
 static bool fast_ok(const DevCfg &d, const void *a, const void *b) {
     const uintptr_t al = (uintptr_t)a | (uintptr_t)b;
@@ -945,6 +1019,106 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
     if (strat == STRAT_LBG2D) launch(episode_kernel<STRAT_LBG2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
     else if (strat == STRAT_LBG3D) launch(episode_kernel<STRAT_LBG3D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
     else launch(episode_kernel<STRAT_MACS2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    return launch_status();
+}
+
+// ---- rolling window ---------------------------------------------------------------------------------------------
+static int check_wcfg(const tapenv_window_config *w) {
+    if (!w) return TAPENV_EINVAL;
+    if (w->batch < 0 || w->total_blocks < 1 || w->window < 1 || w->window > w->total_blocks) return TAPENV_EINVAL;
+    if (w->dim != 2 && w->dim != 3) return TAPENV_EINVAL;
+    if (w->rotate_types != (w->dim == 2 ? 2 : 6)) return TAPENV_ESHAPE;      // InitialContainer: factorial(block_dim), generate.py:1610
+    if (w->node_order != TAPENV_WINDOW_ORDER_REFERENCE && w->node_order != TAPENV_WINDOW_ORDER_SORTED) return TAPENV_EENUM;
+    if (w->total_blocks > kWinMaxTotal || w->window > kWinMaxWindow) return TAPENV_ELIMIT;
+    if (w->window * w->rotate_types > kMaxCandidates) return TAPENV_ELIMIT;
+    return TAPENV_OK;
+}
+
+static WinCfg wincfg_of(const tapenv_window_config *w) {
+    WinCfg d;
+    d.B = w->batch; d.T = w->total_blocks; d.n = w->window; d.dim = w->dim; d.R = w->rotate_types; d.S = d.n * d.R;
+    d.setorder = (w->node_order == TAPENV_WINDOW_ORDER_REFERENCE && 2 * d.n < d.T) ? 1 : 0;   // FilterAtlas.__iter__ (window.cuh)
+    d.SV = d.S % 4 == 0 ? d.S / 4 : 1;
+    d.RP = 32 / d.SV > 0 ? 32 / d.SV : 1;
+    d.PB = (d.n + d.RP - 1) / d.RP;
+    d.inv_n = (65536u + d.n - 1) / d.n;
+    d.inv_SV = (65536u + d.SV - 1) / d.SV;
+    // last axis of itertools.permutations(range(dim))[r]: 2D (0,1),(1,0); 3D (0,1,2),(0,2,1),(1,0,2),(1,2,0),(2,0,1),(2,1,0)
+    // code 0 -> (left,right), 1 -> (forward,backward), 2 -> zeros; in 2D a last axis of 1 is the vertical one (generate.py:1802-1806)
+    d.lastcodes = d.dim == 2 ? (2u | (0u << 2)) : (2u | (1u << 2) | (2u << 4) | (0u << 6) | (1u << 8) | (0u << 10));
+    d.blocks_env = (unsigned)(d.R * d.T * d.dim);
+    return d;
+}
+
+size_t tapenv_window_state_bytes(const tapenv_window_config *wcfg) {
+    if (check_wcfg(wcfg) != TAPENV_OK) return 0;
+    return (size_t)wcfg->batch * kWinStateWords * sizeof(unsigned);
+}
+
+int tapenv_window_reset(const tapenv_window_config *wcfg, void *wstate, void *stream) {
+    const int rc = check_wcfg(wcfg);
+    if (rc != TAPENV_OK) return rc;
+    if (wcfg->batch == 0) return TAPENV_OK;
+    if (!wstate) return TAPENV_EINVAL;
+    const int total = wcfg->batch * kWinStateWords;
+    launch(window_reset_kernel, (total + 255) / 256, 256, (cudaStream_t)stream, (int)wcfg->batch, (int)wcfg->total_blocks, (unsigned *)wstate);
+    return launch_status();
+}
+
+static bool win_fast_ok(const WinCfg &w, const void *a, const void *b, const void *c2) {
+    const uintptr_t al = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c2;
+    return w.S % 4 == 0 && al % 16 == 0;
+}
+
+int tapenv_window_next(const tapenv_window_config *wcfg, void *wstate, const uint64_t *pred, const int32_t *blocks,
+                       const int64_t *prev_ptr, float *static_out, float *dynamic_out, float *cur_mask_out,
+                       float *mask_out, int32_t *nodes_out, int32_t *remaining_out, void *stream) {
+    const int rc = check_wcfg(wcfg);
+    if (rc != TAPENV_OK) return rc;
+    if (wcfg->batch == 0) return TAPENV_OK;
+    if (!wstate || !pred || !blocks || !static_out || !dynamic_out) return TAPENV_EINVAL;
+    const WinCfg w = wincfg_of(wcfg);
+    DevCfg c; memset(&c, 0, sizeof(c));
+    StatePtrs st; memset(&st, 0, sizeof(st));
+    const dim3 block(32 * kWarpsPerCta), grid((w.B + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t s = (cudaStream_t)stream;
+#define TAPENV_WIN_ARGS w, c, st, (unsigned *)wstate, (const unsigned long long *)pred, (const int *)blocks
+    if (win_fast_ok(w, dynamic_out, cur_mask_out, mask_out))
+        launch(window_kernel<-1, true>, grid, block, s, TAPENV_WIN_ARGS, prev_ptr, (float *)nullptr, (float *)nullptr, static_out,
+               dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);
+    else
+        launch(window_kernel<-1, false>, grid, block, s, TAPENV_WIN_ARGS, prev_ptr, (float *)nullptr, (float *)nullptr, static_out,
+               dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);
+    return launch_status();
+}
+
+int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_window_config *wcfg, void *wstate,
+                        const uint64_t *pred, const int32_t *blocks, const int64_t *ptr, float *dec_static_out,
+                        float *dec_dynamic_out, float *static_out, float *dynamic_out, float *cur_mask_out,
+                        float *mask_out, int32_t *nodes_out, int32_t *remaining_out, void *stream) {
+    TAPENV_PROLOGUE(cfg)
+    const int rcw = check_wcfg(wcfg);
+    if (rcw != TAPENV_OK) return rcw;
+    if (cfg->batch != wcfg->batch || cfg->dim != wcfg->dim || cfg->blocks_num != wcfg->window ||
+        cfg->rotate_types != wcfg->rotate_types || cfg->static_rows != 1 + cfg->dim) return TAPENV_ESHAPE;
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;      // LB: tapenv_window_next + tapenv_add_blocks
+    if (d.B == 0) return TAPENV_OK;
+    if (!state || !wstate || !pred || !blocks || !ptr || !static_out || !dynamic_out) return TAPENV_EINVAL;
+    const WinCfg w = wincfg_of(wcfg);
+    const DevCfg c = d;
+    const StatePtrs st = stateptrs_of(cfg, state);
+    const bool fast = win_fast_ok(w, dynamic_out, cur_mask_out, mask_out);
+#define TAPENV_ROLL(STRAT)                                                                                              \
+    do {                                                                                                                \
+        if (fast) launch(window_kernel<STRAT, true>, grid, block, s, TAPENV_WIN_ARGS, ptr, dec_static_out, dec_dynamic_out, \
+                         static_out, dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);      \
+        else launch(window_kernel<STRAT, false>, grid, block, s, TAPENV_WIN_ARGS, ptr, dec_static_out, dec_dynamic_out, \
+                    static_out, dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);           \
+    } while (0)
+    if (strat == STRAT_LBG2D) TAPENV_ROLL(STRAT_LBG2D);
+    else if (strat == STRAT_LBG3D) TAPENV_ROLL(STRAT_LBG3D);
+    else TAPENV_ROLL(STRAT_MACS2D);
     return launch_status();
 }
 

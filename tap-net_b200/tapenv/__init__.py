@@ -17,7 +17,8 @@ from . import dist
 from .dataset import PACKDataset
 from .episode import calc_positions_lb_greedy, calc_positions_mcs, reward
 from .dropin import install, uninstall
+from .rolling import BatchedInitialContainers, RollingRunner, RollingHostPipeline, pack_graphs
 
 __all__ = ["PACKDataset", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
            "update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
-           "TapEnvError"]
+           "TapEnvError", "BatchedInitialContainers", "RollingRunner", "RollingHostPipeline", "pack_graphs"]

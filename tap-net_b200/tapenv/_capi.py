@@ -25,12 +25,17 @@ class PeerComm(C.Structure):  # struct tapenv_peer_comm
     _fields_ = [("world", c_int32), ("rank", c_int32), ("peer", c_void_p * 8)]
 
 
+class WindowConfig(C.Structure):  # struct tapenv_window_config
+    _fields_ = [(n, c_int32) for n in ("batch", "total_blocks", "window", "dim", "rotate_types", "node_order")]
+
+
 class Limits(C.Structure):  # struct tapenv_limits
     _fields_ = [(n, c_int32) for n in ("max_width_2d", "max_cells_3d", "max_candidates", "max_blocks")]
 
 
 OK, EINVAL, EENUM, ELIMIT, ESHAPE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 LB_GREEDY, MACS, LB = 0, 1, 2
+WINDOW_ORDER_REFERENCE, WINDOW_ORDER_SORTED = 0, 1
 
 # every symbol include/tapenv.h declares: name -> (restype, argtypes)
 P = c_void_p
@@ -55,6 +60,10 @@ SYMBOLS = {
     "tapenv_comm_bytes": (c_size_t, []),
     "tapenv_reward_allreduce": (c_int, [CFG, P, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
+    "tapenv_window_state_bytes": (c_size_t, [C.POINTER(WindowConfig)]),
+    "tapenv_window_reset": (c_int, [C.POINTER(WindowConfig), P, P]),
+    "tapenv_window_next": (c_int, [C.POINTER(WindowConfig)] + [P] * 11),
+    "tapenv_rolling_step": (c_int, [CFG, P, C.POINTER(WindowConfig)] + [P] * 13),
 }
 
 

@@ -1,0 +1,287 @@
+"""Rolling-window packing (rolling.py:575-640) for a batch of instances on one GPU.
+
+`BatchedInitialContainers` is generate.InitialContainer (generate.py:1589-1825) for B instances at once: the five
+precedence graphs live in HBM as predecessor bit masks, the mutable part (gm's node set, after_nodes_list,
+sub_graph_nodes) is 64 bytes per instance, and `convert_to_input` is one kernel launch for the whole batch instead of
+five networkx sub-graph copies per instance and step.  `RollingRunner` is rolling.validate's per-instance loop with
+the batch axis restored: ONE launch per decode step (tapenv_rolling_step: place the chosen block, drop it from the
+window, refill, emit the next window's static / dynamic / masks).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from .containers import BatchedContainers
+from .ops import _dev, _p, _stream
+
+
+def pack_graphs(adj):
+    """adj [B,5,T,T] 0/1 with adj[b,g,u,v] = edge u -> v (deps_g[u,v] == True, generate.py:1636-1664)
+    -> predecessor masks int64 [B,5,T]: bit u of pred[b,g,v]."""
+    adj = np.asarray(adj)
+    B, G, T, _ = adj.shape
+    assert G == 5 and T <= 64
+    w = (np.uint64(1) << np.arange(T, dtype=np.uint64))[None, None, :, None]
+    pred = (adj.astype(np.uint64) * w).sum(axis=2, dtype=np.uint64)
+    return pred.view(np.int64)
+
+
+class BatchedInitialContainers(object):
+    """B generate.InitialContainer objects.  graphs: int64 [B,5,T] predecessor masks (pack_graphs) or the [B,5,T,T]
+    adjacency; blocks: [B,R*T,dim] rotation-major block sizes (rolling.py:483-485)."""
+
+    def __init__(self, graphs, blocks, blocks_num, child_graph_size, block_dim, device=None,
+                 node_order=_capi.WINDOW_ORDER_REFERENCE, input_type="bot"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tapenv: a CUDA device is required (no CPU fallback exists)")
+        if input_type != "bot":
+            raise _capi.TapEnvError(_capi.EUNSUPPORTED, "InitialContainer.convert_to_input only works for 'bot' inputs (generate.py:1790-1806)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        graphs = np.asarray(graphs) if not isinstance(graphs, torch.Tensor) else graphs
+        if not isinstance(graphs, torch.Tensor):
+            if graphs.ndim == 4:
+                graphs = pack_graphs(graphs)
+            graphs = torch.from_numpy(np.ascontiguousarray(graphs, dtype=np.int64))
+        if not isinstance(blocks, torch.Tensor):
+            blocks = torch.from_numpy(np.ascontiguousarray(blocks, dtype=np.int32))
+        self.blocks_num, self.child_graph_size, self.block_dim = int(blocks_num), int(child_graph_size), int(block_dim)
+        self.rotate_types = math.factorial(self.block_dim)
+        B = int(graphs.shape[0])
+        T, n, R, dim = self.blocks_num, self.child_graph_size, self.rotate_types, self.block_dim
+        if tuple(graphs.shape) != (B, 5, T) or tuple(blocks.shape) != (B, R * T, dim):
+            raise _capi.TapEnvError(_capi.ESHAPE, "graphs %s / blocks %s" % (tuple(graphs.shape), tuple(blocks.shape)))
+        self.batch_size = B
+        self.S = n * R
+        self.wcfg = _capi.WindowConfig(B, T, n, dim, R, int(node_order))
+        nbytes = int(_capi.lib.tapenv_window_state_bytes(C.byref(self.wcfg)))
+        if B > 0 and nbytes == 0:
+            raise _capi.TapEnvError(_capi.ELIMIT, "window config (total_blocks <= 64, window <= 32, window*R <= 64)")
+        self.graphs = graphs.to(self.device, torch.int64).contiguous()
+        self.blocks = blocks.to(self.device, torch.int32).contiguous()
+        self.state = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=self.device)
+        self.sub_graph_nodes = torch.full((B, n), -1, dtype=torch.int32, device=self.device)   # sorted, as generate.py:1766 leaves it
+        self.remaining = torch.full((B,), T, dtype=torch.int32, device=self.device)             # len(after_nodes_list)
+        self._pending = None
+        self.reset()
+
+    def reset(self):
+        """Back to the freshly constructed InitialContainer (generate.py:1666-1673)."""
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_window_reset(C.byref(self.wcfg), _p(self.state), _stream()), "window_reset")
+        self._pending = None
+
+    # ---- the reference's three calls ------------------------------------------------------------------
+    def remove_block(self, ptr):
+        """rolling.py:636-640 for the whole batch: drop sub_graph_nodes[ptr mod n] of every instance.  Like the
+        reference ("the graph will update when you call convert_to_input", generate.py:1811) the removal is applied by
+        the next convert_to_input launch."""
+        self._pending = _dev(ptr, "ptr", torch.int64)
+
+    def convert_to_input(self, out=None, masks=None):
+        """-> (static f32 [B,1+dim,S], dynamic f32 [B,3n,S]) (generate.py:1770-1808).  masks=(cur, mask) optionally
+        receives the initial masks rolling.DRL.forward derives from `dynamic` (rolling.py:325-335)."""
+        B, n, S, dim = self.batch_size, self.child_graph_size, self.S, self.block_dim
+        if out is None:
+            static = torch.empty(B, 1 + dim, S, dtype=torch.float32, device=self.device)
+            dynamic = torch.empty(B, 3 * n, S, dtype=torch.float32, device=self.device)
+        else:
+            static, dynamic = out
+        cur, mask = masks if masks is not None else (None, None)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_window_next(C.byref(self.wcfg), _p(self.state), _p(self.graphs), _p(self.blocks),
+                                                     _p(self._pending), _p(static), _p(dynamic), _p(cur), _p(mask),
+                                                     _p(self.sub_graph_nodes), _p(self.remaining), _stream()), "window_next")
+        self._pending = None
+        return static, dynamic
+
+    def is_last_graph(self):
+        """generate.py:1824-1825 per instance -> bool [B] (device).  Every instance admits exactly one node per call
+        after the first, so the flags agree across a batch of equally sized instances."""
+        return self.remaining == 0
+
+    # ---- state views ------------------------------------------------------------------------------------
+    @property
+    def flags(self):
+        """int32 [B] sticky: 1 no in-degree-0 node (the reference would spin), 2 window not full at convert (the reference
+        raises), 4 pointer outside the window."""
+        return self.state.view(torch.int32).view(self.batch_size, 16)[:, 13]
+
+    def check_flags(self):
+        bad = int((self.flags != 0).sum().item())
+        if bad:
+            raise IndexError("tapenv: %d rolling window(s) in an invalid state (flags %s)" % (bad, sorted(set(self.flags.tolist()) - {0})))
+
+
+class RollingRunner(object):
+    """rolling.validate's loop (rolling.py:589-640) + the env section of rolling.DRL.forward for B instances, the
+    network replaced by a pointer source.  Per instance: T - n + 1 windows; the first T - n are decoded for ONE step
+    (one_step=True), the last completely.  `step(ptr)` is one launch while windows remain, the fused decode step
+    (tapenv_step) inside the last window."""
+
+    def __init__(self, env, windows, ptr_seq=None, use_graph=False, partial_sums=True, exchange=None):
+        assert isinstance(env, BatchedContainers) and isinstance(windows, BatchedInitialContainers)
+        assert env.batch_size == windows.batch_size and env.window == windows.child_graph_size
+        assert env.blocks_num >= windows.blocks_num, "the container must hold total_blocks_num blocks (rolling.py:702-703)"
+        self.env, self.win = env, windows
+        B, n, S, dim = env.batch_size, windows.child_graph_size, windows.S, windows.block_dim
+        dev = env.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.static = [torch.empty(B, 1 + dim, S, **f32) for _ in range(2)]
+        self.dynamic = [torch.empty(B, 3 * n, S, **f32) for _ in range(2)]
+        self.cur = [torch.empty(B, S, **f32) for _ in range(2)]
+        self.mask = [torch.empty(B, S, **f32) for _ in range(2)]
+        self.dec_static = torch.empty(B, dim, **f32)
+        self.dec_dyn = torch.empty(B, env.enc_len, **f32)
+        self.total = windows.blocks_num
+        self.t = 0
+        self.slot = 0                                 # ping-pong index of dynamic / masks
+        self.sslot = 0                                # ... of static (unchanged inside the last window)
+        # whole-episode replay of a recorded pointer sequence int64 [T,B] (EpisodeRunner's interface)
+        self.ptr_seq = ptr_seq
+        self.partial_sums = partial_sums
+        self.exchange = exchange
+        self.reward = self.sums = self.total_sums = None
+        # clear + window reset + first window + T steps + reward (+ sums)
+        self.launches_per_episode = 3 + self.total + 1 + (1 if (partial_sums or exchange is not None) else 0)
+        self.graph = None
+        if use_graph:
+            assert ptr_seq is not None
+            self._capture()
+
+    @property
+    def steps_total(self):
+        return self.total
+
+    def begin(self):
+        """clear_container (rolling.py:659) + a fresh InitialContainer + the first window -> (static, dynamic, cur_mask)."""
+        self.env.clear_container()
+        self.win.reset()
+        self.t, self.slot, self.sslot = 0, 0, 0
+        self.win.convert_to_input(out=(self.static[0], self.dynamic[0]), masks=(self.cur[0], self.mask[0]))
+        return self.static[0], self.dynamic[0], self.cur[0]
+
+    def step(self, ptr):
+        """One decode step for every instance; returns (static, dynamic, cur_mask, decoder_static, decoder_dynamic)
+        the network sees next."""
+        env, win = self.env, self.win
+        ptr = _dev(ptr, "ptr", torch.int64)
+        n, T = win.child_graph_size, self.total
+        s = self.slot
+        if self.t < T - n:                             # one_step window: place + advance the window, ONE launch
+            o = s ^ 1
+            with torch.cuda.device(env.device):
+                _capi.check(_capi.lib.tapenv_rolling_step(
+                    C.byref(env.cfg), _p(env.state), C.byref(win.wcfg), _p(win.state), _p(win.graphs), _p(win.blocks),
+                    _p(ptr), _p(self.dec_static), _p(self.dec_dyn), _p(self.static[self.sslot ^ 1]), _p(self.dynamic[o]),
+                    _p(self.cur[o]), _p(self.mask[o]), _p(win.sub_graph_nodes), _p(win.remaining), _stream()), "rolling_step")
+            env._version += 1
+            self.slot = o
+            self.sslot ^= 1
+        else:                                          # last window: the ordinary fused decode step
+            o = s ^ 1
+            env.step(ptr, self.static[self.sslot], self.dynamic[s], self.mask[s],
+                     out=(self.dynamic[o], self.cur[o], self.mask[o], self.dec_static, self.dec_dyn))
+            self.slot = o
+        self.t += 1
+        o = self.slot
+        return self.static[self.sslot], self.dynamic[o], self.cur[o], self.dec_static, env._shape_enc(self.dec_dyn)
+
+    def _episode(self):
+        self.begin()
+        for t in range(self.total):
+            self.step(self.ptr_seq[t])
+        if self.exchange is not None:
+            self.reward, self.sums, self.total_sums = self.env.calc_ratio(exchange=self.exchange)
+        else:
+            res = self.env.calc_ratio(partial_sums=self.partial_sums)
+            self.reward, self.sums = res if self.partial_sums else (res, None)
+
+    def _capture(self):
+        dev = self.env.device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            self._episode()                           # warm-up outside capture
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._episode()
+        self.graph = g
+
+    def run(self, ptr_seq=None):
+        """One rolling episode for every instance with the recorded pointers int64 [T,B] (given here, or the
+        `ptr_seq` buffer handed to the constructor -- required for CUDA-graph replay); returns calc_ratio f32 [B]."""
+        if ptr_seq is not None:
+            assert self.graph is None, "a captured runner replays its own ptr_seq buffer"
+            self.ptr_seq = ptr_seq
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._episode()
+        return self.reward
+
+
+class RollingHostPipeline(object):
+    """Rolling episodes whose inputs live in HOST memory (what rolling.RollingDataset holds per instance: the
+    precedence graphs and the block list): double-buffered H2D upload of (graphs, blocks, ptr_seq) on a copy stream,
+    episode replay on the compute stream, D2H of rewards + sums.  Same protocol as runner.HostPipeline."""
+
+    def __init__(self, env, total_blocks, window, depth=2, use_graph=True, exchange=None,
+                 node_order=_capi.WINDOW_ORDER_REFERENCE):
+        self.env = env
+        dev = env.device
+        B, dim = env.batch_size, env.block_dim
+        R = math.factorial(dim)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(depth):
+            graphs = torch.zeros(B, 5, total_blocks, dtype=torch.int64, device=dev)
+            blocks = torch.ones(B, R * total_blocks, dim, dtype=torch.int32, device=dev)
+            pq = torch.zeros(total_blocks, B, dtype=torch.int64, device=dev)
+            win = BatchedInitialContainers(graphs, blocks, total_blocks, window, dim, device=dev, node_order=node_order)
+            runner = RollingRunner(env, win, ptr_seq=pq, use_graph=use_graph, partial_sums=True, exchange=exchange)
+            self.slots.append(dict(win=win, ptr=pq, runner=runner, uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(),
+                                   done=torch.cuda.Event(), reward=torch.empty(B, dtype=torch.float32).pin_memory(),
+                                   sums=torch.empty(3, dtype=torch.float64).pin_memory(), busy=False))
+        self.head = self.tail = self.inflight = 0
+        self.h2d_bytes = B * 5 * total_blocks * 8 + B * R * total_blocks * dim * 4 + total_blocks * B * 8
+        self.d2h_bytes = B * 4 + 24
+
+    def submit(self, graphs_h, blocks_h, ptr_h, after_episode=None):
+        if self.inflight == self.depth:
+            raise RuntimeError("pipeline full: call result() first")
+        s = self.slots[self.head]
+        compute = torch.cuda.current_stream(self.env.device)
+        with torch.cuda.stream(self.copy_stream):
+            if s["busy"]:
+                self.copy_stream.wait_event(s["consumed"])
+            s["win"].graphs.copy_(graphs_h, non_blocking=True)
+            s["win"].blocks.copy_(blocks_h, non_blocking=True)
+            s["ptr"].copy_(ptr_h, non_blocking=True)
+            s["uploaded"].record(self.copy_stream)
+        compute.wait_event(s["uploaded"])
+        r = s["runner"].run()
+        s["consumed"].record(compute)
+        if after_episode is not None:
+            after_episode(s["runner"])
+        s["reward"].copy_(r, non_blocking=True)
+        run = s["runner"]
+        s["sums"].copy_(run.total_sums if run.total_sums is not None else run.sums, non_blocking=True)
+        s["done"].record(compute)
+        s["busy"] = True
+        self.head = (self.head + 1) % self.depth
+        self.inflight += 1
+
+    def result(self):
+        if self.inflight == 0:
+            raise RuntimeError("nothing in flight")
+        s = self.slots[self.tail]
+        s["done"].synchronize()
+        self.tail = (self.tail + 1) % self.depth
+        self.inflight -= 1
+        return s["reward"], s["sums"]

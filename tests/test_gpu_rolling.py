@@ -1,0 +1,193 @@
+"""GPU parity of the rolling window (tapenv_window_next / tapenv_rolling_step, generate.InitialContainer +
+rolling.validate's loop) through the C ABI: bit-exact against the trajectories recorded from the live reference and
+against the CPU oracle on larger seeded batches."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from tests.golden_io import load_rolling, load_traj
+
+pytestmark = pytest.mark.gpu
+
+
+def _tapenv():
+    import tapenv
+    return tapenv
+
+
+def _dyn_from_bits(bits, n, S):
+    return np.unpackbits(bits)[:3 * n * S].reshape(3 * n, S).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["traj_rolling_3d", "traj_rolling_2d"])
+def test_window_sequence_vs_reference_trajectory(name):
+    """convert_to_input / remove_block / is_last_graph replayed with the reference's own pointers."""
+    tapenv = _tapenv()
+    traj = load_traj(name)
+    num, n = int(traj["num"]), int(traj["window"])
+    data = load_rolling(str(traj["source"]), num)
+    T, dim = data["T"], data["dim"]
+    win = tapenv.BatchedInitialContainers(data["adj"], data["blocks"], T, n, dim)
+    S = win.S
+    calls = traj["static"].shape[1]
+    ptrs = traj["ptr"]                                    # [num, T]
+    t = 0
+    for c in range(calls):
+        cur = torch.empty(num, S, device="cuda"); mask = torch.empty(num, S, device="cuda")
+        static, dynamic = win.convert_to_input(masks=(cur, mask))
+        assert np.array_equal(static.cpu().numpy(), traj["static"][:, c].astype(np.float32)), c
+        ref_dyn = np.stack([_dyn_from_bits(traj["dynamic_bits"][b, c], n, S) for b in range(num)])
+        assert np.array_equal(dynamic.cpu().numpy(), ref_dyn), c
+        assert np.array_equal(win.sub_graph_nodes.cpu().numpy(), traj["nodes"][:, c]), c
+        assert np.array_equal(cur.cpu().numpy(), oracle.initial_mask(ref_dyn, n, win.rotate_types))
+        assert bool((mask == 1).all())
+        last = bool(win.is_last_graph().all())
+        assert last == (c == calls - 1) and bool(win.is_last_graph().any()) == last
+        t += n if last else 1
+        win.remove_block(torch.from_numpy(ptrs[:, t - 1].astype(np.int64)).cuda())
+    win.check_flags()
+
+
+@pytest.mark.parametrize("name", ["traj_rolling_3d", "traj_rolling_2d"])
+def test_rolling_runner_vs_reference_trajectory(name):
+    """The fused rolling decode step: heightmap and returned encoding after EVERY step, final positions / stable /
+    calc_ratio, against the live-reference recording."""
+    tapenv = _tapenv()
+    traj = load_traj(name)
+    num, n = int(traj["num"]), int(traj["window"])
+    data = load_rolling(str(traj["source"]), num)
+    T, dim = data["T"], data["dim"]
+    size = traj["container_size"].tolist()
+    env = tapenv.BatchedContainers(size, T, str(traj["reward_type"]), str(traj["heightmap_type"]),
+                                   packing_strategy=str(traj["packing_strategy"]), batch_size=num, window=n)
+    win = tapenv.BatchedInitialContainers(data["adj"], data["blocks"], T, n, dim)
+    run = tapenv.RollingRunner(env, win)
+    S = win.S
+    static, dynamic, cur = run.begin()
+    call = 0
+    for t in range(T):
+        if t <= T - n:                                    # a fresh window is visible at the start of these steps
+            assert np.array_equal(static.cpu().numpy(), traj["static"][:, call].astype(np.float32)), t
+            ref_dyn = np.stack([_dyn_from_bits(traj["dynamic_bits"][b, call], n, S) for b in range(num)])
+            assert np.array_equal(dynamic.cpu().numpy(), ref_dyn), t
+            call += 1
+        ptr = torch.from_numpy(traj["ptr"][:, t].astype(np.int64)).cuda()
+        assert bool(torch.gather(cur, 1, ptr[:, None]).eq(1).all()), "recorded pointer must be accessible"
+        static, dynamic, cur, dec_static, dec_dyn = run.step(ptr)
+        assert np.array_equal(env.heightmap.cpu().numpy().reshape(num, -1), traj["heightmap"][:, t]), t
+        assert np.array_equal(dec_dyn.cpu().numpy().reshape(num, -1), traj["dec_dyn"][:, t].astype(np.float32)), t
+    assert np.array_equal(env.positions.cpu().numpy(), traj["positions"])
+    assert np.array_equal(env.stable.cpu().numpy(), traj["stable"])
+    r = env.calc_ratio().cpu().numpy().astype(np.float64)
+    assert np.abs(r - traj["ratio"]).max() <= 1e-6
+    env.check_flags(); win.check_flags()
+
+
+def _record_policy(run, T, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    static, dynamic, cur = run.begin()
+    ptrs = []
+    for t in range(T):
+        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+        ptrs.append(ptr)
+        static, dynamic, cur, _, _ = run.step(ptr)
+    return torch.stack(ptrs)
+
+
+@pytest.mark.parametrize("src,B,size,rt,strat", [
+    ("rolling3d_t50.npz", 2048, [5, 5, 250], "C+P+S-lb-soft", "LB_GREEDY"),
+    ("rolling2d_t50.npz", 1024, [5, 250], "C+P+S-lb-hard", "LB_GREEDY"),
+    ("rolling2d_t50.npz", 512, [7, 250], "C+P+S-mcs-soft", "MACS"),
+])
+def test_rolling_batch_vs_oracle(src, B, size, rt, strat):
+    """Large tiled batches under an on-device random-valid policy, against the threaded CPU oracle driver."""
+    tapenv = _tapenv()
+    data = load_rolling(src)
+    pool, T, dim = data["adj"].shape[0], data["T"], data["dim"]
+    idx = np.arange(B) % pool
+    adj, blocks = data["adj"][idx], data["blocks"][idx]
+    n = 10
+    env = tapenv.BatchedContainers(size, T, rt, "diff", packing_strategy=strat, batch_size=B, window=n)
+    win = tapenv.BatchedInitialContainers(adj, blocks, T, n, dim)
+    run = tapenv.RollingRunner(env, win)
+    ptr_seq = _record_policy(run, T, seed=7)
+    r = env.calc_ratio().cpu().numpy()
+    hm = env.heightmap.cpu().numpy().reshape(B, -1)
+    env.check_flags(); win.check_flags()
+    o = oracle.rolling_batch(adj, blocks, ptr_seq.cpu().numpy(), size, n, rt, "diff", strat, nthreads=8)
+    assert o["status"] == 0
+    assert np.array_equal(hm, o["heightmap"])
+    assert np.abs(r.astype(np.float64) - o["reward"].astype(np.float64)).max() <= 1e-6
+    # replay reproduces itself (state fully reset by begin())
+    r2 = run.run(ptr_seq).cpu().numpy()
+    assert np.array_equal(r, r2)
+
+
+@pytest.mark.parametrize("src,T,n,order", [
+    ("rolling2d_t50.npz", 50, 20, 0),     # 20-node windows: CPython's set table grows to 128 slots (sequential path)
+    ("rolling2d_t50.npz", 50, 9, 0),      # S = 18: scalar emission path
+    ("rolling2d_t50.npz", 50, 25, 0),     # 2n >= T: networkx enumerates in ascending order
+    ("rolling2d_t50.npz", 50, 10, 1),     # TAPENV_WINDOW_ORDER_SORTED
+    ("rolling3d_t50.npz", 50, 7, 0),      # S = 42: scalar path in 3D
+    ("rolling3d_t50.npz", 50, 10, 1),
+    ("rolling2d_t50.npz", 50, 50, 0),     # window == total: not representable (S > 64) -> error, see below
+])
+def test_window_shapes_vs_oracle(src, T, n, order):
+    tapenv = _tapenv()
+    num = 48
+    data = load_rolling(src, num)
+    dim = data["dim"]
+    R = 2 if dim == 2 else 6
+    if n * R > 64:
+        with pytest.raises(ValueError):
+            tapenv.BatchedInitialContainers(data["adj"], data["blocks"], T, n, dim, node_order=order)
+        return
+    win = tapenv.BatchedInitialContainers(data["adj"], data["blocks"], T, n, dim, node_order=order)
+    ocs = [oracle.InitialContainer(data["adj"][b], data["blocks"][b], T, n, dim, order=order) for b in range(num)]
+    rng = np.random.RandomState(3)
+    S = n * R
+    for call in range(T - n + 1):
+        static, dynamic = win.convert_to_input()
+        outs = [oc.convert_to_input() for oc in ocs]
+        assert np.array_equal(static.cpu().numpy(), np.stack([o[0] for o in outs])), call
+        dref = np.stack([o[1] for o in outs])
+        assert np.array_equal(dynamic.cpu().numpy(), dref), call
+        assert np.array_equal(win.sub_graph_nodes.cpu().numpy(), np.array([oc.sub_graph_nodes for oc in ocs])), call
+        last = all(oc.is_last_graph() for oc in ocs)
+        assert bool(win.is_last_graph().all()) == last
+        if last:
+            break
+        cur = oracle.initial_mask(dref, n, R)
+        u = rng.random_sample((num, S)) * (cur > 0) + 1e-9 * rng.random_sample((num, S))
+        ptr = np.argmax(u, axis=1).astype(np.int64)
+        for b, oc in enumerate(ocs):
+            oc.remove_block(oc.sub_graph_nodes[int(ptr[b]) % n])
+        win.remove_block(torch.from_numpy(ptr).cuda())
+    win.check_flags()
+
+
+def test_window_flags_and_errors():
+    tapenv = _tapenv()
+    data = load_rolling("rolling2d_t50.npz", 4)
+    win = tapenv.BatchedInitialContainers(data["adj"], data["blocks"], 50, 10, 2)
+    win.convert_to_input()
+    win.remove_block(torch.tensor([0, 19, 20, -1], dtype=torch.int64, device="cuda"))      # 20 and -1 are outside [0,S)
+    win.convert_to_input()
+    assert win.flags.cpu().tolist() == [0, 0, 4, 4]
+    with pytest.raises(IndexError):
+        win.check_flags()
+    # a cyclic movement graph: the reference would never return
+    adj = data["adj"].copy()
+    adj[:, 0] = 0
+    for u in range(50):
+        adj[0, 0, u, (u + 1) % 50] = 1
+    cyc = tapenv.BatchedInitialContainers(adj, data["blocks"], 50, 10, 2)
+    cyc.convert_to_input()
+    f = cyc.flags.cpu().tolist()
+    assert f[0] & 1 and f[1] == 0
+    with pytest.raises(ValueError):
+        tapenv.BatchedInitialContainers(data["adj"], data["blocks"], 50, 10, 2, input_type="rot")
+    empty = tapenv.BatchedInitialContainers(data["adj"][:0], data["blocks"][:0], 50, 10, 2)
+    s, d = empty.convert_to_input()
+    assert s.shape == (0, 3, 20) and d.shape == (0, 30, 20)
