@@ -628,6 +628,52 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * steps_per_episode * args.steps / float(te.item())
     assert np.array_equal(rw_pin.numpy(), reward_ref.cpu().numpy())
+
+    # ---- e2e, packed upload: the same episodes fed from the loader's compact host format (u8 static, bit-row dynamic:
+    # tapenv.pack_inputs / PACKDataset.packed()); the fp32 tensors are produced on the device by tapenv_reset_packed ----
+    e2e_packed = None
+    if Wn == 1 and strat != "LB":
+        su8, bits = tapenv.pack_inputs(static_h[0], dynamic_h[0])
+        su8_pin, bits_pin = torch.from_numpy(su8).pin_memory(), torch.from_numpy(bits).pin_memory()
+        pipe_p = tapenv.HostPipeline(env, n, depth=2, use_graph=not args.no_graph, windows=1, exchange=exchange, packed=True)
+
+        def e2e_packed_run(k):
+            last = None
+            for i in range(k):
+                if pipe_p.inflight == pipe_p.depth:
+                    last = pipe_p.result()
+                pipe_p.submit(su8_pin, bits_pin, pq_pin, after_episode=after)
+            while pipe_p.inflight:
+                last = pipe_p.result()
+            return last
+
+        e2e_packed_run(3)
+        barrier()
+        t0 = time.perf_counter()
+        rwp, _ = e2e_packed_run(args.steps)
+        barrier()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        assert np.array_equal(rwp.numpy(), reward_ref.cpu().numpy())
+        e2e_packed = {"value": world * B * steps_per_episode * args.steps / float(tp.item()), "unit": UNIT,
+                      "h2d_bytes_per_step": int(pipe_p.h2d_bytes), "d2h_bytes_per_step": int(pipe_p.d2h_bytes),
+                      "ms_per_step": 1e3 * float(tp.item()) / args.steps,
+                      "api": "tapenv.HostPipeline(packed=True): u8 static + bit-row dynamic + ptr_seq from pinned host memory, "
+                             "expanded to the fp32 tensors on the device (tapenv_reset_packed)"}
+    # plain pinned H2D bandwidth of this box, for reading the e2e numbers (the fp32 path is PCIe-bound)
+    big = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    big_d = torch.empty_like(big, device=dev)
+    big_d.copy_(big, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eh0.record()
+    for _ in range(4):
+        big_d.copy_(big, non_blocking=True)
+    eh1.record()
+    torch.cuda.synchronize(dev)
+    h2d_gbs = 4 * big.numel() / (eh0.elapsed_time(eh1) * 1e-3) / 1e9
+    del big, big_d
     clocks = sampler.result()
 
     # ---- extra: the whole-episode kernel (K7, tapenv_episode): one launch per episode, no intermediate tensors ----
@@ -691,7 +737,9 @@ def run_ours(args):
             "device_ms_sum_per_step": dev_ms / args.steps, "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
-                    "api": "tapenv.HostPipeline.submit/result (double-buffered upload + BatchedContainers.reset/step/calc_ratio), pinned host buffers"},
+                    "api": "tapenv.HostPipeline.submit/result (double-buffered upload + BatchedContainers.reset/step/calc_ratio), pinned host buffers",
+                    "h2d_gbs_achieved": pipe.h2d_bytes * args.steps / float(te.item()) / 1e9, "h2d_gbs_box": h2d_gbs},
+            "e2e_packed": e2e_packed,
             "episode_kernel": k7,
             "roofline": {"bound": "hbm", "kernel": "step_kernel (fused update_dynamic+update_mask+add_new_block)",
                          "achieved": achieved, "peak": peak,

@@ -164,6 +164,17 @@ int tapenv_reset(const tapenv_config *cfg, void *state, const float *dynamic,
 int tapenv_initial_mask(const tapenv_config *cfg, const float *dynamic, float *cur_mask_out, float *mask_out,
                         void *stream);
 
+/* K0 for a packed host format.  The dataset tensors are small integers (static, pack.py:144-147) and 0/1 flags
+ * (dynamic, pack.py:101-223) stored as fp32; a loader may keep and upload them as u8 / bit rows (20x fewer PCIe
+ * bytes per batch than trainer.py:189-192's `.cuda()` of the fp32 tensors) and expand them on the device:
+ *   static_u8    u8  [B, static_rows, S]
+ *   dynamic_bits u32 [B, tapenv_packed_words()]: bit (row*S + col) -- word (q >> 5), bit (q & 31) -- <=> dynamic[row,col] == 1
+ * Writes the fp32 tensors (static_out [B,static_rows,S], dynamic_out [B,dyn_rows,S]), clears the containers when
+ * state != NULL (tools.py:3611-3661) and emits the initial masks (model.py:297-307) -- tapenv_reset on packed input. */
+int32_t tapenv_packed_words(const tapenv_config *cfg);
+int tapenv_reset_packed(const tapenv_config *cfg, void *state, const uint8_t *static_u8, const uint32_t *dynamic_bits,
+                        float *static_out, float *dynamic_out, float *cur_mask_out, float *mask_out, void *stream);
+
 /* pack.update_dynamic(dynamic, static, chosen_idx, input_type, allow_rot) (pack.py:333-376).
  * Out-of-place; block id is read from static[:,0,ptr] (pack.py:347). */
 int tapenv_update_dynamic(const tapenv_config *cfg, const float *dynamic, const float *static_,

@@ -266,6 +266,84 @@ reset_kernel(DevCfg c, StatePtrs st, int clear_state, const float *__restrict__ 
     mask_pass<SH>(c, lane, false, 0.f, 0.f, -1, bits.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
 }
 
+
+// ------------------------------------------------------------------------------------
+// K0 for packed host formats: the dataset's tensors hold small integers (static) and 0/1 (dynamic) in fp32
+// (pack.py:101-223), 2 720 B per environment at C2 of which 135 B are information.  A loader that keeps them as
+// u8 / bit rows uploads 20x fewer PCIe bytes; this kernel expands them into the fp32 tensors the network and the
+// step kernels consume, clears the containers and derives the initial masks (model.py:294-307) in one launch.
+// Bit q = row*S + col of `bits` (u32 words, little-endian bit order) <=> dynamic[row, col] == 1.
+// ------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+unpack_reset_kernel(DevCfg c, StatePtrs st, int clear_state, const unsigned char *__restrict__ static_u8,
+                    const unsigned *__restrict__ bits, int words_env, float *__restrict__ static_out,
+                    float *__restrict__ dynamic_out, float *__restrict__ cur_mask, float *__restrict__ mask) {
+    typedef Shape<0, 0, 0> SH;
+    __shared__ uint4 lut[16];                         // nibble -> four fp32 0/1 values
+    int lane, warp; const int b = env_index(lane, warp);
+    if (threadIdx.x < 16) {
+        const unsigned t = threadIdx.x, one = 0x3f800000u;
+        lut[t] = make_uint4((t & 1u) * one, ((t >> 1) & 1u) * one, ((t >> 2) & 1u) * one, ((t >> 3) & 1u) * one);
+    }
+    __syncthreads();
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const unsigned *wb = bits + (size_t)b * words_env;
+    if (clear_state) {
+        const int cells = c.dim == 2 ? c.W : c.W * c.L;
+        for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
+        for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
+        for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
+        if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
+    }
+    const unsigned char *su = static_u8 + (size_t)b * c.static_env;
+    float *so = static_out + (size_t)b * c.static_env;
+    for (int i = lane; i < (int)c.static_env; i += 32) so[i] = (float)su[i];
+    float *dyo = env_ptr(dynamic_out, b, c.dyn_env);
+    unsigned long long w[3] = {0ull, 0ull, 0ull};
+    if (FAST) {
+        const int rsub = (int)(((unsigned)lane * c.inv_SV) >> 16), cv = lane - rsub * c.SV;
+        const bool on = rsub < c.RP;
+        unsigned nibs[3] = {0u, 0u, 0u};
+        uint4 *dst = reinterpret_cast<uint4 *>(dyo) + lane;
+        const int pstride = c.RP * c.SV, bstride = c.n * c.SV;
+        for (int p = 0; p < c.PB; ++p) {
+            const int row = p * c.RP + rsub;
+            if (!(on && row < c.n)) continue;
+#pragma unroll
+            for (int bd = 0; bd < 3; ++bd) {
+                if (bd >= c.nbands) continue;
+                const int q0 = (bd * c.n + row) * c.S + 4 * cv;      // S % 4 == 0: the four bits share one word
+                const int wi = q0 >> 5;
+                const unsigned word = __ldg(wb + wi);                 // <= 300 B per environment: L1-resident after the first touch
+                const unsigned nib = (word >> (q0 & 31)) & 0xfu;
+                nibs[bd] |= nib;
+                stg_stream4(dst + p * pstride + bd * bstride, lut[nib]);
+            }
+        }
+#pragma unroll
+        for (int bd = 0; bd < 3; ++bd) {
+            const unsigned long long word = on ? ((unsigned long long)nibs[bd] << (4 * cv)) : 0ull;
+            w[bd] = (unsigned long long)warp_or((unsigned)word) | ((unsigned long long)warp_or((unsigned)(word >> 32)) << 32);
+        }
+    } else {
+        const int total = c.dyn_rows * c.S;
+        for (int q = lane; q < total; q += 32) {
+            const int row = q / c.S, col = q - row * c.S;
+            const int band = row / c.n;
+            const unsigned bit = (__ldg(wb + (q >> 5)) >> (q & 31)) & 1u;
+            if (band < 3) w[band] |= (unsigned long long)bit << col;
+            dyo[q] = bit ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int bd = 0; bd < 3; ++bd)
+            w[bd] = (unsigned long long)warp_or((unsigned)w[bd]) | ((unsigned long long)warp_or((unsigned)(w[bd] >> 32)) << 32);
+    }
+    BandBits bb; bb.move = w[0]; bb.small = w[1]; bb.large = w[2];
+    mask_pass<SH>(c, lane, false, 0.f, 0.f, -1, bb.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
+}
+
 // ------------------------------------------------------------------------------------
 // unfused pieces (signature parity with pack.update_dynamic / pack.update_mask / add_new_block)
 // ------------------------------------------------------------------------------------
@@ -692,8 +770,14 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
               int *__restrict__ remaining_out) {
     constexpr int ES = STRAT < 0 ? STRAT_LBG2D : STRAT;
     __shared__ WinShared shs[kWarpsPerCta];
+    __shared__ uint4 lut[16];                         // nibble -> four fp32 0/1 values
     __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
     int lane, warp; const int b = env_index(lane, warp);
+    if (threadIdx.x < 16) {
+        const unsigned t = threadIdx.x, one = 0x3f800000u;
+        lut[t] = make_uint4((t & 1u) * one, ((t >> 1) & 1u) * one, ((t >> 2) & 1u) * one, ((t >> 3) & 1u) * one);
+    }
+    __syncthreads();
     grid_dependency_sync();
     if (b >= w.B) return;
     WinShared &sh = shs[warp];
@@ -732,7 +816,7 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
                 container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
         }
     }
-    window_advance<FAST>(w, sh, b, lane, gone, after, len, flags, rm, ws, pe, pm0, pm1, blk, static_out, dynamic_out,
+    window_advance<FAST>(w, sh, lut, b, lane, gone, after, len, flags, rm, ws, pe, pm0, pm1, blk, static_out, dynamic_out,
                          cur_mask, mask_out, nodes_out, remaining_out);
 }
 
@@ -1022,6 +1106,33 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
     return launch_status();
 }
 
+int32_t tapenv_packed_words(const tapenv_config *cfg) {
+    if (check_cfg(cfg) != TAPENV_OK) return -1;
+    const int bitsn = cfg->dyn_rows * cfg->blocks_num * cfg->rotate_types;
+    return ((bitsn + 31) / 32 + 3) / 4 * 4;                             // rows of 16-byte multiples
+}
+
+int tapenv_reset_packed(const tapenv_config *cfg, void *state, const uint8_t *static_u8, const uint32_t *dynamic_bits,
+                        float *static_out, float *dynamic_out, float *cur_mask_out, float *mask_out, void *stream) {
+    TAPENV_PROLOGUE(cfg)
+    if (d.B == 0) return TAPENV_OK;
+    if (!static_u8 || !dynamic_bits || !static_out || !dynamic_out || !cur_mask_out) return TAPENV_EINVAL;
+    StatePtrs st; memset(&st, 0, sizeof(st));
+    if (state) st = stateptrs_of(cfg, state);
+    const int words = tapenv_packed_words(cfg);
+    const int clear = state && cfg->strategy != TAPENV_LB ? 1 : 0;
+    if (state && cfg->strategy == TAPENV_LB) {                          // LB keeps voxel grids / x lists: cleared by the plain reset
+        launch(reset_kernel<false>, grid, block, s, d, st, 1, (const float *)nullptr, (float *)nullptr, (float *)nullptr);
+    }
+    if (fast_ok(d, dynamic_out, nullptr) && d.SV * d.RP <= 32)
+        launch(unpack_reset_kernel<true>, grid, block, s, d, st, clear, (const unsigned char *)static_u8, (const unsigned *)dynamic_bits, words,
+               static_out, dynamic_out, cur_mask_out, mask_out);
+    else
+        launch(unpack_reset_kernel<false>, grid, block, s, d, st, clear, (const unsigned char *)static_u8, (const unsigned *)dynamic_bits, words,
+               static_out, dynamic_out, cur_mask_out, mask_out);
+    return launch_status();
+}
+
 // ---- rolling window ---------------------------------------------------------------------------------------------
 static int check_wcfg(const tapenv_window_config *w) {
     if (!w) return TAPENV_EINVAL;
@@ -1047,6 +1158,14 @@ static WinCfg wincfg_of(const tapenv_window_config *w) {
     // code 0 -> (left,right), 1 -> (forward,backward), 2 -> zeros; in 2D a last axis of 1 is the vertical one (generate.py:1802-1806)
     d.lastcodes = d.dim == 2 ? (2u | (0u << 2)) : (2u | (1u << 2) | (2u << 4) | (0u << 6) | (1u << 8) | (0u << 10));
     d.blocks_env = (unsigned)(d.R * d.T * d.dim);
+    d.mul_all = d.mul_c0 = d.mul_c1 = 0ull;
+    for (int r = 0; r < d.R; ++r) {
+        const unsigned code = (d.lastcodes >> (2 * r)) & 3u;
+        const unsigned long long bit = 1ull << (r * d.n);
+        d.mul_all |= bit;
+        if (code == 0u) d.mul_c0 |= bit;
+        if (code == 1u) d.mul_c1 |= bit;
+    }
     return d;
 }
 

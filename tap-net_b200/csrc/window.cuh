@@ -16,7 +16,8 @@
 // P is NOT the sorted window when 2*window < total: networkx's subgraph view then enumerates the Python *set* of the
 // window nodes (coreviews.FilterAtlas.__iter__), whose order is CPython's open-addressing layout (setobject.c).  The
 // reference indexes `dynamic` by P while `static` uses the sorted list; this is reproduced bit-exactly -- the
-// 8/32-slot table lives one slot per lane and an insertion is a ballot + find-first-set over the probe window.
+// probe sequence of every insertion runs on warp-uniform values (8-slot table = one 64-bit word, 32-slot table = an
+// occupancy word + one slot per lane).
 #pragma once
 #include "tapenv_common.cuh"
 
@@ -33,10 +34,13 @@ struct WinCfg {
     unsigned inv_n, inv_SV;  // ceil(65536/d)
     unsigned lastcodes;      // 2 bits per rotation: 0 -> (left,right), 1 -> (forward,backward), 2 -> zeros (generate.py:1793-1806)
     unsigned blocks_env;     // R*T*dim
+    // replication multipliers: sum of 2^(r*n) over all rotations / those with code 0 / code 1 -- an n-bit sub-matrix row
+    // times one of these is that row repeated into the column blocks of the rotations it applies to
+    unsigned long long mul_all, mul_c0, mul_c1;
 };
 
 struct WinShared {           // per warp
-    unsigned colbits[6][32]; // [g][jj]: bit i' = sub_deps_g[i'][jj]; row 5 = zeros (up/down)
+    unsigned long long rows[96];   // dynamic row (band*n + i') as a bit row over the S candidate columns
     unsigned char list[32];  // window in list order (survivors sorted, then admissions), later sorted
     unsigned char perm[32];  // P
     unsigned char tab[2][128];   // sequential set emulation for windows above 18 nodes
@@ -44,40 +48,50 @@ struct WinShared {           // per warp
 
 __device__ __forceinline__ unsigned long long below64(int v) { return v >= 64 ? ~0ull : ((1ull << v) - 1ull); }
 
-// one CPython set insertion (set_add_entry / set_insert_clean probe order, distinct keys) into a table of mask+1 <= 32
-// slots held one per lane (`slot` < 0: unused)
-__device__ __forceinline__ void pyset_insert32(int &slot, int lane, int key, unsigned mask) {
-    unsigned i = (unsigned)key & mask, perturb = (unsigned)key;
-    const unsigned valid = mask >= 31u ? 0xffffffffu : ((1u << (mask + 1u)) - 1u);
+// one CPython set insertion (set_add_entry / set_insert_clean probe order, distinct keys) into the 32-slot table.  The
+// occupancy word `occ` and the key are warp-uniform, so the whole probe sequence runs on uniform values; only the owner
+// lane of the chosen slot records the key.
+__device__ __forceinline__ void pyset_insert32(unsigned &occ, int &slot, int lane, int key) {
+    unsigned i = (unsigned)key & 31u, perturb = (unsigned)key;
     for (int guard = 0; guard < 64; ++guard) {
-        const unsigned emptyb = __ballot_sync(TAPENV_FULL_MASK, slot < 0) & valid;
-        const unsigned probes = (i + 9u <= mask) ? 9u : 0u;                  // LINEAR_PROBES
-        const unsigned win = (emptyb >> i) & ((2u << probes) - 1u);
+        const unsigned probes = (i + 9u <= 31u) ? 9u : 0u;                   // LINEAR_PROBES
+        const unsigned win = ((~occ) >> i) & ((2u << probes) - 1u);
         if (win) {
-            if (lane == (int)(i + __ffs(win) - 1)) slot = key;
+            const unsigned s = i + (unsigned)__ffs((int)win) - 1u;
+            occ |= 1u << s;
+            if (lane == (int)s) slot = key;
             return;
         }
         perturb >>= 5;                                                       // PERTURB_SHIFT
-        i = (i * 5u + 1u + perturb) & mask;
+        i = (i * 5u + 1u + perturb) & 31u;
     }
 }
 
 // iteration order of set(list[0..len)) -> perm[0..len).  len <= 18 keeps CPython's table at <= 32 slots.
 __device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int len) {
     if (len <= 18) {
-        int slot = -1, fill = 0;
-        unsigned mask = 7u;
-        for (int q = 0; q < len; ++q) {
-            pyset_insert32(slot, lane, sh.list[q], mask);
-            ++fill;
-            if ((unsigned)fill * 5u >= mask * 3u && mask == 7u) {            // set_table_resize(used * 4): 8 -> 32 at fill 5
-                const int old = slot;
-                slot = -1; mask = 31u;
-                for (int s = 0; s < 8; ++s) {
-                    const int k = __shfl_sync(TAPENV_FULL_MASK, old, s);
-                    if (k >= 0) pyset_insert32(slot, lane, k, mask);
-                }
+        // the first 5 insertions go into the initial 8-slot table (mask 7: no linear probes, only the perturbed
+        // recurrence), kept as 8 bytes (key + 1, 0 = unused) of one uniform 64-bit word
+        unsigned long long t8 = 0ull;
+        const int first = len < 5 ? len : 5;
+        int q = 0;
+        for (; q < first; ++q) {
+            const unsigned key = sh.list[q];
+            unsigned i = key & 7u, perturb = key;
+            for (int guard = 0; guard < 64 && ((t8 >> (8u * i)) & 0xffull); ++guard) { perturb >>= 5; i = (i * 5u + 1u + perturb) & 7u; }
+            t8 |= (unsigned long long)(key + 1u) << (8u * i);
+        }
+        unsigned occ = 0u;
+        int slot = -1;
+        if (len < 5) {                                                       // fill * 5 < mask * 3: the table never grows
+            const unsigned byte = lane < 8 ? (unsigned)((t8 >> (8 * lane)) & 0xffull) : 0u;
+            slot = (int)byte - 1;
+        } else {                                                             // set_table_resize(used * 4): 8 -> 32 slots at fill 5,
+            for (int s = 0; s < 8; ++s) {                                    // old entries re-inserted in slot order
+                const int k = (int)((t8 >> (8 * s)) & 0xffull) - 1;
+                if (k >= 0) pyset_insert32(occ, slot, lane, k);
             }
+            for (; q < len; ++q) pyset_insert32(occ, slot, lane, sh.list[q]);
         }
         const unsigned full = __ballot_sync(TAPENV_FULL_MASK, slot >= 0);
         if (slot >= 0) sh.perm[__popc(full & ((1u << lane) - 1u))] = (unsigned char)slot;
@@ -123,7 +137,7 @@ __device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int le
 // remove_block(sub_graph_nodes[rm]) (rm < 0: nothing) + sub_deps_graph + convert_to_input for environment b.
 // On entry sh.list holds the stored window (list order == sorted).  Emits the tensors and stores the new state.
 template <bool FAST>
-__device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, int b, int lane, unsigned long long gone,
+__device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, const uint4 *lut, int b, int lane, unsigned long long gone,
                                                unsigned long long after, int len, int flags, int rm, unsigned *ws,
                                                const unsigned long long *__restrict__ pe, unsigned long long pm0,
                                                unsigned long long pm1, const int *__restrict__ blk,
@@ -171,29 +185,61 @@ __device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, i
     const unsigned long long mybit = mynode >= 0 ? (1ull << mynode) : 0ull;
     const unsigned long long winmask = (unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)mybit) |
                                        ((unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)(mybit >> 32)) << 32);
-    // ---- decompose: node enumeration P, five [n,n] sub-matrices as column words (generate.py:1682-1724, :1750-1764) ----
-    unsigned cb[5] = {0u, 0u, 0u, 0u, 0u};
+    // ---- decompose: node enumeration P, the five [n,n] sub-matrices (generate.py:1682-1724, :1750-1764) ----
+    // Lane jj holds the predecessor words of column node P[jj]; row i' of sub-matrix g is the ballot over the columns of
+    // "P[i'] is a predecessor of P[jj]" (+ the diagonal self-loop of the rotation graphs), kept by lane i'.
+    unsigned myrow[5] = {0u, 0u, 0u, 0u, 0u};
     if (decompose) {
         if (w.setorder) pyset_order_warp(sh, lane, len);
         else { if (mynode >= 0) sh.perm[__popcll(winmask & below64(mynode))] = (unsigned char)mynode; __syncwarp(); }
+        const int ng = w.dim == 3 ? 5 : 3;                  // 2D: forward/backward have no edges
+        unsigned lo[5] = {0u, 0u, 0u, 0u, 0u}, hi[5] = {0u, 0u, 0u, 0u, 0u};
+        unsigned loopbits = 0u;                             // bit g: a predecessor of this column still waits outside (:1690-1705)
         if (lane < len) {
             const int v = sh.perm[lane];
-            unsigned long long pg[5];
+            const unsigned alo = (unsigned)after, ahi = (unsigned)(after >> 32);
 #pragma unroll
-            for (int g = 0; g < 5; ++g) pg[g] = (g == 0 || g < 3 || w.dim == 3) ? pe[g * T + v] : 0ull;
-            for (int i = 0; i < len; ++i) {
-                const int u = sh.perm[i];
-#pragma unroll
-                for (int g = 0; g < 5; ++g) cb[g] |= (unsigned)((pg[g] >> u) & 1ull) << i;
+            for (int g = 0; g < 5; ++g) {
+                if (g < ng) {
+                    const unsigned long long pg = pe[g * T + v];
+                    lo[g] = (unsigned)pg; hi[g] = (unsigned)(pg >> 32);
+                    if (g >= 1 && ((lo[g] & alo) | (hi[g] & ahi))) loopbits |= 1u << g;
+                }
             }
+        }
+        for (int i = 0; i < len; ++i) {
+            const int u = sh.perm[i];                       // warp-uniform
+            const unsigned diag = lane == i ? loopbits : 0u;
+            if (u < 32) {
 #pragma unroll
-            for (int g = 1; g < 5; ++g) if (pg[g] & after) cb[g] |= 1u << lane;      // :1690-1705
+                for (int g = 0; g < 5; ++g) {
+                    if (g < ng) {
+                        const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, ((lo[g] >> u) | (diag >> g)) & 1u);
+                        if (lane == i) myrow[g] = rowbits;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    if (g < ng) {
+                        const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, ((hi[g] >> (u - 32)) | (diag >> g)) & 1u);
+                        if (lane == i) myrow[g] = rowbits;
+                    }
+                }
+            }
         }
         gone |= winmask;                                    // :1713-1723
     }
-#pragma unroll
-    for (int g = 0; g < 5; ++g) sh.colbits[g][lane] = cb[g];
-    sh.colbits[5][lane] = 0u;
+    // dynamic rows: band 0 = move in every rotation block; bands 1/2 = (left,right) where the rotation's last axis is x,
+    // (forward,backward) where it is y, zeros where it is the vertical axis (generate.py:1790-1806)
+    const unsigned long long row0 = (unsigned long long)myrow[0] * w.mul_all;
+    const unsigned long long row1 = (unsigned long long)myrow[1] * w.mul_c0 + (unsigned long long)myrow[3] * w.mul_c1;
+    const unsigned long long row2 = (unsigned long long)myrow[2] * w.mul_c0 + (unsigned long long)myrow[4] * w.mul_c1;
+    if (lane < n) { sh.rows[lane] = row0; sh.rows[n + lane] = row1; sh.rows[2 * n + lane] = row2; }
+    const unsigned long long any0 = (unsigned long long)warp_or((unsigned)row0) | ((unsigned long long)warp_or((unsigned)(row0 >> 32)) << 32);
+    const unsigned long long any1 = (unsigned long long)warp_or((unsigned)row1) | ((unsigned long long)warp_or((unsigned)(row1 >> 32)) << 32);
+    const unsigned long long any2 = (unsigned long long)warp_or((unsigned)row2) | ((unsigned long long)warp_or((unsigned)(row2 >> 32)) << 32);
+    const unsigned long long blocked = any0 | (any1 & any2);      // rolling.py:325-335
     // ---- self.sub_graph_nodes.sort() (:1766) ----
     __syncwarp();
     if (mynode >= 0) sh.list[__popcll(winmask & below64(mynode))] = (unsigned char)mynode;
@@ -223,58 +269,35 @@ __device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, i
     }
     // ---- dynamic [3n,S] and the initial masks (rolling.py:325-335) ----
     float *dyo = dynamic_out + (size_t)b * 3 * n * S;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = lane + 32 * half;
+        if (j < S) {
+            if (cur_mask) cur_mask[(size_t)b * S + j] = ((blocked >> j) & 1ull) ? 0.f : 1.f;
+            if (mask_out) mask_out[(size_t)b * S + j] = 1.f;
+        }
+    }
     if (FAST) {
+        // lane = (row-in-pass, column group): one 64-bit row word from shared memory, one nibble, one 128-bit store
         const int rsub = (int)(((unsigned)lane * w.inv_SV) >> 16), cv = lane - rsub * w.SV;
         const bool on = rsub < w.RP;
-        unsigned W[3][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int col = 4 * cv + k;
-            const int r = (int)(((unsigned)col * w.inv_n) >> 16), jj = col - r * n;
-            const unsigned code = (w.lastcodes >> (2 * r)) & 3u;
-            const int ga = code == 0u ? 1 : (code == 1u ? 3 : 5), gb = code == 0u ? 2 : (code == 1u ? 4 : 5);
-            const bool ok = on && col < S;
-            W[0][k] = ok ? sh.colbits[0][jj] : 0u; W[1][k] = ok ? sh.colbits[ga][jj] : 0u; W[2][k] = ok ? sh.colbits[gb][jj] : 0u;
-        }
+        const bool hi_half = 4 * cv >= 32;
+        const int sh4 = (4 * cv) & 31;
         uint4 *dst = reinterpret_cast<uint4 *>(dyo) + lane;
-        const int pstride = w.RP * w.SV, bstride = n * w.SV;
-        for (int p = 0; p < w.PB; ++p) {
-            const int row = p * w.RP + rsub;
-            if (on && row < n) {
-#pragma unroll
-                for (int bd = 0; bd < 3; ++bd) {
-                    uint4 v;
-                    v.x = (0u - ((W[bd][0] >> row) & 1u)) & 0x3f800000u; v.y = (0u - ((W[bd][1] >> row) & 1u)) & 0x3f800000u;
-                    v.z = (0u - ((W[bd][2] >> row) & 1u)) & 0x3f800000u; v.w = (0u - ((W[bd][3] >> row) & 1u)) & 0x3f800000u;
-                    stg_stream4(dst + p * pstride + bd * bstride, v);
-                }
+        const int pstride = w.RP * w.SV, rows3 = 3 * n;
+        const uint2 *rws = reinterpret_cast<const uint2 *>(sh.rows);
+        for (int fr = rsub; fr < rows3; fr += w.RP) {
+            if (on) {
+                const uint2 rw = rws[fr];
+                const unsigned nib = ((hi_half ? rw.y : rw.x) >> sh4) & 0xfu;
+                stg_stream4(dst, lut[nib]);
             }
-        }
-        if (on && rsub == 0) {
-            float4 cur, one = make_float4(1.f, 1.f, 1.f, 1.f);
-            cur.x = (W[0][0] | ((W[1][0] != 0u && W[2][0] != 0u) ? 1u : 0u)) ? 0.f : 1.f;
-            cur.y = (W[0][1] | ((W[1][1] != 0u && W[2][1] != 0u) ? 1u : 0u)) ? 0.f : 1.f;
-            cur.z = (W[0][2] | ((W[1][2] != 0u && W[2][2] != 0u) ? 1u : 0u)) ? 0.f : 1.f;
-            cur.w = (W[0][3] | ((W[1][3] != 0u && W[2][3] != 0u) ? 1u : 0u)) ? 0.f : 1.f;
-            if (cur_mask) reinterpret_cast<float4 *>(cur_mask + (size_t)b * S)[cv] = cur;
-            if (mask_out) reinterpret_cast<float4 *>(mask_out + (size_t)b * S)[cv] = one;
+            dst += pstride;
         }
     } else {
         for (int q = lane; q < 3 * n * S; q += 32) {
-            const int rowf = q / S, col = q - rowf * S;
-            const int bd = rowf / n, row = rowf - bd * n;
-            const int r = col / n, jj = col - r * n;
-            const unsigned code = (w.lastcodes >> (2 * r)) & 3u;
-            const int g = bd == 0 ? 0 : (code == 0u ? bd : (code == 1u ? 2 + bd : 5));
-            dyo[q] = ((sh.colbits[g][jj] >> row) & 1u) ? 1.f : 0.f;
-        }
-        for (int col = lane; col < S; col += 32) {
-            const int r = col / n, jj = col - r * n;
-            const unsigned code = (w.lastcodes >> (2 * r)) & 3u;
-            const int ga = code == 0u ? 1 : (code == 1u ? 3 : 5), gb = code == 0u ? 2 : (code == 1u ? 4 : 5);
-            const bool blocked = sh.colbits[0][jj] != 0u || (sh.colbits[ga][jj] != 0u && sh.colbits[gb][jj] != 0u);
-            if (cur_mask) cur_mask[(size_t)b * S + col] = blocked ? 0.f : 1.f;
-            if (mask_out) mask_out[(size_t)b * S + col] = 1.f;
+            const int fr = q / S, col = q - fr * S;
+            dyo[q] = ((sh.rows[fr] >> col) & 1ull) ? 1.f : 0.f;
         }
     }
 }

@@ -14,11 +14,11 @@ from .ops import update_dynamic, update_mask
 from .containers import BatchedContainers, Container
 from .runner import EpisodeRunner, HostPipeline
 from . import dist
-from .dataset import PACKDataset
+from .dataset import PACKDataset, pack_inputs
 from .episode import calc_positions_lb_greedy, calc_positions_mcs, reward
 from .dropin import install, uninstall
 from .rolling import BatchedInitialContainers, RollingRunner, RollingHostPipeline, pack_graphs
 
-__all__ = ["PACKDataset", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
+__all__ = ["PACKDataset", "pack_inputs", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
            "update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
            "TapEnvError", "BatchedInitialContainers", "RollingRunner", "RollingHostPipeline", "pack_graphs"]

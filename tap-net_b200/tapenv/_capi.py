@@ -60,6 +60,8 @@ SYMBOLS = {
     "tapenv_comm_bytes": (c_size_t, []),
     "tapenv_reward_allreduce": (c_int, [CFG, P, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
+    "tapenv_packed_words": (c_int32, [CFG]),
+    "tapenv_reset_packed": (c_int, [CFG, P, P, P, P, P, P, P, P]),
     "tapenv_window_state_bytes": (c_size_t, [C.POINTER(WindowConfig)]),
     "tapenv_window_reset": (c_int, [C.POINTER(WindowConfig), P, P]),
     "tapenv_window_next": (c_int, [C.POINTER(WindowConfig)] + [P] * 11),

@@ -134,6 +134,28 @@ class BatchedContainers(object):
                                                _stream()), "reset")
         return cur, mask
 
+    def reset_packed(self, static_u8, dynamic_bits, out=None):
+        """reset() for inputs uploaded in the packed host format (tapenv.pack_inputs: u8 static, bit-row dynamic):
+        expands them to the fp32 tensors, clears the containers, emits the initial masks -- one launch.
+        -> (static f32 [B,rows,S], dynamic f32 [B,3n,S], current_mask, mask)."""
+        static_u8 = _dev(static_u8, "static_u8", torch.uint8)
+        dynamic_bits = _dev(dynamic_bits, "dynamic_bits", torch.int32)
+        B, S = self.batch_size, self.S
+        words = int(_capi.lib.tapenv_packed_words(C.byref(self.cfg)))
+        if tuple(static_u8.shape) != (B, self.cfg.static_rows, S) or tuple(dynamic_bits.shape) != (B, words):
+            raise _capi.TapEnvError(_capi.ESHAPE, "packed inputs %s %s" % (tuple(static_u8.shape), tuple(dynamic_bits.shape)))
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if out is None:
+            static, dynamic = torch.empty(B, self.cfg.static_rows, S, **f32), torch.empty(B, self.cfg.dyn_rows, S, **f32)
+            cur, mask = torch.empty(B, S, **f32), torch.empty(B, S, **f32)
+        else:
+            static, dynamic, cur, mask = out
+        self._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reset_packed(C.byref(self.cfg), _p(self.state), _p(static_u8), _p(dynamic_bits),
+                                                      _p(static), _p(dynamic), _p(cur), _p(mask), _stream()), "reset_packed")
+        return static, dynamic, cur, mask
+
     def initial_mask(self, dynamic):
         """The accessibility masks of a freshly (re)filled window, container untouched (model.py:297-307,
         rolling.py:325-335) -> (current_mask, mask)."""

@@ -19,6 +19,29 @@ def _load(path):
     return np.atleast_2d(np.loadtxt(path).astype("float32"))
 
 
+def packed_words(dyn_rows, S):
+    """u32 words per environment of the bit-row `dynamic` (rows padded to 16 bytes; == tapenv_packed_words)."""
+    return ((dyn_rows * S + 31) // 32 + 3) // 4 * 4
+
+
+def pack_inputs(static, dynamic):
+    """Host-side compaction of a batch for upload: static f32 [B,rows,S] (small non-negative integers) -> u8,
+    dynamic f32 [B,3n,S] (0/1, pack.py:101-223) -> int32 [B, packed_words] bit rows, bit (row*S + col) little-endian.
+    Expanded on the device by BatchedContainers.reset_packed (tapenv_reset_packed)."""
+    static = np.asarray(static)
+    dynamic = np.asarray(dynamic)
+    if not ((static == np.round(static)).all() and static.min() >= 0 and static.max() < 256):
+        raise ValueError("static is not u8-representable")
+    if not np.isin(dynamic, (0.0, 1.0)).all():
+        raise ValueError("dynamic must hold 0/1")
+    B, rows, S = dynamic.shape
+    words = packed_words(rows, S)
+    bits = np.zeros((B, words * 4), np.uint8)
+    pk = np.packbits(dynamic.reshape(B, -1).astype(np.uint8), axis=1, bitorder="little")
+    bits[:, :pk.shape[1]] = pk
+    return np.ascontiguousarray(static.astype(np.uint8)), np.ascontiguousarray(bits).view("<i4")
+
+
 class PACKDataset(Dataset):
     def __init__(self, data_file, blocks_num, num_samples, seed, input_type, heightmap_type, allow_rot,
                  container_width, mix_data_file=None, unit=1, no_precedence=False):
@@ -98,6 +121,14 @@ class PACKDataset(Dataset):
 
     def __len__(self):
         return self.num_samples
+
+    def packed(self):
+        """The whole set in the compact upload format -> (static_u8 [N,rows,S] uint8, dynamic_bits [N,words] int32)
+        CPU tensors (pin them once; BatchedContainers.reset_packed expands a batch on the device)."""
+        if getattr(self, "_packed", None) is None:
+            su8, bits = pack_inputs(self.static.numpy(), self.dynamic.numpy())
+            self._packed = (torch.from_numpy(su8), torch.from_numpy(bits))
+        return self._packed
 
     def __getitem__(self, idx):
         return (self.static[idx], self.dynamic[idx], self.decoder_static[idx], self.decoder_dynamic[idx])

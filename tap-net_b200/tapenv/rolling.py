@@ -285,3 +285,116 @@ class RollingHostPipeline(object):
         self.tail = (self.tail + 1) % self.depth
         self.inflight -= 1
         return s["reward"], s["sums"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Dataset side (host, one-off): the precedence graphs of an initial packing and rolling.RollingDataset
+# ----------------------------------------------------------------------------------------------------------------
+def calc_dependent(blocks, positions, container_size, arm_size=1):
+    """The five precedence relations generate.calc_dependent derives from the voxel grid of an initial packing
+    (generate.py:575-647 for 2D, :649-752 for 3D), computed from the block intervals instead of by scanning voxels.
+    blocks / positions: int [T,dim] (un-rotated sizes, corner positions).  Returns bool [5,T,T] in InitialContainer's
+    graph order (move, left, right, forward, backward) with out[g,u,v] == True <=> deps_g[u,v] (edge u -> v).
+
+      move      3D: u rests directly above v in some footprint column -- consecutive blocks of that column's stack,
+                whatever the gap (the voxel scan stops at the first block it meets, :676-701).
+                2D: u is anywhere above v over a shared column (np.unique over the whole strip, :603-613).
+      left/right (and forward/backward in 3D): v needs that side free to be rotated; u -> v if u occupies the
+                neighbouring strip (2D: `arm_size` columns; 3D: the one-cell plane, restricted to the block's middle
+                cells along the other axis) at or above v's mid height; v -> v when v touches the wall."""
+    blocks = np.asarray(blocks, dtype=np.int64)
+    pos = np.asarray(positions, dtype=np.int64)
+    T, dim = blocks.shape
+    lo, hi = pos, pos + blocks                                   # half-open extents per axis
+    out = np.zeros((5, T, T), dtype=bool)
+    idx = np.arange(T)
+    zmid = lo[:, -1] + (blocks[:, -1] - 1) // 2                  # z + int((bz-1)/2)
+
+    def overlap(a_lo, a_hi, b_lo, b_hi):                         # [T,1] x [1,T] half-open interval intersection
+        return (a_lo[:, None] < b_hi[None, :]) & (b_lo[None, :] < a_hi[:, None])
+
+    if dim == 2:
+        W = int(container_size[0])
+        xov = overlap(lo[:, 0], hi[:, 0], lo[:, 0], hi[:, 0])
+        below = xov & (lo[None, :, 1] < lo[:, None, 1])          # [u,v]: v has cells under u's bottom edge
+        above = xov & (hi[:, None, 1] > hi[None, :, 1])          # [u,v]: u has cells over v's top edge
+        out[0] = (below | above) & (idx[:, None] != idx[None, :])
+        tall = hi[:, None, 1] > zmid[None, :]                    # [u,v]: u reaches v's mid height
+        wall_l = lo[:, 0] < arm_size
+        left = overlap(lo[:, 0], hi[:, 0], lo[:, 0] - arm_size, lo[:, 0]) & tall
+        out[1] = np.where(wall_l[None, :], np.eye(T, dtype=bool), left)
+        wall_r = hi[:, 0] > W - arm_size
+        right = overlap(lo[:, 0], hi[:, 0], hi[:, 0], hi[:, 0] + arm_size) & tall
+        out[2] = np.where(wall_r[None, :], np.eye(T, dtype=bool), right)
+        return out
+
+    W, L = int(container_size[0]), int(container_size[1])
+    # move: per footprint column, consecutive blocks of the stack
+    order = np.argsort(lo[:, 2], kind="stable")
+    top_block = -np.ones((W, L), dtype=np.int64)                 # highest block seen so far per column
+    for u in order:
+        x0, x1, y0, y1 = lo[u, 0], hi[u, 0], lo[u, 1], hi[u, 1]
+        under = np.unique(top_block[x0:x1, y0:y1])
+        out[0, u, under[under >= 0]] = True
+        top_block[x0:x1, y0:y1] = u
+    # rotation: middle cells along the other horizontal axis (y_mid_1:y_mid_2, :705-713), from mid height upwards
+    def mid_range(a_lo, size):
+        m1 = a_lo + (size - 1) // 2
+        m2 = a_lo + size // 2
+        return m1, np.where(m1 == m2, m2 + 1, m2)
+    ym1, ym2 = mid_range(lo[:, 1], blocks[:, 1])
+    xm1, xm2 = mid_range(lo[:, 0], blocks[:, 0])
+    tall = hi[:, None, 2] > zmid[None, :]
+    eye = np.eye(T, dtype=bool)
+    y_mid = overlap(lo[:, 1], hi[:, 1], ym1, ym2)                # [u,v]: u covers one of v's middle y cells
+    x_mid = overlap(lo[:, 0], hi[:, 0], xm1, xm2)
+
+    def plane(u_lo, u_hi, cell):                                  # [u,v]: u occupies coordinate cell[v] along that axis
+        return (u_lo[:, None] <= cell[None, :]) & (cell[None, :] < u_hi[:, None])
+    out[1] = np.where((lo[:, 0] == 0)[None, :], eye, plane(lo[:, 0], hi[:, 0], lo[:, 0] - 1) & y_mid & tall)
+    out[2] = np.where((hi[:, 0] == W)[None, :], eye, plane(lo[:, 0], hi[:, 0], hi[:, 0]) & y_mid & tall)
+    out[3] = np.where((lo[:, 1] == 0)[None, :], eye, plane(lo[:, 1], hi[:, 1], lo[:, 1] - 1) & x_mid & tall)
+    out[4] = np.where((hi[:, 1] == L)[None, :], eye, plane(lo[:, 1], hi[:, 1], hi[:, 1]) & x_mid & tall)
+    return out
+
+
+class RollingDataset(object):
+    """rolling.RollingDataset (rolling.py:462-534): reads blocks.txt / pos.txt of a rolling dataset directory and
+    builds the initial containers -- here ONE BatchedInitialContainers for all `num_samples` instances (attribute
+    `initial_containers`), plus the reference's zero decoder inputs.  dep_*.txt / container.txt are not needed: like
+    the reference, the graphs are recomputed from the geometry (generate.py:1619)."""
+
+    def __init__(self, data_file, total_blocks_num, net_blocks_num, num_samples, block_dim, seed, input_type,
+                 heightmap_type, allow_rot, container_width, initial_container_width, initial_container_height,
+                 mix_data_file=None, unit=1, device=None, node_order=_capi.WINDOW_ORDER_REFERENCE):
+        if seed is None:
+            seed = np.random.randint(123456)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        T, dim = int(total_blocks_num), int(block_dim)
+        R = math.factorial(dim)
+        blocks = np.atleast_2d(np.loadtxt(data_file + "blocks.txt")).astype("int")
+        positions = np.atleast_2d(np.loadtxt(data_file + "pos.txt")).astype("int")
+        data_size = len(blocks) // R
+        blocks = blocks.reshape(data_size, R, dim, T).transpose(0, 1, 3, 2).reshape(data_size, R * T, dim)   # :483-485
+        positions = positions.reshape(len(positions), dim, T).transpose(0, 2, 1)                              # :490-491
+        ics = ([initial_container_width, initial_container_height] if dim == 2
+               else [initial_container_width, initial_container_width, initial_container_height])
+        N = int(num_samples)
+        adj = np.stack([calc_dependent(blocks[b, :T], positions[b], ics) for b in range(N)])
+        self.blocks, self.positions, self.graphs = blocks[:N], positions[:N], pack_graphs(adj)
+        self.initial_containers = BatchedInitialContainers(self.graphs, blocks[:N], T, net_blocks_num, dim, device=device,
+                                                           node_order=node_order, input_type=input_type)
+        static_dim, hm_num = dim, 1                                                                           # :504-533
+        if heightmap_type == "diff":
+            hm_w = container_width * unit - 1 if dim == 2 else container_width * unit
+            if dim == 3:
+                hm_num = 2
+        else:
+            hm_w = container_width * unit
+        self.decoder_static = torch.zeros(1, static_dim, 1, requires_grad=True)
+        if dim == 2:
+            self.decoder_dynamic = torch.zeros(1, int(hm_w), 1, requires_grad=True)
+        else:
+            self.decoder_dynamic = torch.zeros(1, hm_num, int(hm_w), int(hm_w), requires_grad=True)
+        self.num_samples = N

@@ -98,3 +98,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(d, f)).read()
                 assert not bad.search(src), os.path.join(d, f)
+
+
+def test_pack_inputs_layout():
+    """Host-side compaction used by the packed upload path: u8 static, little-endian bit rows padded to 16 bytes."""
+    import numpy as np
+    from tapenv.dataset import pack_inputs, packed_words
+    from tests.golden_io import load_inputs
+    static, dynamic = load_inputs("rand3d_n10.npz", 5)
+    su8, bits = pack_inputs(static, dynamic)
+    B, rows, S = dynamic.shape
+    assert su8.dtype == np.uint8 and np.array_equal(su8.astype(np.float32), static)
+    assert bits.dtype == np.int32 and bits.shape == (B, packed_words(rows, S)) and bits.shape[1] % 4 == 0
+    flat = dynamic.reshape(B, -1)
+    for q in (0, 1, 31, 32, 777, rows * S - 1):
+        assert np.array_equal((bits[:, q >> 5] >> (q & 31)) & 1, flat[:, q].astype(np.int32))
+    u = bits.view(np.uint32)
+    assert int(sum(bin(int(v)).count("1") for v in u.reshape(-1))) == int(flat.sum())      # padding bits are zero
+    import tapenv
+    cfg = tapenv.make_config(B, 10, [5, 5, 50])
+    assert int(tapenv._capi.lib.tapenv_packed_words(C.byref(cfg))) == bits.shape[1]

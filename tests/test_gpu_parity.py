@@ -384,3 +384,70 @@ def test_rolling_style_container_outlives_the_window():
     for i in range(12):
         blk = static_all[i, 1:4, i % 60]
         assert np.array_equal(one.add_new_block(blk), ref1.add_new_block(blk))
+
+
+@pytest.mark.parametrize("fixture,size,num,strat,rt", [
+    ("rand2d_n10.npz", [5, 50], 333, "LB_GREEDY", "C+P+S-lb-soft"),       # S = 20: 128-bit path
+    ("rand3d_n10.npz", [5, 5, 50], 130, "LB_GREEDY", "C+P+S-lb-soft"),    # S = 60, 1800 bits per environment
+    ("ppsg2d_n20.npz", [7, 50], 65, "MACS", "C+P+S-mcs-hard"),            # S = 40, 2400 bits
+    ("rand2d_n10.npz", [5, 50], 40, "LB", "C+P+S-lb-soft"),               # LB keeps extra state: cleared by the plain reset
+])
+def test_packed_reset_expands_to_the_reference_tensors(fixture, size, num, strat, rt):
+    """tapenv_reset_packed: u8 static + bit-row dynamic -> exactly the fp32 tensors PACKDataset holds, the initial masks
+    of model.py:297-307, a cleared container; an episode started from it equals one started from the fp32 tensors."""
+    torch = _torch()
+    import tapenv
+    static, dynamic = load_inputs(fixture, num)
+    dim = len(size)
+    n = static.shape[2] // (2 if dim == 2 else 6)
+    su8, bits = tapenv.pack_inputs(static, dynamic)
+    env = tapenv.BatchedContainers(size, n, rt, "diff", packing_strategy=strat, batch_size=num)
+    ptr_seq = random_valid_ptrs(static, dynamic, size, seed=11)
+    st, dy = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+
+    def episode(start):
+        s_, d_, cur, mask = start()
+        cur0 = cur.clone()
+        for t in range(n):
+            d_, cur, mask, _, _ = env.step(torch.from_numpy(ptr_seq[t]).cuda(), s_, d_, mask)
+        return cur0, env.heightmap.clone(), env.calc_ratio().clone(), env.positions.clone()
+
+    def plain():
+        cur, mask = env.reset(dy)
+        return st, dy, cur, mask
+
+    def packed():
+        # dirty the state first: reset_packed must clear it
+        env.step(torch.from_numpy(ptr_seq[0]).cuda(), st, dy, torch.ones(num, static.shape[2], device="cuda"))
+        s_, d_, cur, mask = env.reset_packed(torch.from_numpy(su8).cuda(), torch.from_numpy(bits).cuda())
+        assert torch.equal(s_, st) and torch.equal(d_, dy)
+        assert bool((mask == 1).all()) and int(env.current_blocks_num.sum()) == 0 and int(env.heightmap.abs().sum()) == 0
+        return s_, d_, cur, mask
+
+    a, b = episode(plain), episode(packed)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    env.check_flags()
+
+
+def test_packed_reset_scalar_path_and_errors():
+    """S % 4 != 0 takes the element-wise expansion; wrong shapes are rejected before any launch."""
+    torch = _torch()
+    import tapenv
+    rng = np.random.RandomState(0)
+    B, n, R = 9, 7, 2
+    S = n * R
+    static = np.zeros((B, 3, S), np.float32)
+    static[:, 0] = np.tile(np.arange(n), R)[None]
+    static[:, 1:] = rng.randint(1, 5, size=(B, 2, S))
+    dynamic = (rng.random_sample((B, 3 * n, S)) < 0.1).astype(np.float32)
+    su8, bits = tapenv.pack_inputs(static, dynamic)
+    env = tapenv.BatchedContainers([5, 50], n, "C+P+S-lb-soft", "diff", batch_size=B)
+    s_, d_, cur, mask = env.reset_packed(torch.from_numpy(su8).cuda(), torch.from_numpy(bits).cuda())
+    assert np.array_equal(s_.cpu().numpy(), static) and np.array_equal(d_.cpu().numpy(), dynamic)
+    cur_ref, _ = env.reset(torch.from_numpy(dynamic).cuda())
+    assert torch.equal(cur, cur_ref)
+    with pytest.raises(ValueError):
+        env.reset_packed(torch.from_numpy(su8).cuda(), torch.from_numpy(bits[:, :-1].copy()).cuda())
+    with pytest.raises(ValueError):
+        tapenv.pack_inputs(static, dynamic * 2)

@@ -114,3 +114,47 @@ def test_window_differential_live(dim, T, n, trials):
             ptr = int(rng.choice(ok)) if len(ok) else int(rng.randint(n * R))
             bid = int(ic.sub_graph_nodes[ptr % n])
             ic.remove_block(bid); oc.remove_block(bid)
+
+
+def _product_calc_dependent():
+    # host-side numpy code of the product package; imported lazily (the package dlopens libtapenv.so, no GPU needed)
+    from tapenv.rolling import calc_dependent, pack_graphs
+    return calc_dependent, pack_graphs
+
+
+@pytest.mark.parametrize("name", ["rolling3d_t50.npz", "rolling2d_t50.npz"])
+def test_calc_dependent_reproduces_the_fixture_graphs(name):
+    """tapenv.rolling.calc_dependent (interval arithmetic) vs the graphs generate.InitialContainer built by voxel
+    scanning, recorded in the fixtures: every instance, all five relations."""
+    calc_dependent, pack_graphs = _product_calc_dependent()
+    z = load_rolling(name)
+    T, dim = z["T"], z["dim"]
+    ics = [7, 250] if dim == 2 else [7, 7, 250]
+    for b in range(z["adj"].shape[0]):
+        got = calc_dependent(z["blocks"][b, :T], z["positions"][b], ics)
+        assert np.array_equal(got.astype(np.uint8), z["adj"][b]), b
+    pred = pack_graphs(z["adj"][:3])
+    for g, u, v in [(0, 3, 5), (1, 0, 0), (2, 7, 7)]:
+        assert ((int(pred[1, g, v]) >> u) & 1) == int(z["adj"][1, g, u, v])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+@pytest.mark.parametrize("dim,T,arm", [(2, 30, 1), (2, 20, 2), (3, 30, 1), (3, 12, 1)])
+def test_calc_dependent_live(dim, T, arm):
+    calc_dependent, _ = _product_calc_dependent()
+    generate = refshim.load(("tools", "generate"))["generate"]
+    np.random.seed(77 + dim + T)
+    ics = [7, 250] if dim == 2 else [6, 8, 250]
+    R = 2 if dim == 2 else 6
+    for tr in range(12):
+        rot_blocks, positions, _, _, _ = generate.generate_blocks(T, ics, arm, [1, 5])
+        blocks = np.asarray(rot_blocks).reshape(R, dim, T).transpose(0, 2, 1).reshape(R * T, dim)[:T]
+        pos = np.asarray(positions).reshape(dim, T).transpose(1, 0)
+        cont = np.zeros(ics, dtype=int)
+        for i in range(T):
+            sl = tuple(slice(int(pos[i, d]), int(pos[i, d] + blocks[i, d])) for d in range(dim))
+            cont[sl] = i + 1
+        ref = generate.calc_dependent(blocks, pos, cont, arm)[:5]
+        got = calc_dependent(blocks, pos, ics, arm)
+        for g in range(5):
+            assert np.array_equal(got[g], np.asarray(ref[g]).astype(bool)), (tr, g)
