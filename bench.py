@@ -368,7 +368,9 @@ def run_rolling(args):
     gr_pin = torch.from_numpy(graphs_h).pin_memory()
     bl_pin = torch.from_numpy(blocks_h).pin_memory()
     pq_pin = ptr_seq0.cpu().pin_memory()
-    pipe = tapenv.RollingHostPipeline(env, T, n, depth=2, use_graph=not args.no_graph, exchange=exchange)
+    from tapenv.rolling import rotation_structured
+    pipe = tapenv.RollingHostPipeline(env, T, n, depth=2, use_graph=not args.no_graph, exchange=exchange,
+                                      blocks_are_rotations=rotation_structured(blocks_h, T, dim))    # checked once per dataset, untimed
 
     def e2e_run(k):
         last = None

@@ -266,6 +266,10 @@ typedef struct tapenv_window_config {
     int32_t dim;            /* 2 or 3 */
     int32_t rotate_types;   /* factorial(dim)                        (generate.py:1610) */
     int32_t node_order;     /* TAPENV_WINDOW_ORDER_* */
+    int32_t blocks_are_rotations; /* != 0: blocks[b, r*T+i, d] == blocks[b, i, perm_r[d]] with perm_r the r-th of
+                               itertools.permutations(range(dim)) -- how generate.generate_blocks writes every dataset
+                               (rolling.py:60-63).  The kernel then reads T*dim instead of R*T*dim values per instance.
+                               Set it only after checking the array; 0 is always correct. */
 } tapenv_window_config;
 size_t tapenv_window_state_bytes(const tapenv_window_config *wcfg);
 /* InitialContainer.__init__ tail (generate.py:1666-1673): nothing removed, every node in after_nodes_list, empty window. */

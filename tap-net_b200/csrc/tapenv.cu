@@ -762,7 +762,7 @@ __global__ void window_reset_kernel(int B, int T, unsigned *wstate) {
 }
 
 template <int STRAT, bool FAST>                      // STRAT < 0: window only
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 32 / kWarpsPerCta)
 window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, const unsigned long long *__restrict__ pred,
               const int *__restrict__ blocks, const int64_t *__restrict__ ptr, float *__restrict__ dec_static,
               float *__restrict__ dec_dyn, float *__restrict__ static_out, float *__restrict__ dynamic_out,
@@ -798,26 +798,34 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
     sh.list[lane] = (unsigned char)(__shfl_sync(TAPENV_FULL_MASK, word, 4 + (lane >> 2)) >> (8 * (lane & 3)));
     __syncwarp();
     const int *blk = blocks + (size_t)b * w.blocks_env;
-    int rm = -1;
+    int rm = -1, node = -1, prot = 0;
+    bool place = false;
+    float dimv = 0.f;
     if (ptr) {
         const bool badp = p64 < 0 || p64 >= w.S;      // the reference's gather / list index would raise
         const int p = badp ? 0 : (int)p64;
-        const int r = (int)(((unsigned)p * w.inv_n) >> 16), idx = p - r * w.n;     // rolling.py:637-638
+        prot = (int)(((unsigned)p * w.inv_n) >> 16);
+        const int idx = p - prot * w.n;               // rolling.py:637-638
         if (badp || idx >= len) flags |= 4; else rm = idx;
         if (STRAT >= 0) {
-            const int node = rm >= 0 ? (int)sh.list[idx] : -1;
-            float dimv = 0.f;
-            if (lane < w.dim && node >= 0) dimv = (float)blk[(node + r * w.T) * w.dim + lane];     // == static[:,1:,ptr] of the previous window
-            if (dec_static && lane < w.dim) dec_static[(size_t)b * w.dim + lane] = dimv;
-            const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
-            const int by = ES == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
-            const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, w.dim - 1);
-            if (node >= 0)
-                container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+            node = rm >= 0 ? (int)sh.list[idx] : -1;
+            place = node >= 0;
+            if (lane < w.dim && place) dimv = (float)blk[(node + prot * w.T) * w.dim + lane];     // == static[:,1:,ptr] of the previous window
         }
     }
-    window_advance<FAST>(w, sh, lut, b, lane, gone, after, len, flags, rm, ws, pe, pm0, pm1, blk, static_out, dynamic_out,
-                         cur_mask, mask_out, nodes_out, remaining_out);
+    // phase A of the window (admission + early loads), then the placement, then decompose / emission: the placement's
+    // ~500 warp-instructions run while the window's loads are in flight
+    const WinEarly early = window_refill(w, sh, lane, gone, after, len, flags, rm, pe, pm0, pm1, blk);
+    if (STRAT >= 0 && ptr) {
+        if (dec_static && lane < w.dim) dec_static[(size_t)b * w.dim + lane] = dimv;
+        const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+        const int by = ES == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+        const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, w.dim - 1);
+        if (place)
+            container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+    }
+    window_emit<FAST>(w, sh, lut, b, lane, early, ws, pe, blk, static_out, dynamic_out, cur_mask, mask_out, nodes_out,
+                      remaining_out);
 }
 
 // fast path needs 128-bit rows and 16-byte aligned tensors
@@ -1158,6 +1166,14 @@ static WinCfg wincfg_of(const tapenv_window_config *w) {
     // code 0 -> (left,right), 1 -> (forward,backward), 2 -> zeros; in 2D a last axis of 1 is the vertical one (generate.py:1802-1806)
     d.lastcodes = d.dim == 2 ? (2u | (0u << 2)) : (2u | (1u << 2) | (2u << 4) | (0u << 6) | (1u << 8) | (0u << 10));
     d.blocks_env = (unsigned)(d.R * d.T * d.dim);
+    d.rotblocks = w->blocks_are_rotations ? 1 : 0;
+    // perm_r[d] of itertools.permutations(range(dim)), 2 bits per (r, d), 6 bits per rotation
+    static const int P2[2][3] = {{0, 1, 0}, {1, 0, 0}};
+    static const int P3[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    d.permcodes = 0ull;
+    for (int r = 0; r < d.R; ++r)
+        for (int k = 0; k < 3; ++k)
+            d.permcodes |= (unsigned long long)(d.dim == 2 ? P2[r][k] : P3[r][k]) << (6 * r + 2 * k);
     d.mul_all = d.mul_c0 = d.mul_c1 = 0ull;
     for (int r = 0; r < d.R; ++r) {
         const unsigned code = (d.lastcodes >> (2 * r)) & 3u;

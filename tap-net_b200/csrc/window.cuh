@@ -37,13 +37,18 @@ struct WinCfg {
     // replication multipliers: sum of 2^(r*n) over all rotations / those with code 0 / code 1 -- an n-bit sub-matrix row
     // times one of these is that row repeated into the column blocks of the rotations it applies to
     unsigned long long mul_all, mul_c0, mul_c1;
+    // rotblocks != 0: blocks[r*T + i][d] == blocks[i][perm_r[d]] for the rotations of itertools.permutations(range(dim))
+    // (true for every reference dataset: generate_blocks writes the rotations that way) -- the kernel then reads the n
+    // un-rotated rows instead of S scattered ones.  permcodes: 2 bits per (r, d) = perm_r[d], 6 bits per rotation.
+    int rotblocks;
+    unsigned long long permcodes;
 };
 
 struct WinShared {           // per warp
     unsigned long long rows[96];   // dynamic row (band*n + i') as a bit row over the S candidate columns
-    unsigned char list[32];  // window in list order (survivors sorted, then admissions), later sorted
+    unsigned char list[32];  // window in list order (survivors sorted, then admissions)
+    unsigned char sorted[32];// ... sorted ascending (sub_graph_nodes after :1766)
     unsigned char perm[32];  // P
-    unsigned char tab[2][128];   // sequential set emulation for windows above 18 nodes
 };
 
 __device__ __forceinline__ unsigned long long below64(int v) { return v >= 64 ? ~0ull : ((1ull << v) - 1ull); }
@@ -67,9 +72,24 @@ __device__ __forceinline__ void pyset_insert32(unsigned &occ, int &slot, int lan
     }
 }
 
-// iteration order of set(list[0..len)) -> perm[0..len).  len <= 18 keeps CPython's table at <= 32 slots.
-__device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int len) {
-    if (len <= 18) {
+// iteration order of set(list[0..len)) -> perm[0..len), keys < 64.
+//   len >= 19: the table has grown to 128 slots (fill 19 >= 31*3/5), every key sits in slot `key` -> ascending order.
+//   5 <= len <= 18 (32 slots): when no two keys agree modulo 32 every key sits in slot key & 31 whatever the insertion
+//   order -> order by key & 31 (a rank computation); otherwise the insertions are replayed.
+//   len < 5: the initial 8-slot table, replayed.
+__device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int len, int mynode, unsigned long long winmask) {
+    if (len >= 19) {
+        if (mynode >= 0) sh.perm[__popcll(winmask & below64(mynode))] = (unsigned char)mynode;
+        __syncwarp();
+        return;
+    }
+    const unsigned homes = (unsigned)winmask | (unsigned)(winmask >> 32);            // slots key & 31 in use
+    if (len >= 5 && __popc(homes) == len) {
+        if (mynode >= 0) sh.perm[__popc(homes & ((1u << (mynode & 31)) - 1u))] = (unsigned char)mynode;
+        __syncwarp();
+        return;
+    }
+    {
         // the first 5 insertions go into the initial 8-slot table (mask 7: no linear probes, only the perturbed
         // recurrence), kept as 8 bytes (key + 1, 0 = unused) of one uniform 64-bit word
         unsigned long long t8 = 0ull;
@@ -95,56 +115,27 @@ __device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int le
         }
         const unsigned full = __ballot_sync(TAPENV_FULL_MASK, slot >= 0);
         if (slot >= 0) sh.perm[__popc(full & ((1u << lane) - 1u))] = (unsigned char)slot;
-    } else {                                                                 // 19..32 nodes: the table reaches 128 slots
-        if (lane == 0) {
-            unsigned char *table = sh.tab[0], *other = sh.tab[1];
-            unsigned mask = 7u;
-            int fill = 0;
-            for (unsigned s = 0; s < 128u; ++s) table[s] = 0xff;
-            for (int q = 0; q < len; ++q) {
-                const unsigned key = sh.list[q];
-                unsigned i = key & mask, perturb = key;
-                for (bool placed = false; !placed;) {
-                    const unsigned probes = (i + 9u <= mask) ? 9u : 0u;
-                    for (unsigned j = 0; j <= probes; ++j) if (table[i + j] == 0xff) { table[i + j] = (unsigned char)key; placed = true; break; }
-                    perturb >>= 5; i = (i * 5u + 1u + perturb) & mask;
-                }
-                ++fill;
-                if ((unsigned)fill * 5u >= mask * 3u) {
-                    const unsigned nmask = mask == 7u ? 31u : 127u;
-                    for (unsigned s = 0; s <= nmask; ++s) other[s] = 0xff;
-                    for (unsigned s = 0; s <= mask; ++s) {
-                        if (table[s] == 0xff) continue;
-                        const unsigned k = table[s];
-                        unsigned i2 = k & nmask, pt = k;
-                        for (bool placed = false; !placed;) {
-                            const unsigned probes = (i2 + 9u <= nmask) ? 9u : 0u;
-                            for (unsigned j = 0; j <= probes; ++j) if (other[i2 + j] == 0xff) { other[i2 + j] = (unsigned char)k; placed = true; break; }
-                            pt >>= 5; i2 = (i2 * 5u + 1u + pt) & nmask;
-                        }
-                    }
-                    unsigned char *t = table; table = other; other = t;
-                    mask = nmask;
-                }
-            }
-            int cnt = 0;
-            for (unsigned s = 0; s <= mask; ++s) if (table[s] != 0xff) sh.perm[cnt++] = table[s];
-        }
     }
     __syncwarp();
 }
 
-// remove_block(sub_graph_nodes[rm]) (rm < 0: nothing) + sub_deps_graph + convert_to_input for environment b.
-// On entry sh.list holds the stored window (list order == sorted).  Emits the tensors and stores the new state.
-template <bool FAST>
-__device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, const uint4 *lut, int b, int lane, unsigned long long gone,
-                                               unsigned long long after, int len, int flags, int rm, unsigned *ws,
-                                               const unsigned long long *__restrict__ pe, unsigned long long pm0,
-                                               unsigned long long pm1, const int *__restrict__ blk,
-                                               float *__restrict__ static_out, float *__restrict__ dynamic_out,
-                                               float *__restrict__ cur_mask, float *__restrict__ mask_out,
-                                               int *__restrict__ nodes_out, int *__restrict__ remaining_out) {
-    const int T = w.T, n = w.n, S = w.S;
+struct WinEarly {                // what phase A hands to phase B (registers)
+    unsigned long long gone, after, winmask;
+    int len, flags, mynode;
+    bool decompose;
+    unsigned long long pa, pb;   // predecessor words of (graph slot, SORTED column) for the 3-graphs-per-ballot layout
+    int bd0, bd1, bd2;           // un-rotated edge lengths of sorted node `lane` (rotation-structured blocks)
+};
+
+// Phase A: remove_block(sub_graph_nodes[rm]) (rm < 0: nothing) + the admission loop of sub_deps_graph.  Leaves the
+// window in sh.list (list order: survivors sorted, then admissions) and sh.sorted, and ISSUES the global loads whose
+// addresses depend only on the window's node set, so that their DRAM latency is covered by whatever the caller runs
+// between the two phases (the placement) and by the set-order replay.
+__device__ __forceinline__ WinEarly window_refill(const WinCfg &w, WinShared &sh, int lane, unsigned long long gone,
+                                                  unsigned long long after, int len, int flags, int rm,
+                                                  const unsigned long long *__restrict__ pe, unsigned long long pm0,
+                                                  unsigned long long pm1, const int *__restrict__ blk) {
+    const int T = w.T, n = w.n;
     // ---- remove_block: list.remove(value) (generate.py:1818) ----
     if (rm >= 0 && rm < len) {
         const int mine = sh.list[lane];
@@ -181,48 +172,104 @@ __device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, c
         if (len == n) { decompose = true; break; }          // :1745-1748
     }
     __syncwarp();
-    const int mynode = lane < len ? (int)sh.list[lane] : -1;
-    const unsigned long long mybit = mynode >= 0 ? (1ull << mynode) : 0ull;
-    const unsigned long long winmask = (unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)mybit) |
-                                       ((unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)(mybit >> 32)) << 32);
+    WinEarly e;
+    e.mynode = lane < len ? (int)sh.list[lane] : -1;
+    const unsigned long long mybit = e.mynode >= 0 ? (1ull << e.mynode) : 0ull;
+    e.winmask = (unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)mybit) |
+                ((unsigned long long)__reduce_or_sync(TAPENV_FULL_MASK, (unsigned)(mybit >> 32)) << 32);
+    if (e.mynode >= 0) sh.sorted[__popcll(e.winmask & below64(e.mynode))] = (unsigned char)e.mynode;   // .sort() (:1766)
+    __syncwarp();
+    e.gone = gone; e.after = after; e.len = len; e.flags = flags; e.decompose = decompose;
+    e.pa = e.pb = 0ull;
+    if (decompose && 3 * len <= 32) {
+        const int q = lane >= 2 * len ? 2 : (lane >= len ? 1 : 0), jj = lane - q * len;
+        if (lane < 3 * len) {
+            const int v = sh.sorted[jj];
+            e.pa = pe[q * T + v];
+            if (w.dim == 3 && q < 2) e.pb = pe[(3 + q) * T + v];
+        }
+    }
+    e.bd0 = e.bd1 = e.bd2 = 0;
+    if (w.rotblocks && lane < len) {
+        const int *p = blk + (int)sh.sorted[lane] * w.dim;
+        e.bd0 = p[0]; e.bd1 = p[1];
+        if (w.dim == 3) e.bd2 = p[2];
+    }
+    return e;
+}
+
+// Phase B: decompose + convert_to_input for environment b.  Emits the tensors and stores the new state.
+template <bool FAST>
+__device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, const uint4 *lut, int b, int lane, WinEarly e,
+                                            unsigned *ws, const unsigned long long *__restrict__ pe,
+                                            const int *__restrict__ blk, float *__restrict__ static_out,
+                                            float *__restrict__ dynamic_out, float *__restrict__ cur_mask,
+                                            float *__restrict__ mask_out, int *__restrict__ nodes_out,
+                                            int *__restrict__ remaining_out) {
+    const int T = w.T, n = w.n, S = w.S, len = e.len;
+    const unsigned long long after = e.after, winmask = e.winmask;
+    unsigned long long gone = e.gone;
+    int flags = e.flags;
+    const int mynode = e.mynode;
     // ---- decompose: node enumeration P, the five [n,n] sub-matrices (generate.py:1682-1724, :1750-1764) ----
-    // Lane jj holds the predecessor words of column node P[jj]; row i' of sub-matrix g is the ballot over the columns of
-    // "P[i'] is a predecessor of P[jj]" (+ the diagonal self-loop of the rotation graphs), kept by lane i'.
+    // Row i' of sub-matrix g is the ballot over the columns jj of "P[i'] is a predecessor of P[jj]" (+ the diagonal
+    // self-loop of the rotation graphs), kept by lane i'.
     unsigned myrow[5] = {0u, 0u, 0u, 0u, 0u};
-    if (decompose) {
-        if (w.setorder) pyset_order_warp(sh, lane, len);
+    if (e.decompose) {
+        if (w.setorder) pyset_order_warp(sh, lane, len, mynode, winmask);
         else { if (mynode >= 0) sh.perm[__popcll(winmask & below64(mynode))] = (unsigned char)mynode; __syncwarp(); }
         const int ng = w.dim == 3 ? 5 : 3;                  // 2D: forward/backward have no edges
-        unsigned lo[5] = {0u, 0u, 0u, 0u, 0u}, hi[5] = {0u, 0u, 0u, 0u, 0u};
-        unsigned loopbits = 0u;                             // bit g: a predecessor of this column still waits outside (:1690-1705)
-        if (lane < len) {
-            const int v = sh.perm[lane];
+        if (3 * len <= 32) {
+            // lane = (graph slot q, column jj): one predecessor word per lane and pass, one ballot per sub-matrix row
+            // yields that row of three graphs at once.  Pass 0: move/left/right, pass 1 (3D): forward/backward.  The
+            // words were loaded in phase A by sorted column index; fetch the one of column node P[jj].
+            const int q = lane >= 2 * len ? 2 : (lane >= len ? 1 : 0), jj = lane - q * len;
+            const bool col = lane < 3 * len;
+            const int v = col ? (int)sh.perm[jj] : 0;
+            const int src = col ? q * len + __popcll(winmask & below64(v)) : 0;
             const unsigned alo = (unsigned)after, ahi = (unsigned)(after >> 32);
-#pragma unroll
-            for (int g = 0; g < 5; ++g) {
-                if (g < ng) {
-                    const unsigned long long pg = pe[g * T + v];
-                    lo[g] = (unsigned)pg; hi[g] = (unsigned)(pg >> 32);
-                    if (g >= 1 && ((lo[g] & alo) | (hi[g] & ahi))) loopbits |= 1u << g;
+            const unsigned fld = (1u << len) - 1u;
+            for (int pass = 0; pass < (w.dim == 3 ? 2 : 1); ++pass) {
+                const int g = pass * 3 + q;
+                const bool act = col && g < 5;
+                const unsigned long long word = pass == 0 ? e.pa : e.pb;
+                unsigned plo = __shfl_sync(TAPENV_FULL_MASK, (unsigned)word, src);
+                unsigned phi = __shfl_sync(TAPENV_FULL_MASK, (unsigned)(word >> 32), src);
+                if (!act) { plo = 0u; phi = 0u; }
+                const bool loop = g >= 1 && ((plo & alo) | (phi & ahi)) != 0u;      // :1690-1705
+                unsigned keep = 0u;
+                for (int i = 0; i < len; ++i) {
+                    const int u = sh.perm[i];                   // warp-uniform
+                    const unsigned bit = (u < 32 ? (plo >> u) : (phi >> (u - 32))) & 1u;
+                    const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, bit != 0u || (loop && jj == i));
+                    if (lane == i) keep = rowbits;
                 }
+                if (pass == 0) { myrow[0] = keep & fld; myrow[1] = (keep >> len) & fld; myrow[2] = (keep >> (2 * len)) & fld; }
+                else { myrow[3] = keep & fld; myrow[4] = (keep >> len) & fld; }
             }
-        }
-        for (int i = 0; i < len; ++i) {
-            const int u = sh.perm[i];                       // warp-uniform
-            const unsigned diag = lane == i ? loopbits : 0u;
-            if (u < 32) {
+        } else {
+            unsigned lo[5] = {0u, 0u, 0u, 0u, 0u}, hi[5] = {0u, 0u, 0u, 0u, 0u};
+            unsigned loopbits = 0u;                         // bit g: a predecessor of this column still waits outside (:1690-1705)
+            if (lane < len) {
+                const int v = sh.perm[lane];
+                const unsigned alo = (unsigned)after, ahi = (unsigned)(after >> 32);
 #pragma unroll
                 for (int g = 0; g < 5; ++g) {
                     if (g < ng) {
-                        const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, ((lo[g] >> u) | (diag >> g)) & 1u);
-                        if (lane == i) myrow[g] = rowbits;
+                        const unsigned long long pg = pe[g * T + v];
+                        lo[g] = (unsigned)pg; hi[g] = (unsigned)(pg >> 32);
+                        if (g >= 1 && ((lo[g] & alo) | (hi[g] & ahi))) loopbits |= 1u << g;
                     }
                 }
-            } else {
+            }
+            for (int i = 0; i < len; ++i) {
+                const int u = sh.perm[i];                   // warp-uniform
+                const unsigned diag = lane == i ? loopbits : 0u;
 #pragma unroll
                 for (int g = 0; g < 5; ++g) {
                     if (g < ng) {
-                        const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, ((hi[g] >> (u - 32)) | (diag >> g)) & 1u);
+                        const unsigned bit = u < 32 ? (lo[g] >> u) : (hi[g] >> (u - 32));
+                        const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, (bit | (diag >> g)) & 1u);
                         if (lane == i) myrow[g] = rowbits;
                     }
                 }
@@ -240,12 +287,9 @@ __device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, c
     const unsigned long long any1 = (unsigned long long)warp_or((unsigned)row1) | ((unsigned long long)warp_or((unsigned)(row1 >> 32)) << 32);
     const unsigned long long any2 = (unsigned long long)warp_or((unsigned)row2) | ((unsigned long long)warp_or((unsigned)(row2 >> 32)) << 32);
     const unsigned long long blocked = any0 | (any1 & any2);      // rolling.py:325-335
-    // ---- self.sub_graph_nodes.sort() (:1766) ----
-    __syncwarp();
-    if (mynode >= 0) sh.list[__popcll(winmask & below64(mynode))] = (unsigned char)mynode;
     if (len < n) flags |= 2;                                // the reference raises in np.concatenate (:1788)
     __syncwarp();
-    const int sorted = lane < len ? (int)sh.list[lane] : 0xff;
+    const int sorted = lane < len ? (int)sh.sorted[lane] : 0xff;
     // ---- state ----
     if (lane == 0) {
         *reinterpret_cast<unsigned long long *>(ws) = gone;
@@ -260,10 +304,22 @@ __device__ __forceinline__ void window_advance(const WinCfg &w, WinShared &sh, c
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int j = lane + 32 * half;
-        if (j < S) {
-            const int r = (int)(((unsigned)j * w.inv_n) >> 16), i = j - r * n;
+        const bool on = j < S;
+        const int r = on ? (int)(((unsigned)j * w.inv_n) >> 16) : 0, i = on ? j - r * n : 0;
+        if (w.rotblocks) {                                  // blocks[r*T + node][d] == blocks[node][perm_r[d]]
+            const int a0 = __shfl_sync(TAPENV_FULL_MASK, e.bd0, i), a1 = __shfl_sync(TAPENV_FULL_MASK, e.bd1, i);
+            const int a2 = __shfl_sync(TAPENV_FULL_MASK, e.bd2, i);
+            if (on) {
+                so[j] = (float)i;
+                const unsigned pc = (unsigned)(w.permcodes >> (6 * r));
+                for (int d = 0; d < w.dim; ++d) {
+                    const unsigned c = (pc >> (2 * d)) & 3u;
+                    so[(1 + d) * S + j] = i < len ? (float)(c == 0u ? a0 : (c == 1u ? a1 : a2)) : 0.f;
+                }
+            }
+        } else if (on) {
             so[j] = (float)i;
-            const int node = i < len ? (int)sh.list[i] : -1;
+            const int node = i < len ? (int)sh.sorted[i] : -1;
             for (int d = 0; d < w.dim; ++d) so[(1 + d) * S + j] = node >= 0 ? (float)blk[(node + r * T) * w.dim + d] : 0.f;
         }
     }

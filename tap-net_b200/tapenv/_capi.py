@@ -26,7 +26,7 @@ class PeerComm(C.Structure):  # struct tapenv_peer_comm
 
 
 class WindowConfig(C.Structure):  # struct tapenv_window_config
-    _fields_ = [(n, c_int32) for n in ("batch", "total_blocks", "window", "dim", "rotate_types", "node_order")]
+    _fields_ = [(n, c_int32) for n in ("batch", "total_blocks", "window", "dim", "rotate_types", "node_order", "blocks_are_rotations")]
 
 
 class Limits(C.Structure):  # struct tapenv_limits

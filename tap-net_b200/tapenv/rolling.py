@@ -18,6 +18,17 @@ from .containers import BatchedContainers
 from .ops import _dev, _p, _stream
 
 
+def rotation_structured(blocks, total_blocks, dim):
+    """True iff blocks[..., r*T+i, :] == blocks[..., i, perm_r] for every rotation r of itertools.permutations(range(dim))
+    -- the layout generate.generate_blocks writes (numpy array [B,R*T,dim] or [R*T,dim])."""
+    import itertools
+    blocks = np.asarray(blocks)
+    T = int(total_blocks)
+    base = blocks[..., :T, :]
+    return all(np.array_equal(blocks[..., r * T:(r + 1) * T, :], base[..., list(p)])
+               for r, p in enumerate(itertools.permutations(range(dim))))
+
+
 def pack_graphs(adj):
     """adj [B,5,T,T] 0/1 with adj[b,g,u,v] = edge u -> v (deps_g[u,v] == True, generate.py:1636-1664)
     -> predecessor masks int64 [B,5,T]: bit u of pred[b,g,v]."""
@@ -34,7 +45,7 @@ class BatchedInitialContainers(object):
     adjacency; blocks: [B,R*T,dim] rotation-major block sizes (rolling.py:483-485)."""
 
     def __init__(self, graphs, blocks, blocks_num, child_graph_size, block_dim, device=None,
-                 node_order=_capi.WINDOW_ORDER_REFERENCE, input_type="bot"):
+                 node_order=_capi.WINDOW_ORDER_REFERENCE, input_type="bot", blocks_are_rotations=None):
         if not torch.cuda.is_available():
             raise RuntimeError("tapenv: a CUDA device is required (no CPU fallback exists)")
         if input_type != "bot":
@@ -55,17 +66,37 @@ class BatchedInitialContainers(object):
             raise _capi.TapEnvError(_capi.ESHAPE, "graphs %s / blocks %s" % (tuple(graphs.shape), tuple(blocks.shape)))
         self.batch_size = B
         self.S = n * R
-        self.wcfg = _capi.WindowConfig(B, T, n, dim, R, int(node_order))
+        self.graphs = graphs.to(self.device, torch.int64).contiguous()
+        self.blocks = blocks.to(self.device, torch.int32).contiguous()
+        # blocks_are_rotations: None = check `blocks` now; pass False/True explicitly when the buffer will be overwritten
+        # later (host pipelines) -- False is always correct, True promises the rotation layout of generate_blocks
+        rot = self._rotation_structured() if blocks_are_rotations is None else bool(blocks_are_rotations)
+        self.wcfg = _capi.WindowConfig(B, T, n, dim, R, int(node_order), int(rot))
         nbytes = int(_capi.lib.tapenv_window_state_bytes(C.byref(self.wcfg)))
         if B > 0 and nbytes == 0:
             raise _capi.TapEnvError(_capi.ELIMIT, "window config (total_blocks <= 64, window <= 32, window*R <= 64)")
-        self.graphs = graphs.to(self.device, torch.int64).contiguous()
-        self.blocks = blocks.to(self.device, torch.int32).contiguous()
         self.state = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=self.device)
         self.sub_graph_nodes = torch.full((B, n), -1, dtype=torch.int32, device=self.device)   # sorted, as generate.py:1766 leaves it
         self.remaining = torch.full((B,), T, dtype=torch.int32, device=self.device)             # len(after_nodes_list)
         self._pending = None
         self.reset()
+
+    def _rotation_structured(self):
+        """True iff blocks[:, r*T+i, :] == blocks[:, i, perm_r] for every rotation (how generate.generate_blocks lays the
+        rotations out); checked on the device once, lets the kernel read only the un-rotated rows."""
+        import itertools
+        T, dim = self.blocks_num, self.block_dim
+        if self.blocks.numel() == 0:
+            return True
+        base = self.blocks[:, :T, :]
+        ok = True
+        for r, p in enumerate(itertools.permutations(range(dim))):
+            ok = ok and bool(torch.equal(self.blocks[:, r * T:(r + 1) * T, :], base[:, :, list(p)]))
+        return ok
+
+    def refresh_blocks(self):
+        """Call after overwriting `self.blocks` in place (e.g. a host pipeline re-using the buffers)."""
+        self.wcfg.blocks_are_rotations = int(self._rotation_structured())
 
     def reset(self):
         """Back to the freshly constructed InitialContainer (generate.py:1666-1673)."""
@@ -231,7 +262,9 @@ class RollingHostPipeline(object):
     episode replay on the compute stream, D2H of rewards + sums.  Same protocol as runner.HostPipeline."""
 
     def __init__(self, env, total_blocks, window, depth=2, use_graph=True, exchange=None,
-                 node_order=_capi.WINDOW_ORDER_REFERENCE):
+                 node_order=_capi.WINDOW_ORDER_REFERENCE, blocks_are_rotations=False):
+        """blocks_are_rotations=True promises that every submitted `blocks` array has generate_blocks' rotation layout
+        (rotation_structured(blocks) -- check once per dataset); the default reads all R*T rows."""
         self.env = env
         dev = env.device
         B, dim = env.batch_size, env.block_dim
@@ -243,7 +276,8 @@ class RollingHostPipeline(object):
             graphs = torch.zeros(B, 5, total_blocks, dtype=torch.int64, device=dev)
             blocks = torch.ones(B, R * total_blocks, dim, dtype=torch.int32, device=dev)
             pq = torch.zeros(total_blocks, B, dtype=torch.int64, device=dev)
-            win = BatchedInitialContainers(graphs, blocks, total_blocks, window, dim, device=dev, node_order=node_order)
+            win = BatchedInitialContainers(graphs, blocks, total_blocks, window, dim, device=dev, node_order=node_order,
+                                           blocks_are_rotations=blocks_are_rotations)
             runner = RollingRunner(env, win, ptr_seq=pq, use_graph=use_graph, partial_sums=True, exchange=exchange)
             self.slots.append(dict(win=win, ptr=pq, runner=runner, uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(),
                                    done=torch.cuda.Event(), reward=torch.empty(B, dtype=torch.float32).pin_memory(),

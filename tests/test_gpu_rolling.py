@@ -191,3 +191,37 @@ def test_window_flags_and_errors():
     empty = tapenv.BatchedInitialContainers(data["adj"][:0], data["blocks"][:0], 50, 10, 2)
     s, d = empty.convert_to_input()
     assert s.shape == (0, 3, 20) and d.shape == (0, 30, 20)
+
+
+def test_blocks_without_rotation_structure_take_the_generic_path():
+    """blocks_are_rotations is only an optimisation: arbitrary [R*T,dim] block tables give the same static rows as the
+    oracle (every rotation row read from the table), and the flag is detected from the data."""
+    tapenv = _tapenv()
+    data = load_rolling("rolling3d_t50.npz", 16)
+    T, n, dim = 50, 10, 3
+    blocks = data["blocks"].copy()
+    rng = np.random.RandomState(0)
+    blocks[:, T:] = rng.randint(1, 6, size=blocks[:, T:].shape)          # rotations no longer permutations of row i
+    win = tapenv.BatchedInitialContainers(data["adj"], blocks, T, n, dim)
+    assert win.wcfg.blocks_are_rotations == 0
+    ok = tapenv.BatchedInitialContainers(data["adj"], data["blocks"], T, n, dim)
+    assert ok.wcfg.blocks_are_rotations == 1
+    ocs = [oracle.InitialContainer(data["adj"][b], blocks[b], T, n, dim) for b in range(16)]
+    for call in range(5):
+        static, dynamic = win.convert_to_input()
+        outs = [oc.convert_to_input() for oc in ocs]
+        assert np.array_equal(static.cpu().numpy(), np.stack([o[0] for o in outs]))
+        assert np.array_equal(dynamic.cpu().numpy(), np.stack([o[1] for o in outs]))
+        ptr = np.zeros(16, np.int64)
+        for b, oc in enumerate(ocs):
+            oc.remove_block(oc.sub_graph_nodes[0])
+        win.remove_block(torch.from_numpy(ptr).cuda())
+    # the fused step gathers the chosen block from the same table
+    env = tapenv.BatchedContainers([5, 5, 250], T, "C+P+S-lb-soft", "diff", batch_size=16, window=n)
+    win2 = tapenv.BatchedInitialContainers(data["adj"], blocks, T, n, dim)
+    run = tapenv.RollingRunner(env, win2)
+    static, dynamic, cur = run.begin()
+    ptr = torch.argmax(cur, dim=1)
+    want = torch.gather(static[:, 1:], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1)).squeeze(2).clone()
+    _, _, _, dec_static, _ = run.step(ptr)
+    assert torch.equal(dec_static, want)
