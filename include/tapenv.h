@@ -241,6 +241,23 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
                    float *cur_mask_out, float *mask_out, float *dec_dynamic_out, void *stream);
 
 
+/* ---- two-container inputs: input_type 'mul' / 'mul-with' (model.py:286-292, :396-447, :503-507) ----------------------
+ * `static` has 2+dim rows: block id, edge lengths, target container id (0 = A, 1 = B; pack.py:212-216).  Every environment
+ * owns TWO containers (two state buffers of the same config).  The tensor side equals 'bot' (pack.py:300-302, :354-357), so
+ * tapenv_update_dynamic / tapenv_update_mask / tapenv_reset apply unchanged (reset each state).
+ *   tapenv_step_mul: fused decode step; the chosen block goes into the container its candidate names, the decoder input
+ *     is both heightmaps: dec_dynamic_out f32 [B, 2, enc] = cat(A, B) (model.py:421-447).  dec_static_out f32
+ *     [B, dec_static_rows]: dec_static_rows = dim for 'mul' (static[:,1:-1,:]) or dim+1 for 'mul-with' (static[:,1:,:]),
+ *     model.py:388-394.  A target id other than 0/1 sets flag 4 in both states (the reference fails at :437).
+ *   tapenv_add_blocks_mul: the unfused placement (blocks f32 [B,dim], target_ids f32 [B]).
+ *   tapenv_reward_mul: reward_out f32 [B] = (calc_ratio(A) + calc_ratio(B)) / 2, accumulated in fp32 as model.py:503-507 does. */
+int tapenv_step_mul(const tapenv_config *cfg, void *state_a, void *state_b, const int64_t *ptr, const float *static_,
+                    const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                    float *mask_out, float *dec_static_out, int32_t dec_static_rows, float *dec_dynamic_out, void *stream);
+int tapenv_add_blocks_mul(const tapenv_config *cfg, void *state_a, void *state_b, const float *blocks,
+                          const float *target_ids, float *dec_dynamic_out, void *stream);
+int tapenv_reward_mul(const tapenv_config *cfg, const void *state_a, const void *state_b, float *reward_out, void *stream);
+
 /* ---- rolling window --------------------------------------------------------------------------------------------
  * generate.InitialContainer (generate.py:1589-1825) for B instances: the window of `window` (= child_graph_size) nodes
  * the network sees while ONE container takes all `total_blocks` blocks (rolling.py:575-640, :702-703).

@@ -555,6 +555,106 @@ __global__ void reward_kernel(DevCfg c, StatePtrs st, float *__restrict__ reward
     reward[b] = (float)calc_ratio_dev(c, s.x, s.y, s.z, s.w, height);   // scores[batch_index] = ... (model.py:510), fp32 tensor
 }
 
+
+// ------------------------------------------------------------------------------------
+// Two-container inputs ('mul' / 'mul-with', model.py:286-292, :396-447, :503-507): `static` carries one more row, the
+// target container id of every candidate (pack.py:212-216); the chosen block goes into container A (id 0) or B (id 1)
+// of its environment and the decoder sees both heightmaps, cat(A, B) (model.py:421-447).  Tensor side identical to
+// 'bot' (pack.py:300-302, :354-357).
+// ------------------------------------------------------------------------------------
+template <int STRAT>
+__device__ __forceinline__ void mul_place(const DevCfg &c, const StatePtrs &sa, const StatePtrs &sb, int b, int lane, int tgt,
+                                          int bx, int by, int bz, float *dec_dyn, unsigned *ems_keys, int extra_flags) {
+    const bool valid = tgt == 0 || tgt == 1;          // any other id: the reference appends to neither list and fails later
+    const StatePtrs &st = tgt == 1 ? sb : sa;
+    if (valid) {
+        EnvRegs<STRAT> e; e.load(c, st, b, lane);
+        // container_add_block addresses its output as dec_dyn + b*enc_len; here rows are [B][2][enc_len]
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn ? dec_dyn + (size_t)(b + tgt) * c.enc_len : nullptr,
+                                   ems_keys, extra_flags);
+    } else if (lane == 0) {
+        sa.flags[b] |= 4; sb.flags[b] |= 4;
+    }
+    if (dec_dyn) {                                    // the other container: get_heightmap() (tools.py:3824-3856)
+        for (int k = 0; k < 2; ++k) {
+            if (valid && k == tgt) continue;          // already written by add_new_block
+            const StatePtrs &o = k ? sb : sa;
+            EnvRegs<STRAT> e2; e2.load(c, o, b, lane);
+            float *out = dec_dyn + ((size_t)b * 2 + k) * c.enc_len;
+            if (STRAT == STRAT_LBG3D) encode_heightmap_3d(c, lane, e2.x, e2.y, e2.h, out);
+            else encode_heightmap_2d(c, lane, e2.h, out);
+        }
+    }
+}
+
+template <int STRAT, bool FAST>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+step_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
+                const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
+                float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static, int dec_rows,
+                float *__restrict__ dec_dyn) {
+    typedef Shape<0, 0, 0> SH;
+    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const int S = c.S;
+    const float *srow = env_ptr(static_, b, c.static_env);
+    const float *din = env_ptr(dynamic_in, b, c.dyn_env);
+    float *dout = env_ptr(dynamic_out, b, c.dyn_env);
+    const float *min_ = env_ptr(mask_in, b, (unsigned)S);
+    const long long p64 = ptr[b];
+    const float m0 = lane < S ? min_[lane] : 0.f;
+    const float m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
+    const bool badp = p64 < 0 || p64 >= S;
+    const int p = badp ? 0 : (int)p64;
+    const int real = (int)srow[p];                                           // pack.py:355
+    const int tgt = (int)srow[(c.static_rows - 1) * S + p];                  // target_ids = static[:,-1,:] gathered (model.py:396-401)
+    float dimv = 0.f;
+    if (lane < dec_rows) dimv = srow[(1 + lane) * S + p];                    // 'mul': static[:,1:-1,:], 'mul-with': static[:,1:,:] (model.py:388-394)
+    if (dec_static && lane < dec_rows) dec_static[(size_t)b * dec_rows + lane] = dimv;
+    const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+    const int by = DIM == 3 ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+    const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
+    const BandBits bits = dynpass<SH, FAST>(c, lane, din, dout, real);
+    mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
+                  env_ptr(mask_out, b, (unsigned)S));
+    mul_place<STRAT>(c, sa, sb, b, lane, tgt, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+}
+
+template <int STRAT>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+add_blocks_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const float *__restrict__ blocks, const float *__restrict__ target_ids,
+                      float *__restrict__ dec_dyn) {
+    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    int lane, warp; const int b = env_index(lane, warp);
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const float *blk = blocks + (size_t)b * DIM;
+    const int bx = (int)blk[0], by = DIM == 3 ? (int)blk[1] : 1, bz = (int)blk[DIM - 1];
+    mul_place<STRAT>(c, sa, sb, b, lane, (int)target_ids[b], bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+}
+
+// scores = (calc_ratio(A) + calc_ratio(B)) / 2 accumulated in an fp32 tensor (model.py:503-507)
+__global__ void reward_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, float *__restrict__ reward) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const int cells = c.dim == 2 ? c.W : c.W * c.L;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const StatePtrs &st = k ? sb : sa;
+        const int4 s = st.scal[b];
+        int height = 0;
+        for (int i = 0; i < cells; ++i) height = max(height, st.heightmap[(size_t)b * cells + i]);
+        acc = __fadd_rn(acc, (float)calc_ratio_dev(c, s.x, s.y, s.z, s.w, height));
+    }
+    reward[b] = __fdiv_rn(acc, 2.0f);
+}
+
 // ------------------------------------------------------------------------------------
 // K7 whole-episode kernel: reset + `steps` decode steps + reward in ONE launch, for a known pointer
 // sequence.  The precedence tensor is read ONCE and kept as bit rows in shared memory (one 64-bit word per
@@ -927,8 +1027,10 @@ int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, in
     } else if (!strcmp(input_type, "bot") || !strcmp(input_type, "bot-rot") ||
                !strcmp(input_type, "use-static") || !strcmp(input_type, "use-pnet")) {
         cfg->static_rows = 1 + dim; cfg->dyn_rows = 3 * n; cfg->update_time = 3;
-    } else if (!strcmp(input_type, "mul") || !strcmp(input_type, "mul-with") || !strcmp(input_type, "rot-old")) {
-        return TAPENV_EUNSUPPORTED;   // two-container inputs / legacy layout: out of scope
+    } else if (!strcmp(input_type, "mul") || !strcmp(input_type, "mul-with")) {
+        cfg->static_rows = 2 + dim; cfg->dyn_rows = 3 * n; cfg->update_time = 3;   // + target container id row (pack.py:212-216)
+    } else if (!strcmp(input_type, "rot-old")) {
+        return TAPENV_EUNSUPPORTED;   // legacy layout
     } else return TAPENV_EENUM;
     const int rc = check_cfg(cfg);
     if (rc != TAPENV_OK) return rc;
@@ -1138,6 +1240,58 @@ int tapenv_reset_packed(const tapenv_config *cfg, void *state, const uint8_t *st
     else
         launch(unpack_reset_kernel<false>, grid, block, s, d, st, clear, (const unsigned char *)static_u8, (const unsigned *)dynamic_bits, words,
                static_out, dynamic_out, cur_mask_out, mask_out);
+    return launch_status();
+}
+
+// ---- two-container inputs ('mul' / 'mul-with') --------------------------------------------------------------------
+int tapenv_step_mul(const tapenv_config *cfg, void *state_a, void *state_b, const int64_t *ptr, const float *static_,
+                    const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                    float *mask_out, float *dec_static_out, int32_t dec_static_rows, float *dec_dynamic_out, void *stream) {
+    TAPENV_PROLOGUE(cfg)
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;
+    if (cfg->static_rows != 2 + cfg->dim) return TAPENV_ESHAPE;
+    if (dec_static_rows != cfg->dim && dec_static_rows != cfg->dim + 1) return TAPENV_ESHAPE;
+    if (d.B == 0) return TAPENV_OK;
+    if (!state_a || !state_b || state_a == state_b || !ptr || !static_ || !dynamic_in || !mask_in || !dynamic_out || !cur_mask_out || !mask_out)
+        return TAPENV_EINVAL;
+    const StatePtrs sa = stateptrs_of(cfg, state_a), sb = stateptrs_of(cfg, state_b);
+    const bool fast = fast_ok(d, dynamic_in, dynamic_out);
+#define TAPENV_MUL(STRAT)                                                                                               \
+    do {                                                                                                                \
+        if (fast) launch(step_mul_kernel<STRAT, true>, grid, block, s, d, sa, sb, ptr, static_, dynamic_in, mask_in,     \
+                         dynamic_out, cur_mask_out, mask_out, dec_static_out, (int)dec_static_rows, dec_dynamic_out);   \
+        else launch(step_mul_kernel<STRAT, false>, grid, block, s, d, sa, sb, ptr, static_, dynamic_in, mask_in,         \
+                    dynamic_out, cur_mask_out, mask_out, dec_static_out, (int)dec_static_rows, dec_dynamic_out);        \
+    } while (0)
+    if (strat == STRAT_LBG2D) TAPENV_MUL(STRAT_LBG2D);
+    else if (strat == STRAT_LBG3D) TAPENV_MUL(STRAT_LBG3D);
+    else TAPENV_MUL(STRAT_MACS2D);
+    return launch_status();
+}
+
+int tapenv_add_blocks_mul(const tapenv_config *cfg, void *state_a, void *state_b, const float *blocks,
+                          const float *target_ids, float *dec_dynamic_out, void *stream) {
+    TAPENV_PROLOGUE(cfg)
+    const int strat = strategy_kernel(cfg);
+    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;
+    if (d.B == 0) return TAPENV_OK;
+    if (!state_a || !state_b || state_a == state_b || !blocks || !target_ids) return TAPENV_EINVAL;
+    const StatePtrs sa = stateptrs_of(cfg, state_a), sb = stateptrs_of(cfg, state_b);
+    if (strat == STRAT_LBG2D) launch(add_blocks_mul_kernel<STRAT_LBG2D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    else if (strat == STRAT_LBG3D) launch(add_blocks_mul_kernel<STRAT_LBG3D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    else launch(add_blocks_mul_kernel<STRAT_MACS2D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    return launch_status();
+}
+
+int tapenv_reward_mul(const tapenv_config *cfg, const void *state_a, const void *state_b, float *reward_out, void *stream) {
+    int rc_ = check_cfg(cfg);
+    if (rc_ != TAPENV_OK) return rc_;
+    if (cfg->batch == 0) return TAPENV_OK;
+    if (!state_a || !state_b || !reward_out) return TAPENV_EINVAL;
+    const DevCfg d = devcfg_of(cfg);
+    const StatePtrs sa = stateptrs_of(cfg, const_cast<void *>(state_a)), sb = stateptrs_of(cfg, const_cast<void *>(state_b));
+    launch(reward_mul_kernel, (d.B + 127) / 128, 128, (cudaStream_t)stream, d, sa, sb, reward_out);
     return launch_status();
 }
 

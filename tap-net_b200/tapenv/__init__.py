@@ -11,7 +11,7 @@ from . import _capi
 from ._capi import TapEnvError
 from .config import make_config, rotate_types
 from .ops import update_dynamic, update_mask
-from .containers import BatchedContainers, Container
+from .containers import BatchedContainers, BatchedContainerPairs, Container
 from .runner import EpisodeRunner, HostPipeline
 from . import dist
 from .dataset import PACKDataset, pack_inputs
@@ -20,5 +20,5 @@ from .dropin import install, uninstall
 from .rolling import BatchedInitialContainers, RollingRunner, RollingHostPipeline, pack_graphs
 
 __all__ = ["PACKDataset", "pack_inputs", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
-           "update_dynamic", "update_mask", "Container", "BatchedContainers", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
+           "update_dynamic", "update_mask", "Container", "BatchedContainers", "BatchedContainerPairs", "EpisodeRunner", "HostPipeline", "make_config", "rotate_types",
            "TapEnvError", "BatchedInitialContainers", "RollingRunner", "RollingHostPipeline", "pack_graphs"]

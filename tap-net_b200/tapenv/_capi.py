@@ -62,6 +62,9 @@ SYMBOLS = {
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
     "tapenv_packed_words": (c_int32, [CFG]),
     "tapenv_reset_packed": (c_int, [CFG, P, P, P, P, P, P, P, P]),
+    "tapenv_step_mul": (c_int, [CFG] + [P] * 10 + [c_int32, P, P]),
+    "tapenv_add_blocks_mul": (c_int, [CFG] + [P] * 6),
+    "tapenv_reward_mul": (c_int, [CFG, P, P, P, P]),
     "tapenv_window_state_bytes": (c_size_t, [C.POINTER(WindowConfig)]),
     "tapenv_window_reset": (c_int, [C.POINTER(WindowConfig), P, P]),
     "tapenv_window_next": (c_int, [C.POINTER(WindowConfig)] + [P] * 11),

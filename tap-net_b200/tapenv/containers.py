@@ -263,6 +263,88 @@ class BatchedContainers(object):
         return (Container._view_of(self, b) for b in range(self.batch_size))
 
 
+class BatchedContainerPairs(object):
+    """The two container lists model.py builds for input_type 'mul' / 'mul-with' (model.py:286-292:
+    containers_a / containers_b), as two BatchedContainers of one configuration.  Every candidate column of `static`
+    names its target container in the last row (pack.py:212-216); `step` routes the chosen block accordingly and
+    returns both heightmaps, cat(A, B) along dim 1 (model.py:421-447)."""
+
+    def __init__(self, container_size, blocks_num, reward_type, heightmap_type="full", packing_strategy="LB_GREEDY",
+                 batch_size=1, device=None, input_type="mul-with", allow_rot=True):
+        if input_type not in ("mul", "mul-with"):
+            raise _capi.TapEnvError(_capi.EENUM, "BatchedContainerPairs is for input_type 'mul' / 'mul-with'")
+        kw = dict(packing_strategy=packing_strategy, batch_size=batch_size, device=device, input_type=input_type, allow_rot=allow_rot)
+        self.a = BatchedContainers(container_size, blocks_num, reward_type, heightmap_type, **kw)
+        self.b = BatchedContainers(container_size, blocks_num, reward_type, heightmap_type, **kw)
+        self.input_type = input_type
+        self.cfg, self.device, self.batch_size, self.S = self.a.cfg, self.a.device, self.a.batch_size, self.a.S
+        self.block_dim, self.enc_len = self.a.block_dim, self.a.enc_len
+        self.dec_static_rows = self.block_dim + (1 if input_type == "mul-with" else 0)     # model.py:388-394
+
+    def clear_container(self):
+        self.a.clear_container(); self.b.clear_container()
+
+    def reset(self, dynamic):
+        cur, mask = self.a.reset(dynamic)
+        self.b.clear_container()
+        return cur, mask
+
+    def _shape(self, t):
+        B = self.batch_size
+        if self.block_dim == 2:
+            return t.view(B, 2 * self.enc_len)                       # [B, 2*enc] (+ unsqueeze(2) at the caller, model.py:424-430)
+        W, L = self.a.container_size[0], self.a.container_size[1]
+        planes = 2 if self.a.heightmap_type == "diff" else 1
+        return t.view(B, 2 * planes, W, L)                           # model.py:431-441
+
+    def step(self, ptr, static, dynamic, mask, out=None):
+        """-> (dynamic', current_mask, mask', decoder_static [B,dec_static_rows], decoder_dynamic cat(A,B))."""
+        ptr = _dev(ptr, "ptr", torch.int64)
+        static = _dev(static, "static", torch.float32)
+        dynamic = _dev(dynamic, "dynamic", torch.float32)
+        mask = _dev(mask, "mask", torch.float32)
+        B, S = self.batch_size, self.S
+        if tuple(dynamic.shape) != (B, self.cfg.dyn_rows, S) or tuple(static.shape) != (B, self.cfg.static_rows, S) \
+                or tuple(mask.shape) != (B, S) or tuple(ptr.shape) != (B,):
+            raise _capi.TapEnvError(_capi.ESHAPE, "step tensors")
+        if out is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            dyn_out, cur, mask_out = torch.empty_like(dynamic), torch.empty_like(mask), torch.empty_like(mask)
+            dec_static = torch.empty(B, self.dec_static_rows, **f32)
+            dec_dyn = torch.empty(B, 2, self.enc_len, **f32)
+        else:
+            dyn_out, cur, mask_out, dec_static, dec_dyn = out
+        self.a._version += 1; self.b._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_step_mul(C.byref(self.cfg), _p(self.a.state), _p(self.b.state), _p(ptr), _p(static),
+                                                  _p(dynamic), _p(mask), _p(dyn_out), _p(cur), _p(mask_out), _p(dec_static),
+                                                  self.dec_static_rows, _p(dec_dyn), _stream()), "step_mul")
+        return dyn_out, cur, mask_out, dec_static, self._shape(dec_dyn)
+
+    def add_new_blocks(self, blocks, target_ids):
+        """model.py:421-428 for the batch: blocks f32 [B,dim], target_ids [B] (0 -> A, 1 -> B) -> cat(A, B) heightmaps."""
+        blocks = _dev(blocks, "blocks", torch.float32)
+        target_ids = _dev(target_ids, "target_ids", torch.float32).reshape(-1)
+        if tuple(blocks.shape) != (self.batch_size, self.block_dim) or target_ids.numel() != self.batch_size:
+            raise _capi.TapEnvError(_capi.ESHAPE, "blocks / target_ids")
+        out = torch.empty(self.batch_size, 2, self.enc_len, dtype=torch.float32, device=self.device)
+        self.a._version += 1; self.b._version += 1
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_add_blocks_mul(C.byref(self.cfg), _p(self.a.state), _p(self.b.state), _p(blocks),
+                                                        _p(target_ids), _p(out), _stream()), "add_blocks_mul")
+        return self._shape(out)
+
+    def calc_ratio(self):
+        """(calc_ratio(A) + calc_ratio(B)) / 2 in fp32 (model.py:503-507) -> f32 [B]."""
+        r = torch.empty(self.batch_size, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reward_mul(C.byref(self.cfg), _p(self.a.state), _p(self.b.state), _p(r), _stream()), "reward_mul")
+        return r
+
+    def check_flags(self):
+        self.a.check_flags(); self.b.check_flags()
+
+
 class _Group(object):
     """Containers constructed back to back with identical arguments (model.py:294's list comprehension)."""
 

@@ -16,6 +16,8 @@ Writes next to this file:
   kat.npz          the known-answer vectors G1-G5 of SURVEY.md section 4 re-derived from the reference
   rolling{2,3}d_t50.npz   rolling.get_dataset(50, ...) + rolling.RollingDataset: per instance the five precedence
                    graphs of generate.InitialContainer (bit-packed adjacency) + rotation-major blocks + positions
+  traj_*_mul*.npz  the two-container env section of model.DRL.forward (input_type 'mul' / 'mul-with', model.py:396-447,
+                   :499-507) on the live reference: per-step heightmaps of both containers, cat(A,B) decoder input, fp32 scores
   traj_rolling_*.npz      rolling.validate's loop (rolling.py:575-640) on the live reference, network replaced by a
                    seeded random-valid policy: every window's static/dynamic/sub_graph_nodes, every step's
                    ptr / heightmap / returned encoding, final positions / stable / calc_ratio
@@ -310,6 +312,85 @@ def make_rolling_traj():
         print(name, "%.1fs" % (time.time() - t), "mean ratio %.4f" % res["ratio"].mean())
 
 
+def ref_trajectory_mul(static, dynamic, container_size, reward_type, heightmap_type, packing_strategy, seed, input_type):
+    """The two-container env section of model.DRL.forward (model.py:286-292, :376-447, :499-507) on the live reference:
+    static carries the target-container row, the chosen block goes into containers_a / containers_b."""
+    import torch
+    mods = refshim.load(("tools", "pack"))
+    tools, pack = mods["tools"], mods["pack"]
+    static_t = torch.from_numpy(static)
+    dyn = torch.from_numpy(dynamic)
+    B, rows, S = static.shape
+    dim = rows - 2
+    R = 2 if dim == 2 else 6
+    n = S // R
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda: [tools.Container(container_size, n, reward_type, heightmap_type, packing_strategy=packing_strategy) for _ in range(B)]
+    ca, cb = mk(), mk()
+    mask = torch.ones(B, S)
+    dm = dyn[:, n:2 * n].sum(1) * dyn[:, 2 * n:].sum(1) + dyn[:, :n].sum(1)
+    cur = mask.clone(); cur[dm.ne(0)] = 0.0
+    out = dict(ptr=[], hm_a=[], hm_b=[], dec_dyn=[], dec_static=[], cur_mask=[cur.numpy().copy()], mask=[])
+    static_part = static_t[:, 1:-1, :] if input_type == "mul" else static_t[:, 1:, :]                 # model.py:388-394
+    ssz = static_part.shape[1]
+    for t in range(n):
+        ptr = torch.multinomial(cur, 1, generator=g).squeeze(1)
+        dyn = pack.update_dynamic(dyn, static_t, ptr, input_type, True)
+        cur, mask = pack.update_mask(mask, dyn, static_t, ptr, input_type, True)
+        target_ids = torch.gather(static_t[:, -1, :], 1, ptr.view(-1, 1))                               # model.py:396-401
+        decoder_static = torch.gather(static_part, 2, ptr.view(-1, 1, 1).expand(-1, ssz, 1))
+        blocks = decoder_static.transpose(2, 1).squeeze(1).numpy()[:, :dim]
+        ha, hb = [], []
+        for b in range(B):
+            if target_ids[b] == 0:
+                ha.append(np.asarray(ca[b].add_new_block(blocks[b], bool(ptr[b] < n))).copy()); hb.append(np.asarray(cb[b].get_heightmap()).copy())
+            elif target_ids[b] == 1:
+                ha.append(np.asarray(ca[b].get_heightmap()).copy()); hb.append(np.asarray(cb[b].add_new_block(blocks[b], bool(ptr[b] < n))).copy())
+        ha, hb = torch.FloatTensor(np.array(ha)), torch.FloatTensor(np.array(hb))
+        if dim == 2:
+            dd = torch.cat((ha.unsqueeze(2), hb.unsqueeze(2)), 1)                                       # model.py:424-430
+        else:
+            if heightmap_type != "diff":
+                ha, hb = ha.unsqueeze(1), hb.unsqueeze(1)
+            dd = torch.cat((ha, hb), 1)                                                                # model.py:431-441
+        out["ptr"].append(ptr.numpy().copy()); out["dec_dyn"].append(dd.numpy().reshape(B, -1).copy())
+        out["dec_static"].append(decoder_static.squeeze(2).numpy().copy())
+        out["hm_a"].append(np.stack([np.asarray(c.heightmap).reshape(-1).copy() for c in ca]))
+        out["hm_b"].append(np.stack([np.asarray(c.heightmap).reshape(-1).copy() for c in cb]))
+        out["cur_mask"].append(cur.numpy().copy()); out["mask"].append(mask.numpy().copy())
+    scores = torch.zeros(B)                                                                            # model.py:499-507
+    for b in range(B):
+        scores[b] += ca[b].calc_ratio()
+        scores[b] += cb[b].calc_ratio()
+        scores[b] /= 2.0
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["scores"] = scores.numpy().copy()
+    res["positions_a"] = np.stack([np.asarray(c.positions) for c in ca]); res["positions_b"] = np.stack([np.asarray(c.positions) for c in cb])
+    res["static"] = static.astype(np.uint8)
+    res["dynamic_final"] = np.packbits(dyn.numpy().reshape(B, -1).astype(np.uint8), axis=1)
+    return res
+
+
+def make_traj_mul():
+    from tests.golden_io import load_inputs
+    cases = [("traj_2d_mulwith_lbg", "rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", 64, "mul-with"),
+             ("traj_2d_mul_macs", "rand2d_n10.npz", [5, 50], "C+P+S-mul-hard", "zero", "MUL", 48, "mul"),
+             ("traj_3d_mulwith_lbg", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-hard", "diff", "LB_GREEDY", 32, "mul-with"),
+             ("traj_3d_mul_lbg_full", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "full", "LB_GREEDY", 24, "mul")]
+    for name, src, size, rt, hm, strat, num, it in cases:
+        t = time.time()
+        static, dynamic = load_inputs(os.path.join(HERE, src), num)
+        B, rows, S = static.shape
+        R = 2 if len(size) == 2 else 6
+        n = S // R
+        ids = np.random.RandomState(31).randint(0, 2, size=(B, 1, n)).astype(np.float32)             # container.txt row, pack.py:212-216
+        static = np.concatenate([static, np.tile(ids, (1, 1, R))], 1)
+        res = ref_trajectory_mul(static, dynamic, size, rt, hm, strat, seed=77, input_type=it)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), source=src, container_size=np.array(size), reward_type=rt,
+                            heightmap_type=hm, packing_strategy=strat, num=num, input_type=it, **res)
+        print(name, "%.1fs" % (time.time() - t), "mean score %.4f" % res["scores"].mean())
+
+
 def make_kat():
     """Known-answer vectors (G1-G4 sequences, doc/data.md, visual/draw_result.py),
     outputs re-derived here from the live reference."""
@@ -345,7 +426,7 @@ def make_kat():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj")
+    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj,mul")
     ap.add_argument("--ppsg-num", type=int, default=512)
     a = ap.parse_args()
     only = a.only.split(",")
@@ -358,3 +439,4 @@ if __name__ == "__main__":
         make_rolling(3, 512, "rolling3d_t50.npz")
         make_rolling(2, 256, "rolling2d_t50.npz")
     if "rolltraj" in only: make_rolling_traj()
+    if "mul" in only: make_traj_mul()

@@ -451,3 +451,62 @@ def test_packed_reset_scalar_path_and_errors():
         env.reset_packed(torch.from_numpy(su8).cuda(), torch.from_numpy(bits[:, :-1].copy()).cuda())
     with pytest.raises(ValueError):
         tapenv.pack_inputs(static, dynamic * 2)
+
+
+@pytest.mark.parametrize("name", ["traj_2d_mulwith_lbg", "traj_2d_mul_macs", "traj_3d_mulwith_lbg", "traj_3d_mul_lbg_full"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_two_container_inputs(name, fused):
+    """input_type 'mul' / 'mul-with' through tapenv_step_mul (fused) and update_dynamic + update_mask + tapenv_add_blocks_mul
+    (unfused) against the live-reference recording: both heightmaps after every step, cat(A,B) decoder input, decoder_static
+    rows, masks, dynamic, positions; scores bit-equal (fp32 accumulation of model.py:503-507)."""
+    torch = _torch()
+    import tapenv
+    t = load_traj(name)
+    num = int(t["num"])
+    it = str(t["input_type"])
+    static = t["static"].astype(np.float32)
+    _, dynamic = load_inputs(str(t["source"]), num)
+    size = t["container_size"].tolist()
+    dim = len(size)
+    n = static.shape[2] // (2 if dim == 2 else 6)
+    env = tapenv.BatchedContainerPairs(size, n, str(t["reward_type"]), str(t["heightmap_type"]),
+                                       packing_strategy=str(t["packing_strategy"]), batch_size=num, input_type=it)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    cur, mask = env.reset(dyn)
+    assert np.array_equal(cur.cpu().numpy(), t["cur_mask"][0])
+    for k in range(n):
+        ptr = torch.from_numpy(t["ptr"][k].astype(np.int64)).cuda()
+        if fused:
+            dyn, cur, mask, dec_static, dec_dyn = env.step(ptr, st, dyn, mask)
+        else:
+            dyn = tapenv.update_dynamic(dyn, st, ptr, it, True)
+            cur, mask = tapenv.update_mask(mask, dyn, st, ptr, it, True)
+            part = st[:, 1:-1] if it == "mul" else st[:, 1:]
+            dec_static = torch.gather(part, 2, ptr.view(-1, 1, 1).expand(-1, part.shape[1], 1)).squeeze(2)
+            tgt = torch.gather(st[:, -1], 1, ptr.view(-1, 1)).squeeze(1)
+            dec_dyn = env.add_new_blocks(dec_static[:, :dim].contiguous(), tgt)
+        assert np.array_equal(env.a.heightmap.cpu().numpy().reshape(num, -1), t["hm_a"][k]), k
+        assert np.array_equal(env.b.heightmap.cpu().numpy().reshape(num, -1), t["hm_b"][k]), k
+        assert np.array_equal(dec_dyn.cpu().numpy().reshape(num, -1), t["dec_dyn"][k]), k
+        assert np.array_equal(dec_static.cpu().numpy(), t["dec_static"][k]), k
+        assert np.array_equal(cur.cpu().numpy(), t["cur_mask"][k + 1]) and np.array_equal(mask.cpu().numpy(), t["mask"][k])
+    assert np.array_equal(env.a.positions.cpu().numpy(), t["positions_a"])
+    assert np.array_equal(env.b.positions.cpu().numpy(), t["positions_b"])
+    assert np.array_equal(env.calc_ratio().cpu().numpy(), t["scores"])
+    fin = np.unpackbits(t["dynamic_final"], axis=1)[:, :dynamic[0].size].reshape(dynamic.shape).astype(np.float32)
+    assert np.array_equal(dyn.cpu().numpy(), fin)
+    env.check_flags()
+    if dim == 3:
+        assert dec_dyn.shape == (num, 4 if str(t["heightmap_type"]) == "diff" else 2, size[0], size[1])
+
+
+def test_two_container_bad_target_id_is_flagged():
+    torch = _torch()
+    import tapenv
+    env = tapenv.BatchedContainerPairs([5, 50], 10, "C+P+S-lb-soft", "diff", batch_size=3, input_type="mul")
+    out = env.add_new_blocks(torch.tensor([[2., 2.], [1., 3.], [2., 1.]]).cuda(), torch.tensor([0., 1., 2.]).cuda())
+    assert out.shape == (3, 8)
+    assert env.a.flags.cpu().tolist() == [0, 0, 4] and env.b.flags.cpu().tolist() == [0, 0, 4]
+    assert env.a.heightmap.cpu().tolist()[0][:2] == [2, 2] and env.b.heightmap.cpu().tolist()[1][0] == 3
+    with pytest.raises(ValueError):
+        tapenv.BatchedContainerPairs([5, 50], 10, "C+P+S-lb-soft", "diff", batch_size=3, input_type="bot")

@@ -103,3 +103,25 @@ def test_oracle_replays_reference_trajectories(name):
     assert np.array_equal(eb["cur_mask"], r["cur_mask"][-1]) and np.array_equal(eb["mask"], r["mask"][-1])
     assert np.array_equal(eb["dynamic"], r["dynamic"][-1]) and np.array_equal(eb["dec_dyn"], r["dec_dyn"][-1])
     assert B == int(t["num"])
+
+
+MUL_TRAJ = ["traj_2d_mulwith_lbg", "traj_2d_mul_macs", "traj_3d_mulwith_lbg", "traj_3d_mul_lbg_full"]
+
+
+@pytest.mark.parametrize("name", MUL_TRAJ)
+def test_two_container_inputs_golden(name):
+    """input_type 'mul' / 'mul-with' (model.py:396-447, :499-507): the oracle's composition of two containers per
+    environment reproduces the live-reference recording -- both heightmaps per step, cat(A,B) decoder input, masks, fp32 scores."""
+    from tests.rollout import oracle_rollout_mul
+    t = load_traj(name)
+    num = int(t["num"])
+    static = t["static"].astype(np.float32)
+    _, dynamic = load_inputs(str(t["source"]), num)
+    o = oracle_rollout_mul(static, dynamic, t["ptr"], t["container_size"].tolist(), str(t["reward_type"]),
+                           str(t["heightmap_type"]), str(t["packing_strategy"]), str(t["input_type"]))
+    for k in ("hm_a", "hm_b", "cur_mask", "mask", "dec_static", "positions_a", "positions_b"):
+        assert np.array_equal(o[k], t[k]), k
+    assert np.array_equal(o["dec_dyn"].astype(np.float32), t["dec_dyn"])
+    assert np.array_equal(o["scores"], t["scores"])
+    fin = np.unpackbits(t["dynamic_final"], axis=1)[:, :dynamic[0].size].reshape(dynamic.shape).astype(np.float32)
+    assert np.array_equal(o["dynamic"][-1], fin)
