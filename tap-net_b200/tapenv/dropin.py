@@ -7,15 +7,17 @@
     tapenv.uninstall()
 
 Replaces exactly the hot-path symbols: pack.update_dynamic, pack.update_mask, pack.reward,
-tools.Container, tools.calc_positions_lb_greedy.  Everything else of the reference keeps running as it is."""
+tools.Container, tools.calc_positions_lb_greedy (and generate.InitialContainer when `generate` is passed).  Everything else of the reference keeps running as it is."""
 import sys
 
-from . import containers, episode, ops
+from . import containers, episode, ops, rolling
 
 _saved = []
 
 
-def install(pack=None, tools=None):
+def install(pack=None, tools=None, generate=None):
+    """generate: the reference's `generate` module -- also replaces generate.InitialContainer (the rolling window,
+    rolling.py:501) by the GPU-backed per-instance class."""
     pack = pack if pack is not None else sys.modules.get("pack")
     tools = tools if tools is not None else sys.modules.get("tools")
     if pack is None and tools is None:
@@ -27,6 +29,8 @@ def install(pack=None, tools=None):
     if tools is not None:
         repl += [(tools, "Container", containers.Container),
                  (tools, "calc_positions_lb_greedy", episode.calc_positions_lb_greedy)]
+    if generate is not None:
+        repl += [(generate, "InitialContainer", rolling.InitialContainer)]
     for mod, name, new in repl:
         _saved.append((mod, name, getattr(mod, name, None)))
         setattr(mod, name, new)

@@ -432,3 +432,49 @@ class RollingDataset(object):
         else:
             self.decoder_dynamic = torch.zeros(1, hm_num, int(hm_w), int(hm_w), requires_grad=True)
         self.num_samples = N
+
+
+class InitialContainer(object):
+    """generate.InitialContainer with the reference's constructor and call protocol (generate.py:1589-1825), for an
+    UNMODIFIED rolling.py (`generate.InitialContainer = tapenv.rolling.InitialContainer`, or tapenv.install(generate=...)):
+    one instance per object, NumPy in / NumPy out, the window logic on the GPU (batch of one).  rolling.validate walks
+    the instances one by one, so this keeps its structure; the batched classes above are the fast path."""
+
+    def __init__(self, blocks, positions, blocks_num, initial_container_size, allow_bot, child_graph_size,
+                 input_type="bot", device=None, node_order=_capi.WINDOW_ORDER_REFERENCE):
+        blocks = np.asarray(blocks).astype(np.int64)
+        positions = np.asarray(positions).astype(np.int64)
+        T, dim = int(blocks_num), len(initial_container_size)
+        self.input_type, self.block_dim, self.blocks_num = input_type, dim, T
+        self.rotate_types = math.factorial(dim)
+        self.blocks, self.positions = blocks, positions
+        self.all_bot, self.child_graph_size = allow_bot, int(child_graph_size)
+        adj = calc_dependent(blocks[:T], positions, initial_container_size)          # generate.py:1619
+        if not allow_bot:
+            adj[1:] = False                                                          # rotation graphs stay empty (:1641)
+        self.deps = adj
+        self._batch = BatchedInitialContainers(adj[None], blocks[None].astype(np.int32), T, child_graph_size, dim,
+                                               device=device, node_order=node_order, input_type=input_type)
+        self.sub_graph_nodes = []
+        self._remaining = T
+
+    def convert_to_input(self):
+        static, dynamic = self._batch.convert_to_input()
+        nodes = self._batch.sub_graph_nodes[0].cpu().numpy()
+        self.sub_graph_nodes = [int(v) for v in nodes if v >= 0]
+        self._remaining = int(self._batch.remaining[0].item())
+        if len(self.sub_graph_nodes) != self.child_graph_size:
+            raise ValueError("all the input array dimensions ... must match exactly (window of %d nodes, %d expected)"
+                             % (len(self.sub_graph_nodes), self.child_graph_size))   # np.concatenate, generate.py:1788
+        return static[0].cpu().numpy().astype(np.int64), dynamic[0].cpu().numpy().astype(np.float64)
+
+    def remove_block(self, block_id):
+        try:
+            idx = self.sub_graph_nodes.index(int(block_id))
+        except ValueError:
+            return                                                                   # generate.py:1819-1821: silently ignored
+        self._batch.remove_block(torch.tensor([idx], dtype=torch.int64, device=self._batch.device))
+        self.sub_graph_nodes.remove(int(block_id))
+
+    def is_last_graph(self):
+        return self._remaining == 0

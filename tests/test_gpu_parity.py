@@ -510,3 +510,46 @@ def test_two_container_bad_target_id_is_flagged():
     assert env.a.heightmap.cpu().tolist()[0][:2] == [2, 2] and env.b.heightmap.cpu().tolist()[1][0] == 3
     with pytest.raises(ValueError):
         tapenv.BatchedContainerPairs([5, 50], 10, "C+P+S-lb-soft", "diff", batch_size=3, input_type="bot")
+
+
+def _synthetic_inputs(rng, B, n, dim, max_edge, density):
+    """Random well-formed TAP inputs of an arbitrary shape: static rows as PACKDataset lays them out (block id, edge
+    lengths per rotation = permutations of the block's edges), dynamic = sparse 0/1 precedence bands."""
+    import itertools
+    R = 2 if dim == 2 else 6
+    S = n * R
+    edges = rng.randint(1, max_edge + 1, size=(B, n, dim))
+    static = np.zeros((B, 1 + dim, S), np.float32)
+    for r, p in enumerate(itertools.permutations(range(dim))):
+        static[:, 0, r * n:(r + 1) * n] = np.arange(n)
+        for d in range(dim):
+            static[:, 1 + d, r * n:(r + 1) * n] = edges[:, :, p[d]]
+    dynamic = (rng.random_sample((B, 3 * n, S)) < density).astype(np.float32)
+    return static, dynamic
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_fuzz(seed):
+    """Generic (not compile-time specialised) shapes: random n, container width/length, heightmap encoding, reward type and
+    strategy; S % 4 != 0 takes the scalar tensor path.  Every step bit-exact against the oracle."""
+    rng = np.random.RandomState(1000 + seed)
+    dim = 2 if seed % 3 else 3
+    if dim == 2:
+        n = int(rng.randint(2, 25))
+        size = [int(rng.randint(2, 17)), 400]
+        strat = ["LB_GREEDY", "MACS", "LB_GREEDY", "LB"][seed % 4]
+    else:
+        n = int(rng.randint(2, 11))
+        W = int(rng.randint(2, 7)); L = int(rng.randint(2, min(7, 32 // W + 1)))
+        size = [W, L, 400]
+        strat = ["LB_GREEDY", "LB"][seed % 2]
+    if strat == "MACS":
+        rt = ["C+P+S-mcs-soft", "C+P+S-mcs-hard", "C+P-mcs-soft", "mcs-hard"][int(rng.randint(4))]
+    else:
+        rt = ["C+P+S-lb-soft", "C+P+S-lb-hard", "C+P-lb-soft", "C+P-lb-hard"][int(rng.randint(4))]
+    hm = ["full", "zero", "diff"][int(rng.randint(3))]
+    B = int(rng.randint(1, 70))
+    static, dynamic = _synthetic_inputs(rng, B, n, dim, max_edge=min(5, max(size[:-1])), density=0.06)
+    r = oracle_rollout(static, dynamic, size, rt, hm, strat, seed=seed)
+    g = gpu_rollout(static, dynamic, r["ptr"], size, rt, hm, strat, fused=bool(seed % 2) or strat == "LB")
+    assert_same(g, r, r["ptr"], static, dim)

@@ -225,3 +225,34 @@ def test_blocks_without_rotation_structure_take_the_generic_path():
     want = torch.gather(static[:, 1:], 2, ptr.view(-1, 1, 1).expand(-1, dim, 1)).squeeze(2).clone()
     _, _, _, dec_static, _ = run.step(ptr)
     assert torch.equal(dec_static, want)
+
+
+def test_per_instance_initial_container_protocol():
+    """tapenv.rolling.InitialContainer: the reference's constructor (blocks, positions, ...) and the three calls of
+    rolling.validate (rolling.py:593-640), NumPy in / NumPy out, against the oracle driven the same way; the graphs
+    come from tapenv.rolling.calc_dependent."""
+    from tapenv.rolling import InitialContainer
+    data = load_rolling("rolling3d_t50.npz", 3)
+    T, n, dim = 50, 10, 3
+    rng = np.random.RandomState(2)
+    for b in range(3):
+        ic = InitialContainer(data["blocks"][b], data["positions"][b], T, [7, 7, 250], True, n, "bot")
+        assert np.array_equal(ic.deps.astype(np.uint8), data["adj"][b])
+        oc = oracle.InitialContainer(data["adj"][b], data["blocks"][b], T, n, dim)
+        steps = 0
+        while True:
+            static, dynamic = ic.convert_to_input()
+            s_ref, d_ref = oc.convert_to_input()
+            assert static.dtype == np.int64 and dynamic.dtype == np.float64
+            assert np.array_equal(static, s_ref) and np.array_equal(dynamic, d_ref)
+            assert ic.sub_graph_nodes == oc.sub_graph_nodes and ic.is_last_graph() == oc.is_last_graph()
+            if ic.is_last_graph():
+                break
+            ptr = int(rng.randint(n * 6))
+            while ptr >= n:
+                ptr -= n
+            bid = ic.sub_graph_nodes[ptr]
+            ic.remove_block(bid); oc.remove_block(bid)
+            ic.remove_block(999)                                # unknown id: ignored like the reference's try/except
+            steps += 1
+        assert steps == T - n
