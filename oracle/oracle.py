@@ -58,6 +58,8 @@ def lib():
         for name in ("heightmap", "positions", "container", "stable"):
             getattr(L, "tapo_env_" + name).argtypes = [p]
             getattr(L, "tapo_env_" + name).restype = p
+        L.tapo_env_lfs3.argtypes = [p, C.c_int, C.c_int, p]
+        L.tapo_env_lfs3.restype = C.c_int
         L.tapo_env_lfs.argtypes = [p, C.c_int, p]
         L.tapo_env_lfs.restype = C.c_int
         L.tapo_update_dynamic.argtypes = [p, p, p] + [C.c_int] * 6 + [p]
@@ -196,6 +198,14 @@ class Container(object):
     def level_free_space(self):
         out = np.zeros(64, dtype=np.int32)
         res = []
+        if self.block_dim == 3:                  # [z][y] -> x interval list (tools.py:3644-3648)
+            for z in range(self._H):
+                row = []
+                for y in range(self._L):
+                    n = lib().tapo_env_lfs3(self._h, z, y, _ptr(out))
+                    row.append(out[:n].tolist())
+                res.append(row)
+            return res
         for z in range(self._H):
             n = lib().tapo_env_lfs(self._h, z, _ptr(out))
             res.append(out[:n].tolist())

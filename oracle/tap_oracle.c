@@ -53,6 +53,7 @@ typedef struct tapo_env {
     long long valid, empty; /* tools.py:3635-3636 */
     int k;            /* current_blocks_num tools.py:3653 */
     ilist *lfs;       /* [H] MACS 2D level_free_space tools.py:3641-3643 */
+    ilist *lfs3;      /* [H][L] MACS 3D level_free_space tools.py:3644-3648, every row [0, W-1] */
     xlist *lbl;       /* LB: [H] (2D) or [H][L] (3D) level_free_space tools.py:3649-3653, initial [0] */
     int error;        /* sticky: 1 = numpy would have raised IndexError, 2 = limits */
 } tapo_env;
@@ -88,6 +89,9 @@ void tapo_env_clear(tapo_env *e) {
             e->lfs[z].len = 2; e->lfs[z].v[0] = 0; e->lfs[z].v[1] = e->W - 1;
         }
     }
+    if (e->lfs3) {
+        for (int i = 0; i < e->H * e->L; i++) { e->lfs3[i].len = 2; e->lfs3[i].v[0] = 0; e->lfs3[i].v[1] = e->W - 1; }
+    }
     if (e->lbl) {
         int cnt = e->dim == 2 ? e->H : e->H * e->L;
         for (int i = 0; i < cnt; i++) { e->lbl[i].len = 1; e->lbl[i].v[0] = 0; }
@@ -114,6 +118,8 @@ tapo_env *tapo_env_new(int dim, int W, int L, int H, int n, const char *reward_t
     e->stable = (unsigned char *)malloc(n);
     e->lfs = NULL;
     if (strategy == TAPO_MACS && dim == 2) e->lfs = (ilist *)malloc(sizeof(ilist) * H);
+    e->lfs3 = NULL;
+    if (strategy == TAPO_MACS && dim == 3) e->lfs3 = (ilist *)malloc(sizeof(ilist) * (size_t)H * e->L);
     e->lbl = NULL;
     if (strategy == TAPO_LB) e->lbl = (xlist *)malloc(sizeof(xlist) * (size_t)H * (dim == 2 ? 1 : e->L));
     tapo_env_clear(e);
@@ -123,7 +129,7 @@ tapo_env *tapo_env_new(int dim, int W, int L, int H, int n, const char *reward_t
 void tapo_env_free(tapo_env *e) {
     if (!e) return;
     free(e->container); free(e->heightmap); free(e->positions); free(e->blocks);
-    free(e->stable); free(e->lfs); free(e->lbl); free(e);
+    free(e->stable); free(e->lfs); free(e->lfs3); free(e->lbl); free(e);
 }
 
 /* ------------------------------------------------------------------ */
@@ -706,6 +712,375 @@ static void macs_step_2d(tapo_env *e) {
     e->valid = valid;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* tools.py:2751-3165 calc_one_position_mcs_3d -- LITERAL, including
+ *   - the read of a loop variable that is stale at that point of the Python source (`x1` at :2869),
+ *   - numpy's slice clipping / empty-slice semantics ((empty == 0).all() is True),
+ *   - the z (not z+zz) written into the EMS found on top of a partly covered block (:2939-2940),
+ *   - the `_z + block_x` height typo (:2976), the shared `visited` list, phantom (0,0,0) positions of unplaced blocks.
+ * e->error = 1 where the reference would raise (IndexError / UnboundLocalError). */
+#define M3_MAX_EMS 8192
+typedef struct { int v[6]; } ems6;
+#define C3(x, y, z) c[(((x) * L + (y)) * H) + (z)]
+
+/* (container[xa:xb, y, z] == 0).all() with Python slice semantics on the x axis */
+static int m3_row_free(const int *c, int W, int L, int H, int xa, int xb, int y, int z) {
+    if (xb > W) xb = W;
+    for (int x = xa; x < xb; x++) if (C3(x, y, z) != 0) return 0;
+    return 1;
+}
+static int m3_has(const ems6 *l, int n, int a, int b, int cc, int d, int e_, int f) {
+    for (int i = 0; i < n; i++) if (l[i].v[0] == a && l[i].v[1] == b && l[i].v[2] == cc && l[i].v[3] == d && l[i].v[4] == e_ && l[i].v[5] == f) return 1;
+    return 0;
+}
+#define M3_PUSH(a, b, cc, d, e_, f) do { if (ne >= M3_MAX_EMS) { e->error = 2; return; } ems[ne].v[0] = (a); ems[ne].v[1] = (b); ems[ne].v[2] = (cc); ems[ne].v[3] = (d); ems[ne].v[4] = (e_); ems[ne].v[5] = (f); ne++; } while (0)
+
+/* one row of update_level_free_space, levels _z .. _z+bz-1 (:3000-3024) */
+static void m3_lfs_occupy(ilist *fs, int _x, int xx, int bx, int *err) {
+    int idx = il_index(fs, _x);
+    if (idx >= 0) {
+        if ((idx + 1) % 2 == 1) {
+            if (il_index(fs, xx) >= 0) {
+                if (bx == 1) {
+                    if (idx + 1 < fs->len && fs->v[idx + 1] == _x) { il_remove(fs, _x); il_remove(fs, _x); }
+                    else fs->v[idx] = _x + 1;
+                } else { il_remove(fs, _x); il_remove(fs, xx); }
+            } else fs->v[idx] = xx + 1;
+        } else fs->v[idx] = _x - 1;
+    } else {
+        int ix = il_index(fs, xx);
+        if (ix >= 0) fs->v[ix] = _x - 1;
+        else {
+            if (fs->len + 2 > TAPO_MAXW + 4) { *err = 2; return; }
+            fs->v[fs->len++] = _x - 1; fs->v[fs->len++] = xx + 1; il_sort(fs);
+        }
+    }
+}
+/* one row of the levels below the block, 0 .. _z-1 (:3026-3042) */
+static void m3_lfs_under(ilist *fs, int _x, int xx, int bx) {
+    ilist snap = *fs;                                      /* `spaces` is built before editing */
+    for (int s = 0; s + 1 < snap.len; s += 2) {
+        int x1 = snap.v[s], x2 = snap.v[s + 1];
+        if (x1 == x2) {
+            if (x1 >= _x && x1 <= xx) { il_remove(fs, x1); il_remove(fs, x1); }
+        } else if (bx == 1) {
+            if (_x == x1) { int i = il_index(fs, x1); if (i >= 0) fs->v[i] = _x + 1; }
+            else if (_x == x2) { int i = il_index(fs, x2); if (i >= 0) fs->v[i] = xx - 1; }
+        } else if (_x <= x1 && x2 <= xx) { il_remove(fs, x1); il_remove(fs, x2); }
+        else if (_x <= x1 && x1 <= xx) { int i = il_index(fs, x1); if (i >= 0) fs->v[i] = xx + 1; }
+        else if (_x <= x2 && x2 <= xx) { int i = il_index(fs, x2); if (i >= 0) fs->v[i] = _x - 1; }
+    }
+}
+
+/* calc_maximal_usable_spaces(ctn, Hlim) :3052-3080: per level the largest histogram rectangle of empty cells among the
+ * scanned anchors; `ctn` = container with the candidate block written in (update_container :3046-3050) */
+static long long m3_usable(const int *c, int W, int L, int H, int Hlim) {
+    static __thread int hist[TAPO_MAXW][TAPO_MAXW];
+    long long score = 0;
+    for (int hh = 0; hh < Hlim; hh++) {
+        int level_max = 0;
+        for (int i = W - 1; i >= 0; i--)
+            for (int j = 0; j < L; j++) {
+                int hot = C3(i, j, hh) == 0;
+                if (i == W - 1) hist[i][j] = hot;
+                else if (!hot) hist[i][j] = 0;
+                else hist[i][j] = hist[i + 1][j] + hot;
+            }
+        for (int i = 0; i < W; i++)
+            for (int j = 0; j < L; j++) {
+                if (hist[i][j] == 0) continue;
+                if (j > 0 && hist[i][j] == hist[i][j - 1]) continue;
+                int j2, j1;
+                for (j2 = j; j2 < L; j2++) { if (j2 == L - 1) break; if (hist[i][j2 + 1] < hist[i][j]) break; }
+                for (j1 = j; j1 >= 0; j1--) { if (j1 == 0) break; if (hist[i][j1 - 1] < hist[i][j]) break; }
+                int area = hist[i][j] * (j2 - j1 + 1);
+                if (area > level_max) level_max = area;
+            }
+        score += level_max;
+    }
+    return score;
+}
+
+static void macs_step_3d(tapo_env *e) {
+    const int W = e->W, L = e->L, H = e->H, k = e->k;
+    int *h = e->heightmap, *c = e->container;
+    ilist *lfs = e->lfs3;
+    const int bx = e->blocks[k * 3], by = e->blocks[k * 3 + 1], bz = e->blocks[k * 3 + 2];
+    long long valid = e->valid + (long long)bx * by * bz;  /* :2806 */
+    static __thread ems6 ems[M3_MAX_EMS]; int ne = 0;
+    /* Python function-scope loop variables that outlive their loops */
+    int x1 = 0, x2 = 0, y1 = 0, y2 = 0, x1_bound = 0;
+
+    /* ---- EMS from level_free_space :2810-2838 ---- */
+    for (int z = 0; z < H; z++) {
+        const ilist *fsx = &lfs[z * L];
+        if (z + bz > H) break;
+        else if (z > 0) { int same = 1; for (int y = 0; y < L; y++) if (!il_eq(&lfs[(z - 1) * L + y], &fsx[y])) { same = 0; break; } if (same) continue; }
+        for (int y = 0; y < L; y++) {
+            const ilist *fs = &fsx[y];
+            if (y + by > L) break;
+            else if (y > 0 && il_eq(&fsx[y - 1], fs)) continue;
+            for (int s = 0; s + 1 < fs->len; s += 2) {
+                x1 = fs->v[s]; x2 = fs->v[s + 1]; x1_bound = 1;
+                if (x1 + bx > W) break;
+                if (y > 0) {
+                    int idx = il_index(&fsx[y - 1], x1);
+                    if (idx >= 0) { idx += 1; if (idx % 2 == 1 && idx < fsx[y - 1].len && x2 == fsx[y - 1].v[idx]) continue; }
+                }
+                if (z > 0) {
+                    const ilist *lo = &lfs[(z - 1) * L + y];
+                    int idx = il_index(lo, x1);
+                    if (idx >= 0) { idx += 1; if (idx % 2 == 1 && idx < lo->len && x2 == lo->v[idx]) continue; }
+                }
+                int xspace = 1;
+                for (y2 = y; y2 < L; y2++) {
+                    if (y2 == L - 1) break;
+                    if (!m3_row_free(c, W, L, H, x1, x2 + 1, y2 + 1, z)) break;
+                    if (xspace && !(il_index(&fsx[y2 + 1], x1) >= 0 && il_index(&fsx[y2 + 1], x2) >= 0)) {
+                        xspace = 0;                        /* next to settled blocks along the x axis */
+                        M3_PUSH(x1, y, z, x2, y2, z);
+                    }
+                }
+                M3_PUSH(x1, y, z, x2, y2, z);
+            }
+        }
+    }
+
+    /* ---- EMS next to the settled blocks :2841-2940 (every previous block, unplaced ones at their phantom (0,0,0)) ---- */
+    for (int b = 0; b < k; b++) {
+        const int x = e->positions[b * 3], y = e->positions[b * 3 + 1], z = e->positions[b * 3 + 2];
+        const int xx = e->blocks[b * 3], yy = e->blocks[b * 3 + 1], zz = e->blocks[b * 3 + 2];
+        if (z >= H) { e->error = 1; return; }
+        /* upon along the y axis */
+        if (y + yy < L) {
+            if (m3_row_free(c, W, L, H, x, x + xx, y + yy, z)) {                       /* full */
+                if ((x > 0 && C3(x - 1, y + yy, z) == 0) || (x + xx < W && C3(x + xx, y + yy, z) == 0)) {
+                    for (y2 = y + yy; y2 < L; y2++) { if (y2 == L - 1) break; if (!m3_row_free(c, W, L, H, x, x + xx, y2 + 1, z)) break; }
+                    M3_PUSH(x, y + yy, z, x + xx - 1, y2, z);
+                }
+            } else {                                                                  /* part */
+                if (x + xx > W) { e->error = 1; return; }                             /* container[x+xx-1, ...] below would raise */
+                if (C3(x, y + yy, z) == 0) {                                          /* left */
+                    if (x > 0 && C3(x - 1, y + yy, z) == 0) {
+                        for (x2 = x; x2 < x + xx; x2++) { if (x2 == W - 1) break; if (C3(x2 + 1, y + yy, z) != 0) break; }
+                        if (x2 == x + xx) x2 = x + xx - 1;                             /* loop ran to completion */
+                        if (!x1_bound) { e->error = 1; return; }                      /* UnboundLocalError */
+                        for (y2 = y + yy; y2 < L; y2++) { if (y2 == L - 1) break; if (!m3_row_free(c, W, L, H, x1 /* stale, :2869 */, x2 + 1, y2 + 1, z)) break; }
+                        M3_PUSH(x, y + yy, z, x2, y2, z);
+                    }
+                }
+                if (C3(x + xx - 1, y + yy, z) == 0) {                                 /* right */
+                    if (x + xx < W && C3(x + xx, y + yy, z) == 0) {
+                        for (x1 = x + xx - 1; x1 >= x; x1--) { if (x1 == 0) break; if (C3(x1 - 1, y + yy, z) != 0) break; }
+                        if (x1 < x) x1 = x;
+                        x1_bound = 1;
+                        for (y2 = y + yy; y2 < L; y2++) { if (y2 == L - 1) break; if (!m3_row_free(c, W, L, H, x1, x + xx, y2 + 1, z)) break; }
+                        M3_PUSH(x1, y + yy, z, x + xx - 1, y2, z);
+                    }
+                }
+            }
+        }
+        /* under along the y axis */
+        if (y > 0) {
+            if (m3_row_free(c, W, L, H, x, x + xx, y - 1, z)) {                        /* full */
+                if ((x > 0 && C3(x - 1, y - 1, z) == 0) || (x + xx < W && C3(x + xx, y - 1, z) == 0)) {
+                    for (y1 = y - 1; y1 >= 0; y1--) { if (y1 == 0) break; if (!m3_row_free(c, W, L, H, x, x + xx, y1 - 1, z)) break; }
+                    M3_PUSH(x, y1, z, x + xx - 1, y - 1, z);
+                }
+            } else {
+                if (x + xx > W) { e->error = 1; return; }
+                if (C3(x, y - 1, z) == 0) {                                           /* left */
+                    if (x > 0 && C3(x - 1, y - 1, z) == 0) {
+                        for (x2 = x; x2 < x + xx; x2++) { if (x2 == W - 1) break; if (C3(x2 + 1, y - 1, z) != 0) break; }
+                        if (x2 == x + xx) x2 = x + xx - 1;
+                        for (y1 = y - 1; y1 >= 0; y1--) { if (y1 == 0) break; if (!m3_row_free(c, W, L, H, x, x2 + 1, y1 - 1, z)) break; }
+                        M3_PUSH(x, y1, z, x2, y - 1, z);
+                    }
+                }
+                if (C3(x + xx - 1, y - 1, z) == 0) {                                  /* right */
+                    if (x + xx < W && C3(x + xx, y - 1, z) == 0) {
+                        for (x1 = x + xx - 1; x1 >= x; x1--) { if (x1 == 0) break; if (C3(x1 - 1, y - 1, z) != 0) break; }
+                        if (x1 < x) x1 = x;
+                        x1_bound = 1;
+                        for (y1 = y - 1; y1 >= 0; y1--) { if (y1 == 0) break; if (!m3_row_free(c, W, L, H, x1, x + xx, y1 - 1, z)) break; }
+                        M3_PUSH(x1, y1, z, x + xx - 1, y - 1, z);
+                    }
+                }
+            }
+        }
+        /* upon along the z axis (top) */
+        if (z + zz < H) {
+            const int t = z + zz;
+            int full = 1;
+            for (int q = x; q < x + xx && q < W && full; q++) for (int r = y; r < y + yy && r < L; r++) if (C3(q, r, t) != 0) { full = 0; break; }
+            if (full) {
+                if (!m3_has(ems, ne, x, y, t, x + xx - 1, y + yy - 1, t)) M3_PUSH(x, y, t, x + xx - 1, y + yy - 1, t);
+            } else {
+                if (x + xx > W || y + yy > L) { e->error = 1; return; }               /* hotmap is clipped, histmap[i, j] raises */
+                static __thread int hot[TAPO_MAXW][TAPO_MAXW], hist[TAPO_MAXW][TAPO_MAXW];
+                for (int i = 0; i < xx; i++) for (int j = 0; j < yy; j++) hot[i][j] = C3(x + i, y + j, t) == 0;
+                for (int i = xx - 1; i >= 0; i--)
+                    for (int j = 0; j < yy; j++) {
+                        if (i == xx - 1) hist[i][j] = hot[i][j];
+                        else if (hot[i][j] == 0) hist[i][j] = 0;
+                        else hist[i][j] = hist[i + 1][j] + hot[i][j];
+                    }
+                for (int i = 0; i < xx; i++)
+                    for (int j = 0; j < yy; j++) {
+                        if (hist[i][j] == 0) continue;
+                        if (j > 0 && hist[i][j] == hist[i][j - 1]) continue;
+                        if (i > 0) { int eq = 1; for (int r = y + j; r < y + yy; r++) if (C3(x + i, r, t) != C3(x + i - 1, r, t)) { eq = 0; break; } if (eq) continue; }
+                        int i2 = i + hist[i][j] - 1, j2, j1;
+                        for (j2 = j; j2 < yy; j2++) { if (j2 == yy - 1) break; if (hist[i][j2 + 1] < hist[i][j]) break; }
+                        if (i > 0) { int eq = 1; for (int r = y + j; r < y + j2; r++) if (C3(x + i, r, t) != C3(x + i - 1, r, t)) { eq = 0; break; } if (eq) continue; }   /* empty slice when j2 == j */
+                        for (j1 = j; j1 >= 0; j1--) { if (j1 == 0) break; if (hist[i][j1 - 1] < hist[i][j]) break; }
+                        if (!m3_has(ems, ne, x + i, y + j1, z, x + i2, y + j2, z)) M3_PUSH(x + i, y + j1, z /* sic */, x + i2, y + j2, z);
+                    }
+            }
+        }
+    }
+
+    /* ---- candidates: four corners per EMS :2943-3126 ---- */
+    const int nc = ne * 4;
+    static __thread int pos[4 * M3_MAX_EMS][3]; static __thread unsigned char settle[4 * M3_MAX_EMS], stab[4 * M3_MAX_EMS], tried[4 * M3_MAX_EMS];
+    static __thread double comp[4 * M3_MAX_EMS], pyr[4 * M3_MAX_EMS], stb[4 * M3_MAX_EMS]; static __thread long long empty_ems[4 * M3_MAX_EMS];
+    static __thread int hmmax[4 * M3_MAX_EMS];
+    static __thread int visited[1 << 16][3]; int nv = 0;
+    for (int i = 0; i < nc; i++) { settle[i] = stab[i] = tried[i] = 0; comp[i] = pyr[i] = stb[i] = 0.0; empty_ems[i] = e->empty; pos[i][0] = pos[i][1] = pos[i][2] = 0; hmmax[i] = 0; }
+    int hmax0 = 0; for (int q = 0; q < W * L; q++) if (h[q] > hmax0) hmax0 = h[q];
+    const int X = W - bx + 1, Y = L - by + 1;
+    int nsettled = 0;
+    for (int ei = 0; ei < ne; ei++) {
+        const int X1 = ems[ei].v[0], Y1 = ems[ei].v[1], Z = ems[ei].v[2], X2 = ems[ei].v[3], Y2 = ems[ei].v[4];
+        for (int corner = 0; corner < 4; corner++) {
+            const int index = ei * 4 + corner;
+            const int xr = X2 - bx + 2, yr = Y2 - by + 2;    /* reversed(range(0, xr)) / reversed(range(0, yr)) */
+            int ok;
+            if (corner == 0) ok = X1 < X && Y1 < Y;
+            else if (corner == 1) ok = xr > 0 && Y1 < Y;
+            else if (corner == 2) ok = xr > 0 && yr > 0;
+            else ok = X1 < X && yr > 0;
+            if (!ok) continue;
+            tried[index] = 1; hmmax[index] = hmax0;         /* heightmap.copy() */
+            /* itertools.product order: corner 0 (x asc, y asc), 1 (y asc, x desc), 2 (x desc, y desc), 3 (y desc, x asc) */
+            const int na = (corner == 0) ? (X - X1) : (corner == 1) ? (Y - Y1) : (corner == 2) ? xr : yr;
+            const int nb = (corner == 0) ? (Y - Y1) : (corner == 1) ? xr : (corner == 2) ? yr : (X - X1);
+            for (int ia = 0; ia < na && !settle[index]; ia++) {
+                for (int ib = 0; ib < nb && !settle[index]; ib++) {
+                    int _x, _y;
+                    if (corner == 0) { _x = X1 + ia; _y = Y1 + ib; }
+                    else if (corner == 1) { _y = Y1 + ia; _x = xr - 1 - ib; }
+                    else if (corner == 2) { _x = xr - 1 - ia; _y = yr - 1 - ib; }
+                    else { _y = yr - 1 - ia; _x = X1 + ib; }
+                    /* check_position :2955-2968 */
+                    int seen = 0;
+                    for (int v = 0; v < nv; v++) if (visited[v][0] == _x && visited[v][1] == _y && visited[v][2] == Z) { seen = 1; break; }
+                    if (seen) continue;
+                    if (_x < 0 || _y < 0) { e->error = 1; return; }
+                    const int xe = _x + bx < W ? _x + bx : W, ye = _y + by < L ? _y + by : L;
+                    if (Z > 0) {
+                        if (Z - 1 >= H) { e->error = 1; return; }
+                        int allz = 1;
+                        for (int q = _x; q < xe && allz; q++) for (int r = _y; r < ye; r++) if (C3(q, r, Z - 1) != 0) { allz = 0; break; }
+                        if (allz) continue;
+                    }
+                    if (nv >= (1 << 16)) { e->error = 2; return; }
+                    visited[nv][0] = _x; visited[nv][1] = _y; visited[nv][2] = Z; nv++;
+                    int freeall = 1;
+                    for (int q = _x; q < xe && freeall; q++) for (int r = _y; r < ye && freeall; r++) for (int t = Z; t < Z + bz && t < H; t++) if (C3(q, r, t) != 0) { freeall = 0; break; }
+                    if (!freeall) continue;
+                    if (xe - _x != bx || ye - _y != by) { e->error = 1; return; }     /* is_stable would index outside the container */
+                    if (!is_stable_3d(e, bx, by, _x, _y, Z)) { if (e->hard) continue; }
+                    else stab[index] = 1;
+                    pos[index][0] = _x; pos[index][1] = _y; pos[index][2] = Z; settle[index] = 1;
+                }
+            }
+            if (settle[index]) {                            /* calc_C_P_S :2971-2987 */
+                nsettled++;
+                const int _x = pos[index][0], _y = pos[index][1], _z = pos[index][2];
+                int height = 0;
+                for (int q = 0; q < W; q++) for (int r = 0; r < L; r++) {
+                    int hv = (q >= _x && q < _x + bx && r >= _y && r < _y + by) ? _z + bz : h[q * L + r];
+                    if (hv > height) height = hv;
+                }
+                hmmax[index] = height;
+                if (_z + bx > height) height = _z + bz;     /* sic :2976 */
+                const long long bbox = (long long)height * W * L;
+                comp[index] = (double)valid / (double)bbox;
+                long long cnt = 0; const int zlim = _z < H ? _z : H;
+                for (int q = _x; q < _x + bx; q++) for (int r = _y; r < _y + by; r++) for (int t = 0; t < zlim; t++) if (C3(q, r, t) == 0) cnt++;
+                empty_ems[index] += cnt;
+                if (e->useP) pyr[index] = (double)valid / (double)(empty_ems[index] + valid);
+                if (e->useS) {
+                    int sn = 0; for (int q = 0; q < k; q++) sn += e->stable[q];
+                    sn += stab[index];
+                    stb[index] = (double)sn / (double)(k + 1);
+                }
+            }
+        }
+    }
+    if (nsettled == 0) { e->stable[k] = 0; return; }        /* :3129-3132 */
+
+    /* ---- choose :3135-3158 ---- */
+    static __thread double ratio[4 * M3_MAX_EMS];
+    for (int i = 0; i < nc; i++) ratio[i] = e->mcs_start ? 0.0 : (comp[i] + pyr[i]) + stb[i];
+    double best_score = ratio[0]; for (int i = 1; i < nc; i++) if (ratio[i] > best_score) best_score = ratio[i];
+    static __thread int cands[4 * M3_MAX_EMS]; int ncand = 0;
+    for (int i = 0; i < nc; i++) if (ratio[i] == best_score) cands[ncand++] = i;
+    int best_index;
+    if (ncand > 1 && e->mcs_in) {
+        int max_height = 0; for (int i = 0; i < nc; i++) if (hmmax[i] > max_height) max_height = hmmax[i];   /* np.max(heightmap_ems) */
+        if (max_height > H) { e->error = 1; return; }
+        static __thread long long mus[4 * M3_MAX_EMS];
+        int *tmp = (int *)malloc(sizeof(int) * (size_t)W * L * H);
+        for (int i = 0; i < ncand; i++) {
+            mus[i] = 0;
+            if (settle[cands[i]]) {
+                memcpy(tmp, c, sizeof(int) * (size_t)W * L * H);
+                const int _x = pos[cands[i]][0], _y = pos[cands[i]][1], _z = pos[cands[i]][2];
+                for (int q = _x; q < _x + bx; q++) for (int r = _y; r < _y + by; r++) {         /* update_container :3046-3050 */
+                    for (int t = _z; t < _z + bz && t < H; t++) tmp[((q * L + r) * H) + t] = k + 1;
+                    for (int t = 0; t < _z && t < H; t++) if (tmp[((q * L + r) * H) + t] == 0) tmp[((q * L + r) * H) + t] = -1;
+                }
+                mus[i] = m3_usable(tmp, W, L, H, max_height);
+            }
+        }
+        free(tmp);
+        int bi = 0; for (int i = 1; i < ncand; i++) if (mus[i] > mus[bi]) bi = i;
+        best_index = cands[bi];
+        while (!settle[best_index]) {
+            mus[bi] = -1;
+            bi = 0; for (int i = 1; i < ncand; i++) if (mus[i] > mus[bi]) bi = i;
+            best_index = cands[bi];
+        }
+    } else {
+        int ci = 0; best_index = cands[0];
+        while (!settle[best_index]) { ci++; best_index = cands[ci]; }
+    }
+
+    /* ---- commit :3161-3171 ---- */
+    const int _x = pos[best_index][0], _y = pos[best_index][1], _z = pos[best_index][2];
+    if (_z + bz > H) { e->error = 1; return; }              /* update_level_free_space indexes level _z+bz-1 */
+    e->positions[k * 3] = _x; e->positions[k * 3 + 1] = _y; e->positions[k * 3 + 2] = _z;
+    e->stable[k] = stab[best_index];
+    e->empty = empty_ems[best_index];
+    for (int q = _x; q < _x + bx; q++) for (int r = _y; r < _y + by; r++) {
+        for (int t = _z; t < _z + bz; t++) C3(q, r, t) = k + 1;
+        for (int t = 0; t < _z; t++) if (C3(q, r, t) == 0) C3(q, r, t) = -1;
+    }
+    {
+        const int xx = _x + bx - 1; int err = 0;
+        for (int t = _z; t < _z + bz; t++) for (int r = _y; r < _y + by; r++) m3_lfs_occupy(&lfs[t * L + r], _x, xx, bx, &err);
+        for (int t = 0; t < _z; t++) for (int r = _y; r < _y + by; r++) m3_lfs_under(&lfs[t * L + r], _x, xx, bx);
+        if (err) e->error = err;
+    }
+    for (int q = _x; q < _x + bx; q++) for (int r = _y; r < _y + by; r++) h[q * L + r] = _z + bz;
+    e->valid = valid;
+}
+#undef C3
+#undef M3_PUSH
+
 /* ------------------------------------------------------------------ */
 /* LB ("abandoned" but selectable with packing_strategy='LB'): tools.py:1602-1754 (2D), :1756-1914 (3D).
  * Driven through Container.add_new_block (:3683-3686), which never stores the returned bounding_box
@@ -913,7 +1288,7 @@ int tapo_env_add_new_block(tapo_env *e, const float *block, int *hm_out) {
     for (int d = 0; d < e->dim; d++) e->blocks[e->k * e->dim + d] = (int)block[d];
     const int *b = &e->blocks[e->k * e->dim];
     if (e->strategy == TAPO_MACS) {
-        if (e->dim == 2) macs_step_2d(e); else { e->error = 2; return -2; }
+        if (e->dim == 2) macs_step_2d(e); else macs_step_3d(e);
     } else if (e->strategy == TAPO_LB) {
         if (e->dim == 2) lb_step_2d(e); else lb_step_3d(e);
     } else {
@@ -963,6 +1338,7 @@ const int *tapo_env_container(const tapo_env *e) { return e->container; }
 const unsigned char *tapo_env_stable(const tapo_env *e) { return e->stable; }
 int tapo_env_strategy(const tapo_env *e) { return e->strategy; }
 /* MACS: copy level z of level_free_space, returns its length */
+int tapo_env_lfs3(const tapo_env *e, int z, int y, int *out) { if (!e->lfs3 || z >= e->H || y >= e->L) return -1; const ilist *l = &e->lfs3[z * e->L + y]; memcpy(out, l->v, sizeof(int) * l->len); return l->len; }
 int tapo_env_lfs(const tapo_env *e, int z, int *out) { if (!e->lfs || z >= e->H) return -1; memcpy(out, e->lfs[z].v, sizeof(int) * e->lfs[z].len); return e->lfs[z].len; }
 
 /* ------------------------------------------------------------------ */

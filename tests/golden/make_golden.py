@@ -206,6 +206,8 @@ def make_traj():
         ("traj_2d_lb_soft", "rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB", 64),
         ("traj_2d_lb_hard", "rand2d_n10.npz", [5, 50], "C+P+S-lb-hard", "full", "LB", 48),
         ("traj_3d_lb_soft", "rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB", 48),
+        ("traj_3d_macs_soft", "rand3d_n10.npz", [5, 5, 50], "C+P+S-mcs-soft", "diff", "MACS", 40),
+        ("traj_3d_macs_hard", "rand3d_n10.npz", [5, 5, 50], "C+P+S-mcs-hard", "zero", "MACS", 40),
     ]
     only = os.environ.get("TRAJ_ONLY")
     if only:

@@ -74,7 +74,8 @@ def assert_same(g, r, ptr_seq, static, dim):
 
 
 TRAJ = ["traj_2d_lbg_soft", "traj_2d_lbg_hard", "traj_2d_lbg_w7_full", "traj_2d_macs_rand", "traj_2d_macs_ppsg",
-        "traj_3d_lbg_soft", "traj_3d_lbg_hard", "traj_2d_lb_soft", "traj_2d_lb_hard", "traj_3d_lb_soft"]
+        "traj_3d_lbg_soft", "traj_3d_lbg_hard", "traj_2d_lb_soft", "traj_2d_lb_hard", "traj_3d_lb_soft",
+        "traj_3d_macs_soft", "traj_3d_macs_hard"]
 
 
 @pytest.mark.parametrize("fused", [True, False])

@@ -32,6 +32,11 @@ CASES = [
     (2, [6, 50], 12, "C+P+S-lb-hard", "LB", "zero", 100),
     (3, [5, 5, 50], 10, "C+P+S-lb-soft", "LB", "diff", 50),
     (3, [4, 6, 80], 12, "C+P+S-lb-hard", "LB", "full", 30),
+    (3, [5, 5, 50], 10, "C+P+S-mcs-soft", "MACS", "diff", 40),      # calc_one_position_mcs_3d, tools.py:2751-3165
+    (3, [5, 5, 50], 10, "C+P+S-mcs-hard", "MACS", "zero", 40),
+    (3, [4, 6, 80], 14, "C+P-mcs-soft", "MACS", "full", 25),
+    (3, [6, 4, 60], 12, "mcs-hard", "MACS", "diff", 25),
+    (3, [5, 5, 50], 12, "C+P+S-mul-hard", "MUL", "diff", 25),
 ]
 
 
@@ -52,8 +57,10 @@ def test_container_differential(ref, dim, size, n, rt, strat, hm, episodes):
             assert list(c.stable) == [bool(x) for x in r.stable]
         assert c.calc_ratio() == r.calc_ratio()
         assert np.array_equal(c.container, np.asarray(r.container))
-        if strat == "MACS":
+        if strat in ("MACS", "MUL") and dim == 2:
             assert c.level_free_space == [list(map(int, l)) for l in r.level_free_space]
+        if strat in ("MACS", "MUL") and dim == 3:
+            assert c.level_free_space == [[list(map(int, l)) for l in row] for row in r.level_free_space]
 
 
 def test_mask_and_dynamic_differential(ref):
