@@ -802,6 +802,9 @@ static long long m3_usable(const int *c, int W, int L, int H, int Hlim) {
     return score;
 }
 
+static int m3_dbg_max_ne = 0, m3_dbg_max_nv = 0, m3_dbg_max_zlevels = 0;
+int tapo_dbg_m3(int which) { return which == 0 ? m3_dbg_max_ne : (which == 1 ? m3_dbg_max_nv : m3_dbg_max_zlevels); }
+
 static void macs_step_3d(tapo_env *e) {
     const int W = e->W, L = e->L, H = e->H, k = e->k;
     int *h = e->heightmap, *c = e->container;
@@ -1020,6 +1023,9 @@ static void macs_step_3d(tapo_env *e) {
             }
         }
     }
+    if (ne > m3_dbg_max_ne) m3_dbg_max_ne = ne;
+    if (nv > m3_dbg_max_nv) m3_dbg_max_nv = nv;
+    { int zs[256], nz = 0; for (int v = 0; v < nv; v++) { int f = 0; for (int q = 0; q < nz; q++) if (zs[q] == visited[v][2]) f = 1; if (!f && nz < 256) zs[nz++] = visited[v][2]; } if (nz > m3_dbg_max_zlevels) m3_dbg_max_zlevels = nz; }
     if (nsettled == 0) { e->stable[k] = 0; return; }        /* :3129-3132 */
 
     /* ---- choose :3135-3158 ---- */

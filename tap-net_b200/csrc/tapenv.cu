@@ -15,11 +15,16 @@
 #include "place_lbg3d.cuh"
 #include "place_macs2d.cuh"
 #include "place_lb.cuh"
+#include "place_macs3d.cuh"
 #include "window.cuh"
 
 namespace tapenv {
 
-enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2, STRAT_LB = 3 };
+enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2, STRAT_LB = 3, STRAT_MACS3D = 4 };
+
+// strategies that keep a voxel grid + interval lists in the state and run one thread per environment
+static bool voxel_state(const tapenv_config *c) { return c->strategy == TAPENV_LB || (c->strategy == TAPENV_MACS && c->dim == 3); }
+static int lcap_of(const tapenv_config *c) { const int a = c->capacity + 2, b = c->width + 4; return a > b ? a : b; }
 
 // ------------------------------------------------------------------------------------
 // host-side helpers
@@ -43,10 +48,10 @@ static void layout_of(const tapenv_config *c, tapenv_state_layout *L) {
     L->blocks = off;    off = align_up(off + B * cap * dim * sizeof(int32_t), 256);
     L->stable = off;    off = align_up(off + B * cap, 256);
     L->flags = off;     off = align_up(off + B * sizeof(int32_t), 256);
-    const bool lb = c->strategy == TAPENV_LB;
+    const bool lb = voxel_state(c);
     const size_t nlists = (size_t)c->height * (dim == 3 ? (size_t)c->length : 1);
     L->voxels = off;    off = align_up(off + (lb ? B * (size_t)cells_of(c) * (size_t)c->height * sizeof(int16_t) : 0), 256);
-    L->lists = off;     off = align_up(off + (lb ? B * nlists * (cap + 2) : 0), 256);
+    L->lists = off;     off = align_up(off + (lb ? B * nlists * (size_t)lcap_of(c) : 0), 256);
     L->pending = off;   off = align_up(off + (lb ? B * 4 * sizeof(float) : 0), 256);
     L->total = off;
 }
@@ -69,7 +74,7 @@ static DevCfg devcfg_of(const tapenv_config *c) {
     d.inv_L = (65536u + d.L - 1) / (d.L > 0 ? d.L : 1);
     d.dyn_env = (unsigned)(d.dyn_rows * d.S);
     d.static_env = (unsigned)(d.static_rows * d.S);
-    d.lcap = c->capacity + 2;
+    d.lcap = lcap_of(c);
     d.nlists = c->height * (c->dim == 3 ? c->length : 1);
     return d;
 }
@@ -98,7 +103,8 @@ static int check_cfg(const tapenv_config *c) {
     if (c->dim == 3 && c->length < 1) return TAPENV_EINVAL;
     if (c->rotate_types < 1) return TAPENV_EINVAL;
     if (c->strategy != TAPENV_LB_GREEDY && c->strategy != TAPENV_MACS && c->strategy != TAPENV_LB) return TAPENV_EENUM;
-    if (c->strategy == TAPENV_LB && (c->capacity > 250 || c->height > 32767)) return TAPENV_ELIMIT;
+    if (voxel_state(c) && (c->capacity > 250 || c->height > 32767)) return TAPENV_ELIMIT;
+    if (c->strategy == TAPENV_MACS && c->dim == 3 && (c->height > 255 || c->width > 120)) return TAPENV_ELIMIT;   // EMS coordinates are bytes
     if (c->heightmap_type < 0 || c->heightmap_type > 2) return TAPENV_EENUM;
     if (c->ratio_mode < 0 || c->ratio_mode > TAPENV_RATIO_CP_HALF) return TAPENV_EENUM;
     if (c->static_rows < 1 + c->dim) return TAPENV_ESHAPE;
@@ -118,8 +124,9 @@ static int check_cfg(const tapenv_config *c) {
 static int strategy_kernel(const tapenv_config *c) {
     if (c->strategy == TAPENV_LB_GREEDY) return c->dim == 2 ? STRAT_LBG2D : STRAT_LBG3D;
     if (c->strategy == TAPENV_MACS && c->dim == 2) return STRAT_MACS2D;
+    if (c->strategy == TAPENV_MACS && c->dim == 3) return STRAT_MACS3D;
     if (c->strategy == TAPENV_LB) return STRAT_LB;
-    return -1;                                       // MACS 3D: not built (out of scope for v1)
+    return -1;
 }
 
 static int launch_status() { return cudaGetLastError() == cudaSuccess ? TAPENV_OK : TAPENV_ECUDA; }
@@ -259,6 +266,14 @@ reset_kernel(DevCfg c, StatePtrs st, int clear_state, const float *__restrict__ 
             for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
             const size_t nl = (size_t)c.nlists * c.lcap;
             for (size_t i = lane; i < nl; i += 32) st.lists[(size_t)b * nl + i] = (i % c.lcap) == 0 ? 1 : 0;
+        } else if (c.strategy == TAPENV_MACS && c.dim == 3) {   // every (level, row) interval list = [0, W-1] (tools.py:3644-3648)
+            const size_t nv = (size_t)cells * c.H;
+            for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
+            const size_t nl = (size_t)c.nlists * c.lcap;
+            for (size_t i = lane; i < nl; i += 32) {
+                const int q = (int)(i % c.lcap);
+                st.lists[(size_t)b * nl + i] = q == 0 ? 2 : (q == 2 ? (unsigned char)(c.W - 1) : 0);
+            }
         }
     }
     if (dynamic == nullptr) return;
@@ -441,6 +456,62 @@ lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__res
         if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
         else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
         else if (DIM == 2) { for (int i = 0; i + 1 < c.W; ++i) o[i] = (float)(h[i + 1] - h[i]); }
+        else {
+            for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
+                o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
+                o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
+            }
+        }
+    }
+}
+
+
+// MACS 3D: one thread per environment (place_macs3d.cuh).  blocks == nullptr: take the block the fused step's tensor
+// pass left in st.pending.
+__global__ void __launch_bounds__(64)
+macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const int cells = c.W * c.L;
+    const float *blk = blocks ? blocks + (size_t)b * 3 : st.pending + (size_t)b * 4;
+    const int bx = (int)blk[0], by = (int)blk[1], bz = (int)blk[2];           // .astype('int') tools.py:3675
+    M3State s;
+    s.W = c.W; s.L = c.L; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
+    s.vox = st.voxels + (size_t)b * cells * c.H;
+    s.lists = reinterpret_cast<signed char *>(st.lists) + (size_t)b * c.nlists * c.lcap;
+    s.h = st.heightmap + (size_t)b * cells;
+    const int4 sc = st.scal[b];
+    int anomaly = 0;
+    const int k = sc.w;
+    if (k >= c.cap) {
+        anomaly |= 2;
+    } else {
+        int *positions = st.positions + (size_t)b * c.cap * 3, *blks = st.blocks + (size_t)b * c.cap * 3;
+        blks[k * 3] = bx; blks[k * 3 + 1] = by; blks[k * 3 + 2] = bz;
+        int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
+        unsigned char stable = 0;
+        if (bx >= 1 && by >= 1 && bz >= 1 && bx * by <= 32) {
+            const int vol = bx * by * bz;
+            const M3Best best = macs3d_place(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
+            if (best.any && !(anomaly & 1)) {
+                macs3d_commit(s, k, best, bx, by, bz, anomaly);
+                if (!(anomaly & 1)) {
+                    positions[k * 3] = best.x; positions[k * 3 + 1] = best.y; positions[k * 3 + 2] = best.z;
+                    stable = (unsigned char)best.stable;
+                    out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
+                }
+            }
+        }
+        st.stable[(size_t)b * c.cap + k] = stable;
+        st.scal[b] = out;
+    }
+    if (anomaly) st.flags[b] |= anomaly;
+    if (dec_dyn) {                                   // heightmap encodings (tools.py:3716-3743), serial form
+        float *o = dec_dyn + (size_t)b * c.enc_len;
+        const int *h = s.h;
+        if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
+        else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
         else {
             for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
                 o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
@@ -1114,7 +1185,8 @@ int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks
     if (d.B == 0) return TAPENV_OK;
     if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (strat == STRAT_LB) {
+    if (strat == STRAT_MACS3D) launch(macs3d_kernel, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
+    else if (strat == STRAT_LB) {
         if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
         else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
     } else if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
@@ -1144,12 +1216,13 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         if (pf) launch(step_kernel<STRAT, true, N, R, true>, grid, block, s, TAPENV_STEP_ARGS);            \
         else launch(step_kernel<STRAT, true, N, R, false>, grid, block, s, TAPENV_STEP_ARGS);              \
     } while (0)
-    if (strat == STRAT_LB) {                         // tensor pass (no placement) + the thread-per-environment LB kernel
+    if (strat == STRAT_LB || strat == STRAT_MACS3D) { // tensor pass (no placement) + the thread-per-environment placement kernel
         if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
                          dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
         else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
                     dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
-        if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
+        if (strat == STRAT_MACS3D) launch(macs3d_kernel, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
+        else if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
         else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
     } else if (strat == STRAT_LBG2D) {
         if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 10, 2);
@@ -1205,7 +1278,7 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
     if (strat < 0) return TAPENV_EUNSUPPORTED;
-    if (strat == STRAT_LB) return TAPENV_EUNSUPPORTED;      // LB keeps a voxel grid per environment: stepwise API only
+    if (strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;      // voxel-grid strategies: stepwise API only
     if (steps < 0 || steps > 64 || steps > cfg->capacity) return TAPENV_ELIMIT;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !static_ || !dynamic || (steps > 0 && !ptr_seq)) return TAPENV_EINVAL;
@@ -1230,8 +1303,8 @@ int tapenv_reset_packed(const tapenv_config *cfg, void *state, const uint8_t *st
     StatePtrs st; memset(&st, 0, sizeof(st));
     if (state) st = stateptrs_of(cfg, state);
     const int words = tapenv_packed_words(cfg);
-    const int clear = state && cfg->strategy != TAPENV_LB ? 1 : 0;
-    if (state && cfg->strategy == TAPENV_LB) {                          // LB keeps voxel grids / x lists: cleared by the plain reset
+    const int clear = state && !voxel_state(cfg) ? 1 : 0;
+    if (state && voxel_state(cfg)) {                          // LB keeps voxel grids / x lists: cleared by the plain reset
         launch(reset_kernel<false>, grid, block, s, d, st, 1, (const float *)nullptr, (float *)nullptr, (float *)nullptr);
     }
     if (fast_ok(d, dynamic_out, nullptr) && d.SV * d.RP <= 32)
@@ -1249,7 +1322,7 @@ int tapenv_step_mul(const tapenv_config *cfg, void *state_a, void *state_b, cons
                     float *mask_out, float *dec_static_out, int32_t dec_static_rows, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;
+    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;
     if (cfg->static_rows != 2 + cfg->dim) return TAPENV_ESHAPE;
     if (dec_static_rows != cfg->dim && dec_static_rows != cfg->dim + 1) return TAPENV_ESHAPE;
     if (d.B == 0) return TAPENV_OK;
@@ -1274,7 +1347,7 @@ int tapenv_add_blocks_mul(const tapenv_config *cfg, void *state_a, void *state_b
                           const float *target_ids, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;
+    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;
     if (d.B == 0) return TAPENV_OK;
     if (!state_a || !state_b || state_a == state_b || !blocks || !target_ids) return TAPENV_EINVAL;
     const StatePtrs sa = stateptrs_of(cfg, state_a), sb = stateptrs_of(cfg, state_b);
@@ -1391,7 +1464,7 @@ int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_wind
     if (cfg->batch != wcfg->batch || cfg->dim != wcfg->dim || cfg->blocks_num != wcfg->window ||
         cfg->rotate_types != wcfg->rotate_types || cfg->static_rows != 1 + cfg->dim) return TAPENV_ESHAPE;
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB) return TAPENV_EUNSUPPORTED;      // LB: tapenv_window_next + tapenv_add_blocks
+    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;      // voxel-grid strategies: tapenv_window_next + tapenv_add_blocks
     if (d.B == 0) return TAPENV_OK;
     if (!state || !wstate || !pred || !blocks || !ptr || !static_out || !dynamic_out) return TAPENV_EINVAL;
     const WinCfg w = wincfg_of(wcfg);
