@@ -600,6 +600,28 @@ def run_ours(args):
     step_us = 1e3 * tot_ms / cnt
     achieved = B * bytes_step / (step_us * 1e-6) / 1e9
 
+    # context for the fraction: the out-of-place copy of `dynamic` alone (the clone every update_dynamic must make,
+    # pack.py:370) by torch's copy kernel, same cold ring slots, same graph-replay + event method
+    def copy_launches():
+        for i in range(nl):
+            r, w = slots[i]
+            out_bufs[i][0].copy_(r.dynamic[w])
+
+    copy_launches()
+    torch.cuda.synchronize(dev)
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        copy_launches()
+    ctot = 0.0
+    for rep in range(12):
+        env.clear_container()                              # same L2-disturbing prelude as above
+        torch.cuda.synchronize(dev)
+        e0.record(); cg.replay(); e1.record()
+        torch.cuda.synchronize(dev)
+        if rep >= 2:
+            ctot += e0.elapsed_time(e1)
+    copy_us = 1e3 * ctot / (10 * nl)
+
     # ---- timed region 3: e2e -- host buffers in, host rewards out, through the public Python API --------
     # tapenv.HostPipeline: per episode one H2D upload of (static, dynamic, ptr_seq) from pinned memory on a copy
     # stream (double-buffered, overlapping the previous episode's kernels), the episode, D2H of rewards + sums.
@@ -748,7 +770,10 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC.get(args.workload),
                          "algorithmic_bytes_per_env_step": bytes_step, "bytes_per_launch": B * bytes_step,
-                         "launch_us": step_us, "launches_timed": cnt},
+                         "launch_us": step_us, "launches_timed": cnt,
+                         "torch_copy_of_dynamic_us": copy_us,
+                         "note": "torch_copy_of_dynamic_us: torch's copy kernel on the dynamic tensor alone (%.0f%% of the step's bytes), "
+                                 "same slots and timing method -- the practical floor for a launch of this size" % (100.0 * 2 * dynamic_h[0].nbytes / (B * bytes_step))},
             "clocks": clocks,
         }
         if cpu is not None:

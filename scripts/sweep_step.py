@@ -14,6 +14,7 @@ sizes = [int(v) for v in sys.argv[2:]] or [1024, 4096, 16384, 65536]
 dev = torch.device("cuda:0")
 for B in sizes:
     static_h, dynamic_h, size, rt, hm, strat, B, desc, pool = bench.load_workload(wl, B, 0)
+    static_h, dynamic_h = static_h[0], dynamic_h[0]                      # single window
     dim = len(size); R = 2 if dim == 2 else 6; S = static_h.shape[2]; n = S // R
     bytes_step = bench.algorithmic_bytes_per_env_step(n, R, dim, size[0], size[1] if dim == 3 else 1, strat == "MACS" or "mcs" in rt)
     per_set = static_h.nbytes + dynamic_h.nbytes

@@ -932,8 +932,11 @@ __global__ void window_reset_kernel(int B, int T, unsigned *wstate) {
     wstate[q] = v;
 }
 
+#ifndef TAPENV_WINDOW_MIN_BLOCKS
+#define TAPENV_WINDOW_MIN_BLOCKS (32 / TAPENV_WARPS_PER_CTA)
+#endif
 template <int STRAT, bool FAST>                      // STRAT < 0: window only
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 32 / kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, TAPENV_WINDOW_MIN_BLOCKS)
 window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, const unsigned long long *__restrict__ pred,
               const int *__restrict__ blocks, const int64_t *__restrict__ ptr, float *__restrict__ dec_static,
               float *__restrict__ dec_dyn, float *__restrict__ static_out, float *__restrict__ dynamic_out,
