@@ -47,7 +47,7 @@ WINDOWS = {}
 ROLLING = {"c5": (50, 10)}          # workload -> (total_blocks_num, network window)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel at the workload's default batch, from the
 # `ncu --set full` captures summarised under profiles/ (writes stay in the 126 MB L2 at these sizes)
-TRAFFIC = {"c2": 11.34e6}
+TRAFFIC = {"c2": 11.34e6, "c3": 34.14e6, "c4": 10.53e6, "c5": 40.42e6}    # profiles/r01p_*_ncu_full_summary.csv (read + write)
 
 
 def algorithmic_bytes_per_env_step(n, R, dim, W, L, macs):
@@ -734,7 +734,15 @@ def run_ours(args):
                 break
         rate = reps * B * steps_per_episode / el
         parity = bool(np.array_equal(o["reward"], reward_ref.cpu().numpy()))
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        # the reference itself is single-threaded (trainer.py:155, no multiprocessing): the same port on ONE thread, short sample
+        kw1 = dict(kw, nthreads=1)
+        Bs = min(B, 512)
+        r1, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < min(3.0, args.cpu_seconds):
+            oracle.episode_batch(static_h[:, :Bs], dynamic_h[:, :Bs], ptr_h[:, :, :Bs], size, rt, hm, strat, **kw1)
+            r1 += 1
+        rate1 = r1 * Bs * steps_per_episode / (time.perf_counter() - t1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "value_one_thread": rate1,
                "sample": "%d episodes x %d envs x %d steps = %.1f s of oracle/tap_oracle.c on %d pthreads" % (reps, B, steps_per_episode, el, threads),
                "reward_parity_vs_gpu": parity,
                "python_reference_1core": "4.9e3 env-steps/s (unmodified tools.py path, build container, BASELINE.md section 2)"}
