@@ -569,3 +569,52 @@ def test_random_shapes_fuzz(seed):
     if strat == "MACS" and dim == 3:
         assert (g["flags"] == 0).all()
     assert_same(g, r, r["ptr"], static, dim)
+
+
+@pytest.mark.parametrize("fixture,size,strat,rt,B", [("rand2d_n10.npz", [5, 50], "LB_GREEDY", "C+P+S-lb-soft", 65536),
+                                                     ("rand3d_n10.npz", [5, 5, 50], "LB_GREEDY", "C+P+S-lb-hard", 32768),
+                                                     ("ppsg2d_n20.npz", [7, 100], "MACS", "C+P+S-mcs-hard", 8192)])
+def test_full_size_step_properties(fixture, size, strat, rt, B):
+    """Batches at and beyond BASELINE's sizes through size-independent properties of the transition: each block chosen
+    once, masks only ever lose candidates, `dynamic` only ever loses entries, sum(heightmap) == valid + empty, valid ==
+    volume of the placed blocks, and tiled copies of the fixture pool under identical pointers agree bit for bit (the
+    environments are independent) -- plus the oracle on the pool itself."""
+    torch = _torch()
+    import tapenv
+    static_p, dynamic_p = load_inputs(fixture)
+    pool = min(static_p.shape[0], 512)
+    static_p, dynamic_p = static_p[:pool], dynamic_p[:pool]
+    dim = len(size)
+    S = static_p.shape[2]
+    n = S // (2 if dim == 2 else 6)
+    reps = B // pool
+    st = torch.from_numpy(static_p).cuda().repeat(reps, 1, 1)
+    dyn = torch.from_numpy(dynamic_p).cuda().repeat(reps, 1, 1)
+    env = tapenv.BatchedContainers(size, n, rt, "diff", packing_strategy=strat, batch_size=B)
+    cur, mask = env.reset(dyn)
+    weights = torch.arange(S, 0, -1, device="cuda", dtype=torch.float32)
+    ptrs = []
+    for t in range(n):
+        ptr = torch.argmax(cur[:pool] * weights, dim=1).repeat(reps)                      # first accessible candidate
+        prev_dyn, prev_mask = dyn, mask
+        dyn, cur, mask, dec_static, dec_dyn = env.step(ptr, st, dyn, mask)
+        assert bool((dyn <= prev_dyn).all()) and bool((mask <= prev_mask).all()) and bool((cur <= mask).all())
+        ptrs.append(ptr)
+    tour = torch.stack(ptrs, 1)
+    assert bool((torch.sort(tour % n, dim=1).values == torch.arange(n, device="cuda")).all())
+    assert float(mask.sum()) == 0.0 and float(dyn[:, :n].sum()) == 0.0
+    hm = env.heightmap.reshape(B, -1).to(torch.int64)
+    sc = env.scalars.to(torch.int64)
+    assert bool((hm.sum(1) == sc[:, 0] + sc[:, 1]).all())
+    placed_vol = (env.blocks.to(torch.int64).prod(2) * (env.stable.to(torch.int64) >= 0)).sum(1)
+    if not rt.endswith("hard"):
+        assert bool((sc[:, 0] == placed_vol).all())
+    else:
+        assert bool((sc[:, 0] <= placed_vol).all())
+    r = env.calc_ratio()
+    assert bool(torch.equal(hm.view(reps, pool, -1), hm[:pool].expand(reps, pool, -1)))
+    assert bool(torch.equal(r.view(reps, pool), r[:pool].expand(reps, pool)))
+    o = oracle_rollout(static_p, dynamic_p, size, rt, "diff", strat, ptr_seq=tour[:pool].T.cpu().numpy())
+    assert np.array_equal(hm[:pool].cpu().numpy(), o["heightmap"][-1])
+    assert np.array_equal(r[:pool].cpu().numpy(), o["ratio"].astype(np.float32), equal_nan=True)
+    env.check_flags()

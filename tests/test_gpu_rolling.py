@@ -256,3 +256,80 @@ def test_per_instance_initial_container_protocol():
             ic.remove_block(999)                                # unknown id: ignored like the reference's try/except
             steps += 1
         assert steps == T - n
+
+
+def _sub_instance(data, T):
+    """The sub-instance on the first T nodes (edges among them, their block rows in every rotation)."""
+    T0 = data["T"]
+    R = data["blocks"].shape[1] // T0
+    adj = data["adj"][:, :, :T, :T].copy()
+    rows = np.concatenate([np.arange(T) + r * T0 for r in range(R)])
+    return adj, data["blocks"][:, rows].copy()
+
+
+@pytest.mark.parametrize("src,T,n", [("rolling2d_t50.npz", 10, 10), ("rolling2d_t50.npz", 12, 5), ("rolling3d_t50.npz", 10, 10),
+                                     ("rolling3d_t50.npz", 21, 10), ("rolling2d_t50.npz", 33, 16), ("rolling2d_t50.npz", 3, 1)])
+def test_small_totals_and_single_window(src, T, n):
+    """window == total (a single, fully decoded window: no rolling step at all), totals around 2*window (the branch
+    point of networkx's enumeration), a window of one node."""
+    tapenv = _tapenv()
+    data = load_rolling(src, 24)
+    dim = data["dim"]
+    adj, blocks = _sub_instance(data, T)
+    size = [5, 250] if dim == 2 else [5, 5, 250]
+    env = tapenv.BatchedContainers(size, T, "C+P+S-lb-soft", "diff", batch_size=24, window=n)
+    win = tapenv.BatchedInitialContainers(adj, blocks, T, n, dim)
+    run = tapenv.RollingRunner(env, win)
+    ptr_seq = _record_policy(run, T, seed=3)
+    o = oracle.rolling_batch(adj, blocks, ptr_seq.cpu().numpy(), size, n, "C+P+S-lb-soft", "diff", "LB_GREEDY", nthreads=4)
+    assert o["status"] == 0
+    assert np.array_equal(env.heightmap.cpu().numpy().reshape(24, -1), o["heightmap"])
+    assert np.abs(env.calc_ratio().cpu().numpy().astype(np.float64) - o["reward"]).max() <= 1e-6
+    assert int(env.current_blocks_num.min()) == T
+    env.check_flags(); win.check_flags()
+
+
+def test_full_size_rolling_properties():
+    """BASELINE config 5 at its FULL size (65 536 instances x 50 blocks on one GPU), through size-independent properties:
+    (a) every instance packs each of its 50 blocks exactly once and the window tensors stay well-formed,
+    (b) volume conservation: sum(heightmap) == valid_size + empty_size and valid_size == sum of the placed volumes,
+    (c) instances are independent: the batch is 512 distinct instances tiled 128 times under the SAME pointers, so all
+        copies must agree bit for bit -- and with the oracle on the 512 originals."""
+    tapenv = _tapenv()
+    data = load_rolling("rolling3d_t50.npz")
+    pool, T, n, dim = data["adj"].shape[0], 50, 10, 3
+    B = 65536
+    idx = np.arange(B) % pool
+    size = [5, 5, 250]
+    env = tapenv.BatchedContainers(size, T, "C+P+S-lb-soft", "diff", batch_size=B, window=n)
+    win = tapenv.BatchedInitialContainers(data["adj"][idx], data["blocks"][idx], T, n, dim)
+    run = tapenv.RollingRunner(env, win)
+    static, dynamic, cur = run.begin()
+    ptrs, nodes_seen = [], torch.zeros(B, T, dtype=torch.int32, device="cuda")
+    for t in range(T):
+        ptr = torch.argmax(cur[:pool] * torch.arange(cur.shape[1], 0, -1, device="cuda"), dim=1).repeat(B // pool)   # first accessible
+        assert bool(torch.gather(cur, 1, ptr[:, None]).eq(1).all())
+        if t <= T - n:
+            chosen = torch.gather(win.sub_graph_nodes, 1, (ptr % n)[:, None].to(torch.int64)).squeeze(1)
+        else:                                             # inside the last window the node list no longer changes
+            chosen = torch.gather(last_nodes, 1, (ptr % n)[:, None].to(torch.int64)).squeeze(1)
+        if t == T - n:
+            last_nodes = win.sub_graph_nodes.clone()
+        nodes_seen.scatter_add_(1, chosen[:, None].to(torch.int64), torch.ones(B, 1, dtype=torch.int32, device="cuda"))
+        ptrs.append(ptr)
+        static, dynamic, cur, dec_static, _ = run.step(ptr)
+        assert bool((dec_static >= 1).all())
+    assert bool((nodes_seen == 1).all())                                                        # (a)
+    hm = env.heightmap.reshape(B, -1).to(torch.int64)
+    sc = env.scalars.to(torch.int64)
+    assert bool((hm.sum(1) == sc[:, 0] + sc[:, 1]).all())                                       # (b)
+    vol = (env.blocks.to(torch.int64).prod(2) * 1).sum(1)
+    assert bool((sc[:, 0] == vol).all()) and int(sc[:, 3].min()) == T                           # soft reward: every block is placed
+    r = env.calc_ratio()
+    assert bool(torch.equal(hm.view(B // pool, pool, -1), hm[:pool].expand(B // pool, pool, -1)))   # (c)
+    assert bool(torch.equal(r.view(B // pool, pool), r[:pool].expand(B // pool, pool)))
+    o = oracle.rolling_batch(data["adj"], data["blocks"], torch.stack(ptrs)[:, :pool].cpu().numpy(), size, n,
+                             "C+P+S-lb-soft", "diff", "LB_GREEDY", nthreads=8)
+    assert o["status"] == 0 and np.array_equal(hm[:pool].cpu().numpy(), o["heightmap"])
+    assert np.abs(r[:pool].cpu().numpy().astype(np.float64) - o["reward"]).max() <= 1e-6
+    env.check_flags(); win.check_flags()
