@@ -99,6 +99,8 @@ def _record_policy(run, T, seed):
     ("rolling3d_t50.npz", 2048, [5, 5, 250], "C+P+S-lb-soft", "LB_GREEDY"),
     ("rolling2d_t50.npz", 1024, [5, 250], "C+P+S-lb-hard", "LB_GREEDY"),
     ("rolling2d_t50.npz", 512, [7, 250], "C+P+S-mcs-soft", "MACS"),
+    ("rolling3d_t50.npz", 256, [5, 5, 250], "C+P+S-mcs-soft", "MACS"),     # voxel-state strategies: unfused rolling step
+    ("rolling2d_t50.npz", 256, [5, 250], "C+P+S-lb-soft", "LB"),
 ])
 def test_rolling_batch_vs_oracle(src, B, size, rt, strat):
     """Large tiled batches under an on-device random-valid policy, against the threaded CPU oracle driver."""
