@@ -526,8 +526,12 @@ macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *_
 // ------------------------------------------------------------------------------------
 // PLACE_FIRST: run the placement before the precedence pass is consumed (see (3) below) -- chosen when the whole
 // batch is resident in a single wave, where no other warp is left to hide this warp's load latency.
-template <int STRAT, bool FAST, int NT, int RT, bool PLACE_FIRST>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, STRAT == STRAT_LBG2D ? 32 / kWarpsPerCta : 16 / kWarpsPerCta)
+// MINB: CTAs per SM the register allocation must allow.  0 = the strategy's default (2D LB_GREEDY: 8 -> 64 registers;
+// 3D / MACS: 4 -> 88 / 106 registers).  The heavy placements are also built with MINB = 7 (72 registers): that variant is
+// slower per warp but lets 1036 CTAs be resident at once, so a batch of 4096 runs as ONE wave instead of 1.4
+// (profiles/r01q_step_variants.txt: C3 B=4096 16.8 -> 14.4 us) -- chosen per launch in tapenv_step.
+template <int STRAT, bool FAST, int NT, int RT, bool PLACE_FIRST, int MINB = 0>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, MINB > 0 ? MINB : (STRAT == STRAT_LBG2D ? 32 / kWarpsPerCta : 16 / kWarpsPerCta))
 step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
             const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
             float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
@@ -1219,6 +1223,15 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         if (pf) launch(step_kernel<STRAT, true, N, R, true>, grid, block, s, TAPENV_STEP_ARGS);            \
         else launch(step_kernel<STRAT, true, N, R, false>, grid, block, s, TAPENV_STEP_ARGS);              \
     } while (0)
+    // heavy placements (3D, MACS): the 72-register build when it turns a 1.x-wave launch into a single wave
+    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const int kdef = strat == STRAT_LBG3D ? 5 : 4;          // resident CTAs per SM of the default build (88 / 106 registers)
+    const bool lowreg = (int)grid.x > sms * kdef && (int)grid.x <= sms * 7;
+#define TAPENV_STEP_SHAPE_HEAVY(STRAT, N, R)                                                               \
+    do {                                                                                                   \
+        if (lowreg) launch(step_kernel<STRAT, true, N, R, true, 7>, grid, block, s, TAPENV_STEP_ARGS);     \
+        else TAPENV_STEP_SHAPE(STRAT, N, R);                                                               \
+    } while (0)
     if (strat == STRAT_LB || strat == STRAT_MACS3D) { // tensor pass (no placement) + the thread-per-environment placement kernel
         if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
                          dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
@@ -1233,13 +1246,13 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         else if (fast) TAPENV_STEP_SHAPE(STRAT_LBG2D, 0, 0);
         else launch(step_kernel<STRAT_LBG2D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else if (strat == STRAT_LBG3D) {
-        if (fast && bot && d.n == 10 && d.R == 6) TAPENV_STEP_SHAPE(STRAT_LBG3D, 10, 6);
-        else if (fast) TAPENV_STEP_SHAPE(STRAT_LBG3D, 0, 0);
+        if (fast && bot && d.n == 10 && d.R == 6) TAPENV_STEP_SHAPE_HEAVY(STRAT_LBG3D, 10, 6);
+        else if (fast) TAPENV_STEP_SHAPE_HEAVY(STRAT_LBG3D, 0, 0);
         else launch(step_kernel<STRAT_LBG3D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else {
-        if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_MACS2D, 20, 2);
-        else if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_MACS2D, 10, 2);
-        else if (fast) TAPENV_STEP_SHAPE(STRAT_MACS2D, 0, 0);
+        if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE_HEAVY(STRAT_MACS2D, 20, 2);
+        else if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE_HEAVY(STRAT_MACS2D, 10, 2);
+        else if (fast) TAPENV_STEP_SHAPE_HEAVY(STRAT_MACS2D, 0, 0);
         else launch(step_kernel<STRAT_MACS2D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     }
     return launch_status();
