@@ -49,11 +49,12 @@ extern "C" {
 #define TAPENV_ELIMIT (-3)    /* shape outside the compiled limits (see tapenv_limits) */
 #define TAPENV_ESHAPE (-4)    /* S != n*R, dyn_rows too small, ... */
 #define TAPENV_ECUDA (-5)     /* the launch itself failed (cudaGetLastError) */
-#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not built (e.g. MACS 3D) */
+#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not served by this entry point (the 'rot-old' layout; the
+                                    voxel-state strategies LB / MACS 3D in tapenv_episode, tapenv_step_mul, tapenv_rolling_step) */
 
 /* packing_strategy (tools.py:3607, :3679-3701) */
 #define TAPENV_LB_GREEDY 0
-#define TAPENV_MACS 1
+#define TAPENV_MACS 1           /* 2D: heightmap + block history; 3D: voxel grid + interval lists in the state (tools.py:2751-3165) */
 #define TAPENV_LB 2           /* the older corner-list strategy, tools.py:1602-1914; keeps a voxel grid in the state */
 /* heightmap_type (tools.py:3716-3743) */
 #define TAPENV_HM_FULL 0
@@ -106,9 +107,10 @@ typedef struct tapenv_state_layout {
     size_t flags;      /* i32 [B] sticky anomaly bits (the reference would raise IndexError in each case):
                           1 = a stack grew above container height, 2 = more than `capacity` blocks were added,
                           4 = a pointer outside [0,S) was passed to the fused step */
-    size_t voxels;     /* i16 [B,cells,H]  LB only: 0 empty, -1 empty under a block, k+1 block id   (tools.py:3629) */
-    size_t lists;      /* u8  [B,nlists,capacity+2]  LB only: level_free_space x lists, byte 0 = length (tools.py:3649-3653) */
-    size_t pending;    /* f32 [B,4]  LB only: the gathered block handed from the fused step's tensor pass to the placement pass */
+    size_t voxels;     /* i16 [B,cells,H]  LB and MACS 3D: 0 empty, -1 empty under a block, k+1 block id   (tools.py:3629) */
+    size_t lists;      /* i8  [B,nlists,max(capacity+2, width+4)]  LB: level_free_space x lists (tools.py:3649-3653); MACS 3D: the
+                          per-(level,row) interval lists (tools.py:3644-3648); byte 0 = length */
+    size_t pending;    /* f32 [B,4]  LB and MACS 3D: the gathered block handed from the fused step's tensor pass to the placement pass */
     size_t total;      /* == tapenv_state_bytes() */
 } tapenv_state_layout;
 
