@@ -61,11 +61,12 @@ def calc_positions_mcs(blocks, container_size, reward_type):
 def reward(static, tour_indices, reward_type, input_type, allow_rot, container_width, container_height,
            packing_strategy="LB_GREEDY"):
     """pack.reward: re-pack a finished tour and return -(C+P+S) as f32 [B] (pack.py:378-473)."""
-    if input_type in ("mul", "mul-with"):
-        raise NotImplementedError("two-container inputs are outside the accelerated path")
     static = static.detach()
     if not static.is_cuda:
         static = static.cuda()
+    if input_type in ("mul", "mul-with"):
+        return _reward_two_containers(static, tour_indices, reward_type, input_type, allow_rot, container_width,
+                                      container_height, packing_strategy)
     dim = static.shape[1] - 1
     R = rotate_types(dim, allow_rot)
     n = static.shape[2] // R
@@ -76,3 +77,33 @@ def reward(static, tour_indices, reward_type, input_type, allow_rot, container_w
     env, _ = _pack_sequence(seq, size, reward_type, strat)
     ratio = _result(env, False)[3]
     return -ratio.to(torch.float32)
+
+
+def _reward_two_containers(static, tour_indices, reward_type, input_type, allow_rot, container_width, container_height,
+                           packing_strategy):
+    """pack.reward for 'mul' / 'mul-with' (pack.py:455-468): the tour's blocks are split by their target-container id,
+    each part is packed on its own (calc_positions_* on blocks_a / blocks_b) and the two C+P+S sums are averaged; an
+    empty part scores 0."""
+    from .containers import BatchedContainerPairs
+    dim = static.shape[1] - 2
+    R = rotate_types(dim, allow_rot)
+    n = static.shape[2] // R
+    B = static.shape[0]
+    size = [container_width, container_height] if dim == 2 else [container_width, container_width, container_height]
+    idx = tour_indices.to(static.device).long()[:, :n]
+    seq = torch.gather(static[:, 1:1 + dim], 2, idx.unsqueeze(1).expand(-1, dim, -1)).transpose(1, 2).contiguous()   # [B,n,dim]
+    tgt = torch.gather(static[:, -1], 1, idx).contiguous()                                                               # [B,n]
+    strat = "MACS" if packing_strategy in ("MACS", "MUL") else "LB_GREEDY"
+    pairs = BatchedContainerPairs(size, n, reward_type, "full", packing_strategy=strat, batch_size=B, device=static.device,
+                                  input_type=input_type, allow_rot=allow_rot)
+    for i in range(n):
+        pairs.add_new_blocks(seq[:, i].contiguous(), tgt[:, i].contiguous())
+    pairs.check_flags()
+    total = torch.zeros(B, dtype=torch.float64, device=static.device)
+    for env in (pairs.a, pairs.b):
+        sc = env.scalars.to(torch.float64)
+        valid, empty, nstable, k = sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3]
+        hmax = env.heightmap.reshape(B, -1).max(dim=1).values.to(torch.float64)
+        ratio = valid / (hmax * env._cells) + valid / (empty + valid) + nstable / k      # tools.py:2438-2446 with n = len(part)
+        total += torch.where(k > 0, ratio, torch.zeros_like(ratio))                       # `scores_a = 0` for an empty part
+    return -(total / 2).to(torch.float32)

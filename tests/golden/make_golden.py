@@ -393,6 +393,34 @@ def make_traj_mul():
         print(name, "%.1fs" % (time.time() - t), "mean score %.4f" % res["scores"].mean())
 
 
+def make_reward_kat():
+    """pack.reward (pack.py:378-473, the deprecated re-packing reward) on the live reference: single-container 'bot' inputs and
+    the two-container 'mul-with' split, for seeded random tours."""
+    import torch
+    from tests.golden_io import load_inputs
+    pack = refshim.load(("tools", "pack"))["pack"]
+    out = {}
+    rng = np.random.RandomState(17)
+    for name, src, num, it, rt, W, H in [("bot2d", "rand2d_n10.npz", 48, "bot", "C+P+S-lb-soft", 5, 50),
+                                         ("mul2d", "rand2d_n10.npz", 48, "mul-with", "C+P+S-lb-hard", 5, 50),
+                                         ("mul3d", "rand3d_n10.npz", 24, "mul", "C+P+S-lb-soft", 5, 50)]:
+        static, _ = load_inputs(os.path.join(HERE, src), num)
+        B, rows, S = static.shape
+        dim = rows - 1
+        R = 2 if dim == 2 else 6
+        n = S // R
+        if it != "bot":
+            ids = rng.randint(0, 2, size=(B, 1, n)).astype(np.float32)
+            ids[0] = 0                                                  # one environment with an empty container B
+            static = np.concatenate([static, np.tile(ids, (1, 1, R))], 1)
+        tour = np.stack([rng.permutation(n) + n * rng.randint(0, R, size=n) for _ in range(B)]).astype(np.int64)
+        r = pack.reward(torch.from_numpy(static), torch.from_numpy(tour), rt, it, True, W, H)
+        out[name + "_static"] = static.astype(np.uint8); out[name + "_tour"] = tour; out[name + "_reward"] = r.numpy()
+        out[name + "_args"] = np.array([rt, it, str(W), str(H)])
+    np.savez_compressed(os.path.join(HERE, "reward_kat.npz"), **out)
+    print("reward_kat.npz", {k: float(v.mean()) for k, v in out.items() if k.endswith("_reward")})
+
+
 def make_kat():
     """Known-answer vectors (G1-G4 sequences, doc/data.md, visual/draw_result.py),
     outputs re-derived here from the live reference."""
@@ -428,7 +456,7 @@ def make_kat():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj,mul")
+    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj,mul,reward")
     ap.add_argument("--ppsg-num", type=int, default=512)
     a = ap.parse_args()
     only = a.only.split(",")
@@ -442,3 +470,4 @@ if __name__ == "__main__":
         make_rolling(2, 256, "rolling2d_t50.npz")
     if "rolltraj" in only: make_rolling_traj()
     if "mul" in only: make_traj_mul()
+    if "reward" in only: make_reward_kat()

@@ -618,3 +618,18 @@ def test_full_size_step_properties(fixture, size, strat, rt, B):
     assert np.array_equal(hm[:pool].cpu().numpy(), o["heightmap"][-1])
     assert np.array_equal(r[:pool].cpu().numpy(), o["ratio"].astype(np.float32), equal_nan=True)
     env.check_flags()
+
+
+@pytest.mark.parametrize("name", ["bot2d", "mul2d", "mul3d"])
+def test_pack_reward_known_answers(name):
+    """tapenv.reward (pack.reward, pack.py:378-473 -- the deprecated re-packing reward) against values recorded from the live
+    reference, including the two-container split of 'mul' / 'mul-with' (an empty part scores 0)."""
+    torch = _torch()
+    import tapenv
+    z = np.load(golden_path("reward_kat.npz"))
+    rt, it, W, H = [str(v) for v in z[name + "_args"]]
+    static = torch.from_numpy(z[name + "_static"].astype(np.float32)).cuda()
+    tour = torch.from_numpy(z[name + "_tour"]).cuda()
+    r = tapenv.reward(static, tour, rt, it, True, int(W), int(H))
+    assert r.dtype == torch.float32 and r.is_cuda
+    assert np.abs(r.cpu().numpy().astype(np.float64) - z[name + "_reward"].astype(np.float64)).max() <= 1e-6
