@@ -505,14 +505,16 @@ def run_ours(args):
     # Preferred: fused behind the reward kernel over NVLink peer memory (tapenv_reward_allreduce, in the CUDA graph);
     # otherwise an NCCL all-gather of the f64 triples on a side stream, overlapping the next episode.
     exchange, reducer, reduction = None, None, "none (single GPU)"
-    if world > 1 and not args.nccl_reduce:
+    if world > 1 and args.no_reduce:
+        reduction = "none (diagnostic run: --no-reduce)"
+    elif world > 1 and not args.nccl_reduce:
         try:
             exchange = tapenv.dist.PeerExchange(dev)
             reduction = "fused one-shot exchange over NVLink peer memory (tapenv_reward_allreduce), inside the CUDA graph"
         except Exception as e:                          # no symmetric memory / P2P on this box
             exchange = None
             reduction = "PeerExchange unavailable (%s); " % type(e).__name__
-    if world > 1 and exchange is None:
+    if world > 1 and exchange is None and not args.no_reduce:
         reducer = tapenv.dist.RewardReducer(dev)
         reduction = (reduction if reduction.startswith("PeerExchange") else "") + "NCCL all_gather of the f64 triples on a side stream"
 
@@ -803,6 +805,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nccl-reduce", action="store_true", help="multi-GPU: reduce the reward statistics with NCCL instead of the fused peer-memory exchange")
+    ap.add_argument("--no-reduce", action="store_true", help="multi-GPU diagnostic: skip the reward-statistics reduction altogether")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.workload in ROLLING:
