@@ -537,7 +537,7 @@ def _synthetic_inputs(rng, B, n, dim, max_edge, density):
     return static, dynamic
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("TAPENV_FUZZ_SEEDS", "24"))))     # TAPENV_FUZZ_SEEDS=600 for a long run
 def test_random_shapes_fuzz(seed):
     """Generic (not compile-time specialised) shapes: random n, container width/length, heightmap encoding, reward type and
     strategy; S % 4 != 0 takes the scalar tensor path.  Every step bit-exact against the oracle."""

@@ -335,3 +335,44 @@ def test_full_size_rolling_properties():
     assert o["status"] == 0 and np.array_equal(hm[:pool].cpu().numpy(), o["heightmap"])
     assert np.abs(r[:pool].cpu().numpy().astype(np.float64) - o["reward"]).max() <= 1e-6
     env.check_flags(); win.check_flags()
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("TAPENV_FUZZ_SEEDS", "16"))))
+def test_window_random_graphs_fuzz(seed):
+    """Random DAGs (any density, multi-wave admissions), random rotation graphs with wall self-loops, arbitrary block tables,
+    totals 1..64, windows 1..32 (2D) / 1..10 (3D), both node orders, arbitrary (not necessarily accessible) pointers:
+    every window bit-exact against the oracle."""
+    tapenv = _tapenv()
+    rng = np.random.RandomState(5000 + seed)
+    dim = 2 if seed % 2 else 3
+    T = int(rng.randint(1, 65))
+    n = int(rng.randint(1, min(T, 32 if dim == 2 else 10) + 1))
+    R = 2 if dim == 2 else 6
+    B = int(rng.randint(1, 40))
+    order = int(rng.randint(2))
+    dens = [0.02, 0.08, 0.3][int(rng.randint(3))]
+    adj = np.zeros((B, 5, T, T), np.uint8)
+    perm = np.stack([rng.permutation(T) for _ in range(B)])
+    for b in range(B):
+        rank = np.empty(T, int); rank[perm[b]] = np.arange(T)
+        m = (rng.random_sample((T, T)) < dens) & (rank[:, None] > rank[None, :])       # edge u -> v only if u is later in a random order: a DAG
+        adj[b, 0] = m
+        for g in range(1, 5 if dim == 3 else 3):
+            adj[b, g] = rng.random_sample((T, T)) < dens * 0.5
+            adj[b, g][np.arange(T), np.arange(T)] = rng.random_sample(T) < 0.2            # against the wall
+    blocks = rng.randint(1, 6, size=(B, R * T, dim)).astype(np.int32)
+    win = tapenv.BatchedInitialContainers(adj, blocks, T, n, dim, node_order=order)
+    ocs = [oracle.InitialContainer(adj[b], blocks[b], T, n, dim, order=order) for b in range(B)]
+    S = n * R
+    for call in range(T - n + 1):
+        static, dynamic = win.convert_to_input()
+        outs = [oc.convert_to_input() for oc in ocs]
+        assert np.array_equal(static.cpu().numpy(), np.stack([o[0] for o in outs])), (call, T, n)
+        assert np.array_equal(dynamic.cpu().numpy(), np.stack([o[1] for o in outs])), (call, T, n)
+        assert np.array_equal(win.sub_graph_nodes.cpu().numpy(), np.array([oc.sub_graph_nodes for oc in ocs])), call
+        assert bool(win.is_last_graph().all()) == all(oc.is_last_graph() for oc in ocs)
+        ptr = rng.randint(0, S, size=B).astype(np.int64)
+        for b, oc in enumerate(ocs):
+            oc.remove_block(oc.sub_graph_nodes[int(ptr[b]) % n])
+        win.remove_block(torch.from_numpy(ptr).cuda())
+    win.check_flags()
