@@ -58,6 +58,7 @@ __device__ __forceinline__ unsigned long long below64(int v) { return v >= 64 ? 
 // lane of the chosen slot records the key.
 __device__ __forceinline__ void pyset_insert32(unsigned &occ, int &slot, int lane, int key) {
     unsigned i = (unsigned)key & 31u, perturb = (unsigned)key;
+#pragma unroll 1
     for (int guard = 0; guard < 64; ++guard) {
         const unsigned probes = (i + 9u <= 31u) ? 9u : 0u;                   // LINEAR_PROBES
         const unsigned win = ((~occ) >> i) & ((2u << probes) - 1u);
@@ -95,6 +96,7 @@ __device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int le
         unsigned long long t8 = 0ull;
         const int first = len < 5 ? len : 5;
         int q = 0;
+#pragma unroll 1
         for (; q < first; ++q) {
             const unsigned key = sh.list[q];
             unsigned i = key & 7u, perturb = key;
@@ -107,10 +109,12 @@ __device__ __forceinline__ void pyset_order_warp(WinShared &sh, int lane, int le
             const unsigned byte = lane < 8 ? (unsigned)((t8 >> (8 * lane)) & 0xffull) : 0u;
             slot = (int)byte - 1;
         } else {                                                             // set_table_resize(used * 4): 8 -> 32 slots at fill 5,
+#pragma unroll 1
             for (int s = 0; s < 8; ++s) {                                    // old entries re-inserted in slot order
                 const int k = (int)((t8 >> (8 * s)) & 0xffull) - 1;
                 if (k >= 0) pyset_insert32(occ, slot, lane, k);
             }
+#pragma unroll 1
             for (; q < len; ++q) pyset_insert32(occ, slot, lane, sh.list[q]);
         }
         const unsigned full = __ballot_sync(TAPENV_FULL_MASK, slot >= 0);
@@ -150,6 +154,7 @@ __device__ __forceinline__ WinEarly window_refill(const WinCfg &w, WinShared &sh
     unsigned long long alive = fullT & ~gone;
     bool decompose = false;
     const int v0 = lane, v1 = lane + 32;
+#pragma unroll 1
     for (int guard = 0; guard <= kWinMaxTotal; ++guard) {
         const int cnt = __popcll(alive);
         if (cnt == 0) break;
@@ -238,6 +243,7 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
                 if (!act) { plo = 0u; phi = 0u; }
                 const bool loop = g >= 1 && ((plo & alo) | (phi & ahi)) != 0u;      // :1690-1705
                 unsigned keep = 0u;
+#pragma unroll 1
                 for (int i = 0; i < len; ++i) {
                     const int u = sh.perm[i];                   // warp-uniform
                     const unsigned bit = (u < 32 ? (plo >> u) : (phi >> (u - 32))) & 1u;
@@ -262,6 +268,7 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
                     }
                 }
             }
+#pragma unroll 1
             for (int i = 0; i < len; ++i) {
                 const int u = sh.perm[i];                   // warp-uniform
                 const unsigned diag = lane == i ? loopbits : 0u;
@@ -342,6 +349,7 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
         uint4 *dst = reinterpret_cast<uint4 *>(dyo) + lane;
         const int pstride = w.RP * w.SV, rows3 = 3 * n;
         const uint2 *rws = reinterpret_cast<const uint2 *>(sh.rows);
+#pragma unroll 1
         for (int fr = rsub; fr < rows3; fr += w.RP) {
             if (on) {
                 const uint2 rw = rws[fr];
