@@ -87,17 +87,50 @@ class EpisodeRunner(object):
         return self.reward
 
 
-class HostPipeline(object):
-    """Episodes whose inputs live in HOST memory: double-buffered H2D upload of (static, dynamic, ptr_seq) on a copy
-    stream, episode replay on the compute stream, D2H of the rewards -- upload of episode i+1 overlaps the kernels of
-    episode i.  This is the end-to-end path a trainer's DataLoader drives (trainer.py:189-192: one .cuda() per batch).
+def _carve(buf, specs):
+    """Views (dtype, shape) laid out back to back in the uint8 buffer `buf`, each 256-byte aligned."""
+    out, off = [], 0
+    for dtype, shape in specs:
+        n = 1
+        for v in shape:
+            n *= int(v)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        out.append(buf[off: off + nbytes].view(dtype).view(*shape))
+        off = (off + nbytes + 255) // 256 * 256
+    return out
 
-        pipe = HostPipeline(env, static_shape, dynamic_shape, steps)
-        pipe.submit(static_pinned, dynamic_pinned, ptr_seq_pinned)     # returns immediately
-        rewards = pipe.result()                                       # pinned f32 [B] of the OLDEST submitted episode
+
+def _carve_bytes(specs):
+    off = 0
+    for dtype, shape in specs:
+        n = 1
+        for v in shape:
+            n *= int(v)
+        off = (off + n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+    return max(off, 256)
+
+
+class HostBatch(object):
+    """One episode's inputs in ONE contiguous pinned host buffer (HostPipeline.new_host_batch): `static`, `dynamic`,
+    `ptr` are views a loader fills in place; submit() then uploads the batch with a single H2D copy."""
+
+    def __init__(self, specs):
+        self.buffer = torch.empty(_carve_bytes(specs), dtype=torch.uint8).pin_memory()
+        self.static, self.dynamic, self.ptr = _carve(self.buffer, specs)
+
+
+class HostPipeline(object):
+    """Episodes whose inputs live in HOST memory: pipelined H2D upload of (static, dynamic, ptr_seq) on a copy stream,
+    episode replay on the compute stream, D2H of the rewards -- the upload of the next episodes overlaps the kernels of
+    the current one.  This is the end-to-end path a trainer's DataLoader drives (trainer.py:189-192: one .cuda() per batch).
+
+        pipe = HostPipeline(env, steps)
+        pipe.submit(static_pinned, dynamic_pinned, ptr_seq_pinned)     # returns immediately; three H2D copies
+        hb = pipe.new_host_batch(); hb.static[...] = ...; pipe.submit(hb)   # or: one contiguous pinned batch, ONE copy
+        rewards, sums = pipe.result()                                 # pinned f32 [B] / f64 [3] of the OLDEST submitted episode
     """
 
-    def __init__(self, env, steps, depth=2, use_graph=True, windows=1, exchange=None, packed=False):
+    def __init__(self, env, steps, depth=3, use_graph=True, windows=1, exchange=None, packed=False):
         """packed=True: submit() takes (static_u8, dynamic_bits, ptr_seq) in the compact format of tapenv.pack_inputs /
         PACKDataset.packed() -- 20x fewer PCIe bytes; the fp32 tensors are produced on the device (reset_packed)."""
         self.env = env
@@ -108,19 +141,25 @@ class HostPipeline(object):
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
+        if packed:
+            import ctypes as C
+            from . import _capi
+            words = int(_capi.lib.tapenv_packed_words(C.byref(cfg)))
+            self.specs = [(torch.uint8, (B, cfg.static_rows, S)), (torch.int32, (B, words)), (torch.int64, (windows, steps, B))]
+        else:
+            self.specs = [(torch.float32, (windows, B, cfg.static_rows, S)), (torch.float32, (windows, B, cfg.dyn_rows, S)),
+                          (torch.int64, (windows, steps, B))]
         for _ in range(depth):
-            st = torch.empty(windows, B, cfg.static_rows, S, dtype=torch.float32, device=dev)
-            dy = torch.empty(windows, B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
-            pq = torch.zeros(windows, steps, B, dtype=torch.int64, device=dev)
-            pk = None
+            staging = torch.zeros(_carve_bytes(self.specs), dtype=torch.uint8, device=dev)      # same layout as a HostBatch
+            a, b_, pq = _carve(staging, self.specs)
             if packed:
-                import ctypes as C
-                from . import _capi
-                words = int(_capi.lib.tapenv_packed_words(C.byref(cfg)))
-                pk = (torch.zeros(B, cfg.static_rows, S, dtype=torch.uint8, device=dev),
-                      torch.zeros(B, words, dtype=torch.int32, device=dev))
+                st = torch.empty(windows, B, cfg.static_rows, S, dtype=torch.float32, device=dev)
+                dy = torch.empty(windows, B, cfg.dyn_rows, S, dtype=torch.float32, device=dev)
+                pk = (a, b_)
+            else:
+                st, dy, pk = a, b_, None
             runner = EpisodeRunner(env, st, dy, pq, use_graph=use_graph, partial_sums=True, exchange=exchange, packed=pk)
-            self.slots.append(dict(static=st if pk is None else pk[0], dynamic=dy if pk is None else pk[1], ptr=pq, runner=runner,
+            self.slots.append(dict(staging=staging, static=a, dynamic=b_, ptr=pq, runner=runner,
                                    uploaded=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event(),
                                    reward=torch.empty(B, dtype=torch.float32).pin_memory(),
                                    sums=torch.empty(3, dtype=torch.float64).pin_memory(), busy=False))
@@ -132,7 +171,11 @@ class HostPipeline(object):
             self.h2d_bytes = B * cfg.static_rows * S + B * words * 4 + steps * B * 8
         self.d2h_bytes = B * 4 + 24
 
-    def submit(self, static_h, dynamic_h, ptr_h, after_episode=None):
+    def new_host_batch(self):
+        """A pinned host batch with the staging layout of this pipeline (fill .static / .dynamic / .ptr in place)."""
+        return HostBatch(self.specs)
+
+    def submit(self, static_h, dynamic_h=None, ptr_h=None, after_episode=None):
         if self.inflight == self.depth:
             raise RuntimeError("pipeline full: call result() first")
         s = self.slots[self.head]
@@ -140,9 +183,12 @@ class HostPipeline(object):
         with torch.cuda.stream(self.copy_stream):
             if s["busy"]:
                 self.copy_stream.wait_event(s["consumed"])       # the slot's previous episode has read its inputs
-            s["static"].copy_(static_h.view_as(s["static"]), non_blocking=True)
-            s["dynamic"].copy_(dynamic_h.view_as(s["dynamic"]), non_blocking=True)
-            s["ptr"].copy_(ptr_h.view_as(s["ptr"]), non_blocking=True)
+            if isinstance(static_h, HostBatch):                  # one contiguous pinned batch: ONE H2D copy
+                s["staging"].copy_(static_h.buffer, non_blocking=True)
+            else:
+                s["static"].copy_(static_h.view_as(s["static"]), non_blocking=True)
+                s["dynamic"].copy_(dynamic_h.view_as(s["dynamic"]), non_blocking=True)
+                s["ptr"].copy_(ptr_h.view_as(s["ptr"]), non_blocking=True)
             s["uploaded"].record(self.copy_stream)
         compute.wait_event(s["uploaded"])
         r = s["runner"].run()

@@ -633,3 +633,43 @@ def test_pack_reward_known_answers(name):
     r = tapenv.reward(static, tour, rt, it, True, int(W), int(H))
     assert r.dtype == torch.float32 and r.is_cuda
     assert np.abs(r.cpu().numpy().astype(np.float64) - z[name + "_reward"].astype(np.float64)).max() <= 1e-6
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_host_pipeline_uploads(packed, use_graph):
+    """tapenv.HostPipeline: host buffers in, host rewards out -- three separate pinned tensors or one contiguous HostBatch,
+    fp32 or packed; more episodes than the pipeline is deep; every result equals the oracle episode for ITS inputs."""
+    torch = _torch()
+    import tapenv
+    from oracle import oracle
+    B, n, size = 300, 10, [5, 50]
+    static, dynamic = load_inputs("rand2d_n10.npz", 4 * B)
+    env = tapenv.BatchedContainers(size, n, "C+P+S-lb-soft", "diff", batch_size=B)
+    pipe = tapenv.HostPipeline(env, n, depth=3, use_graph=use_graph, packed=packed)
+    batches, want = [], []
+    for i in range(4):
+        st, dy = static[i * B:(i + 1) * B], dynamic[i * B:(i + 1) * B]
+        ptrs = random_valid_ptrs(st, dy, size, seed=20 + i)
+        want.append(oracle.episode_batch(st, dy, ptrs, size, "C+P+S-lb-soft", "diff", "LB_GREEDY", want=("reward",))["reward"])
+        a, b = tapenv.pack_inputs(st, dy) if packed else (st, dy)
+        if i % 2 == 0:                                     # one contiguous pinned batch
+            hb = pipe.new_host_batch()
+            hb.static.copy_(torch.from_numpy(a).view_as(hb.static)); hb.dynamic.copy_(torch.from_numpy(b).view_as(hb.dynamic))
+            hb.ptr.copy_(torch.from_numpy(ptrs).view_as(hb.ptr))
+            batches.append((hb,))
+        else:                                              # three pinned tensors
+            batches.append((torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), torch.from_numpy(ptrs).pin_memory()))
+    got = []
+    order = [0, 1, 2, 3, 1, 0]
+    for i in order:
+        if pipe.inflight == pipe.depth:
+            got.append(pipe.result()[0].clone())
+        pipe.submit(*batches[i])
+    while pipe.inflight:
+        r, sums = pipe.result()
+        got.append(r.clone())
+        assert float(sums[2]) == B
+    assert len(got) == len(order)
+    for i, r in zip(order, got):
+        assert np.array_equal(r.numpy(), want[i]), i
