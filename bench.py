@@ -16,7 +16,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -74,15 +73,18 @@ def load_workload(name, batch, rank):
 # ----------------------------------------------------------------------------------------------
 # clocks (B200_PROFILING.md: sample DURING the timed region)
 # ----------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.025):
-        # NVML queries contend with DMA traffic on the PCIe link: at a 2 ms period they cut pinned H2D copies from 55 to
-        # 32 GB/s (scripts/h2d_probe.py); 25 ms keeps a dozen samples per second of timed work with no measurable effect
-        threading.Thread.__init__(self, daemon=True)
-        self.period = period
+class ClockSampler(object):
+    """SM clock + throttle reasons sampled WHILE the GPU executes the timed region: the timed loops only enqueue work, so
+    after the last enqueue the launching thread polls NVML until the closing event has completed (`sample_until`).  No
+    background thread: a polling thread competes with the launching thread for the GIL and with the DMA engines for the
+    PCIe link -- at a 2 ms period it cut the pinned H2D rate of the e2e leg from 55 to 32 GB/s (scripts/h2d_probe.py)."""
+
+    NAMES = (("HwSlowdown", 0x8, "hw_slowdown"), ("HwThermalSlowdown", 0x40, "hw_thermal_slowdown"),
+             ("SwThermalSlowdown", 0x20, "sw_thermal_slowdown"), ("SwPowerCap", 0x4, "sw_power_cap"))
+
+    def __init__(self, index):
         self.samples = []
         self.reasons = set()
-        self.stop_flag = False
         self.ok = False
         try:
             import pynvml
@@ -90,38 +92,40 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.bits = {getattr(pynvml, "nvmlClocksEventReason" + a, getattr(pynvml, "nvmlClocksThrottleReason" + a, d)): nm
+                         for a, d, nm in self.NAMES}
             self.ok = True
         except Exception:
             self.sm_max = None
 
-    def run(self):
+    def start(self):                      # kept for call-site compatibility: nothing runs in the background
+        return self
+
+    def sample(self):
         if not self.ok:
             return
         nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
-        }
-        while not self.stop_flag:
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            time.sleep(self.period)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, nm in self.bits.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def sample_until(self, event, max_samples=64):
+        """Poll while the GPU is still working towards `event` (a recorded torch.cuda.Event); at least one sample."""
+        self.sample()
+        n = 1
+        while not event.query() and n < max_samples:
+            self.sample()
+            n += 1
 
     def result(self):
-        self.stop_flag = True
-        if self.ok and self.is_alive():
-            self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
@@ -332,6 +336,7 @@ def run_rolling(args):
     for k in range(args.steps):
         runners[k % RING].run()
     e1.record()
+    sampler.sample_until(e1)                               # clocks while the GPU works through the timed episodes
     barrier()
     t_wall = time.perf_counter() - t_wall
     tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -384,7 +389,14 @@ def run_rolling(args):
             last = pipe.result()
         return last
 
-    e2e_run(3)
+    # warm-up of the host->device path itself: on a fresh box the first ~100 ms of pinned copies run at half rate (PCIe link /
+    # IOMMU state); without this the same command measured 8.7e7 on its first run and 1.8e8 on its second (r01x)
+    big = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    big_d = torch.empty_like(big, device=dev)
+    for _ in range(24):
+        big_d.copy_(big, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e2e_run(max(args.warmup, 3) + 16)
     barrier()
     t0 = time.perf_counter()
     rw_pin, sums_pin = e2e_run(args.steps)
@@ -427,7 +439,7 @@ def run_rolling(args):
             "dtype": "int32 state + f64 score, f32 tensors, u64 graph masks", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "blocks": T, "window": n, "env_steps_per_step": world * B * T,
                        "step_definition": "one episode = clear + window reset + first window + %d fused rolling steps (place + remove_block + "
-                                          "convert_to_input) + %d fused decode steps in the last window + reward over the batch" % (T - n, n),
+                                          "convert_to_input) + %d fused decode steps in the last window (the last also emits calc_ratio) + reward sums over the batch" % (T - n, n),
                        "l2": "%.0f MB of ping-pong window tensors per episode > 126 MB L2; %d instance sets alternate" % (per_episode_bytes / 1e6, RING),
                        "cuda_graph": not args.no_graph, "reward_reduction": reduction,
                        "inputs": "reference rolling.get_dataset fixtures (tests/golden), pool of %d tiled" % pool,
@@ -558,6 +570,7 @@ def run_ours(args):
         ev[k][0].record()
         episode(k)
         ev[k][1].record()
+    sampler.sample_until(ev[-1][1])                        # clocks while the GPU works through the timed episodes
     barrier()
     t_wall = time.perf_counter() - t_wall
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -630,7 +643,7 @@ def run_ours(args):
     # tapenv.HostPipeline: per episode one H2D upload of (static, dynamic, ptr_seq) from pinned memory on a copy
     # stream (double-buffered, overlapping the previous episode's kernels), the episode, D2H of rewards + sums.
     pq_pin = ptr_seq0.cpu().pin_memory()
-    pipe = tapenv.HostPipeline(env, n, depth=3, use_graph=not args.no_graph, windows=Wn, exchange=exchange)
+    pipe = tapenv.HostPipeline(env, n, depth=4, use_graph=not args.no_graph, windows=Wn, exchange=exchange)
     hb = pipe.new_host_batch()                             # ONE contiguous pinned batch (what a loader fills in place): one H2D copy per episode
     hb.static.copy_(torch.from_numpy(static_h)); hb.dynamic.copy_(torch.from_numpy(dynamic_h)); hb.ptr.copy_(pq_pin)
     after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if reducer is not None else None   # in-order here: the host reads the totals
@@ -645,7 +658,14 @@ def run_ours(args):
             last = pipe.result()
         return last
 
-    e2e_run(3)
+    # warm-up of the host->device path itself: on a fresh box the first ~100 ms of pinned copies run at half rate (PCIe link /
+    # IOMMU state); without this the same command measured 8.7e7 on its first run and 1.8e8 on its second (r01x)
+    big = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    big_d = torch.empty_like(big, device=dev)
+    for _ in range(24):
+        big_d.copy_(big, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e2e_run(max(args.warmup, 3) + 16)
     barrier()
     t0 = time.perf_counter()
     rw_pin, sums_pin = e2e_run(args.steps)
@@ -662,7 +682,7 @@ def run_ours(args):
     e2e_packed = None
     if Wn == 1 and strat != "LB":
         su8, bits = tapenv.pack_inputs(static_h[0], dynamic_h[0])
-        pipe_p = tapenv.HostPipeline(env, n, depth=3, use_graph=not args.no_graph, windows=1, exchange=exchange, packed=True)
+        pipe_p = tapenv.HostPipeline(env, n, depth=4, use_graph=not args.no_graph, windows=1, exchange=exchange, packed=True)
         hbp = pipe_p.new_host_batch()
         hbp.static.copy_(torch.from_numpy(su8)); hbp.dynamic.copy_(torch.from_numpy(bits)); hbp.ptr.copy_(pq_pin)
 
@@ -676,7 +696,7 @@ def run_ours(args):
                 last = pipe_p.result()
             return last
 
-        e2e_packed_run(3)
+        e2e_packed_run(max(args.warmup, 3) + 16)
         barrier()
         t0 = time.perf_counter()
         rwp, _ = e2e_packed_run(args.steps)
@@ -691,8 +711,6 @@ def run_ours(args):
                       "api": "tapenv.HostPipeline(packed=True): u8 static + bit-row dynamic + ptr_seq from pinned host memory, "
                              "expanded to the fp32 tensors on the device (tapenv_reset_packed)"}
     # plain pinned H2D bandwidth of this box, for reading the e2e numbers (the fp32 path is PCIe-bound)
-    big = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
-    big_d = torch.empty_like(big, device=dev)
     big_d.copy_(big, non_blocking=True)
     torch.cuda.synchronize(dev)
     eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -764,7 +782,7 @@ def run_ours(args):
             "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 state + f64 score, f32 tensors", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "blocks": steps_per_episode, "env_steps_per_step": world * B * steps_per_episode,
-                       "step_definition": "one episode = reset + %d fused decode-step launches%s + reward over the batch"
+                       "step_definition": "one episode = reset + %d fused decode-step launches%s (the last also emits calc_ratio) + reward sums over the batch"
                                           % (steps_per_episode, " (%d windows of %d, masks re-initialised per window)" % (Wn, n) if Wn > 1 else ""),
                        "l2": "inputs rotate over a ring of %d distinct batches (%.0f MB incl. ping-pong outputs) > 126 MB L2" % (RING, RING * 3 * per_set / 1e6),
                        "cuda_graph": not args.no_graph, "reward_reduction": reduction,
@@ -775,7 +793,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / args.steps,
                     "api": "tapenv.HostPipeline.submit/result: one contiguous pinned host batch (fp32 static + dynamic, int64 ptr_seq) -> one H2D copy per episode, "
-                           "3-deep pipeline, BatchedContainers.reset/step/calc_ratio graph, rewards + sums to pinned host memory",
+                           "4-deep pipeline, BatchedContainers.reset/step(+reward)/reward_sums graph, rewards + sums to pinned host memory",
                     "h2d_gbs_achieved": pipe.h2d_bytes * args.steps / float(te.item()) / 1e9, "h2d_gbs_box": h2d_gbs},
             "e2e_packed": e2e_packed,
             "episode_kernel": k7,

@@ -205,6 +205,19 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
                 float *dynamic_out, float *cur_mask_out, float *mask_out,
                 float *dec_static_out, float *dec_dynamic_out, void *stream);
 
+/* tapenv_step + Container.calc_ratio() of the state the step leaves behind: what model.py:499-515 computes right after the
+ * LAST decode step, without a separate launch.  reward_out f32 [B] as tapenv_reward. */
+int tapenv_step_reward(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
+                       const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                       float *mask_out, float *dec_static_out, float *dec_dynamic_out, float *reward_out, void *stream);
+
+/* The deterministic (sum r, sum r^2, B) of an existing reward vector, and -- with comm != NULL -- its cross-GPU exchange
+ * (see tapenv_reward_allreduce): the second half of tapenv_reward / tapenv_reward_allreduce for rewards that
+ * tapenv_step_reward already produced.  partial_sums_out may be NULL when comm is given. */
+struct tapenv_peer_comm;
+int tapenv_reward_sums(const tapenv_config *cfg, const float *reward, double *partial_sums_out, double *total_sums_out,
+                       const struct tapenv_peer_comm *comm, void *stream);
+
 /* Container.calc_ratio() for every environment (tools.py:3887-3966; consumed at
  * model.py:499-515): reward_out f32 [B] = (float) ratio (fp64 -> fp32, NOT negated).
  * partial_sums_out (may be NULL) f64 [3] = (sum r, sum r^2, B) reduced in a fixed

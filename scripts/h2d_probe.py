@@ -21,10 +21,16 @@ bw(64 << 20, 8, label="64 MiB")
 bw(11141120, 50, label="one C2 episode (11.1 MB)")
 bw(11141120, 50, label="again")
 bw(1 << 20, 200, label="1 MiB")
-# with a busy host thread polling NVML like bench.py's ClockSampler
+# with a background thread polling NVML every 2 ms (what bench.py's clock sampler used to be)
 import threading
 import bench
-s = bench.ClockSampler(0); s.start()
-bw(11141120, 50, label="11.1 MB + NVML sampler")
-bw(64 << 20, 8, label="64 MiB + NVML sampler")
+s = bench.ClockSampler(0)
+stop = []
+def poll():
+    while not stop:
+        s.sample(); time.sleep(0.002)
+th = threading.Thread(target=poll, daemon=True); th.start()
+bw(11141120, 50, label="11.1 MB + NVML thread")
+bw(64 << 20, 8, label="64 MiB + NVML thread")
+stop.append(1); th.join()
 print(s.result())

@@ -202,12 +202,33 @@ struct EnvRegs {
     }
 };
 
+// Container.calc_CPS + calc_ratio (tools.py:3887-3966) in IEEE fp64, operation for operation
+__device__ __forceinline__ double calc_ratio_dev(const DevCfg &c, int valid, int empty, int nstable, int k, int height) {
+    const int cells = c.dim == 2 ? c.W : c.W * c.L;
+    double C = 0.0, P = 0.0, S = 0.0;              // current_blocks_num == 0 -> 0, 0, 0 (tools.py:3888-3889)
+    if (k != 0) {
+        C = __ddiv_rn((double)valid, (double)(cells * height));
+        P = __ddiv_rn((double)valid, (double)(empty + valid));
+        S = __ddiv_rn((double)nstable, (double)k);
+    }
+    switch (c.ratio_mode) {
+        case TAPENV_RATIO_C: return __ddiv_rn(C, 3.0);
+        case TAPENV_RATIO_CS: return __ddiv_rn(__dmul_rn(C, S), 3.0);
+        case TAPENV_RATIO_C_P: return __ddiv_rn(__dadd_rn(C, P), 3.0);
+        case TAPENV_RATIO_CP_S: return __ddiv_rn(__dmul_rn(__dadd_rn(C, P), S), 3.0);
+        case TAPENV_RATIO_2C_SUM: return __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, C), P), S), 3.0);
+        case TAPENV_RATIO_CPS: return __ddiv_rn(__dmul_rn(__dmul_rn(C, P), S), 3.0);
+        case TAPENV_RATIO_CP_HALF: return __ddiv_rn(__dadd_rn(C, P), 2.0);
+        default: return __ddiv_rn(__dadd_rn(__dadd_rn(C, P), S), 3.0);
+    }
+}
+
 // Container.add_new_block for one environment (tools.py:3663-3744): placement, commit,
 // current_blocks_num += 1 even when the placement failed (tools.py:3713), heightmap encoding.
 template <int STRAT>
 __device__ __forceinline__ void container_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane,
                                                     EnvRegs<STRAT> &e, int bx, int by, int bz, float *dec_dyn,
-                                                    unsigned *ems_keys, int extra_flags) {
+                                                    unsigned *ems_keys, int extra_flags, float *reward = nullptr) {
     const int dim = (STRAT == STRAT_LBG3D) ? 3 : 2;
     const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
     int anomaly = extra_flags;
@@ -241,6 +262,11 @@ __device__ __forceinline__ void container_add_block(const DevCfg &c, const State
     if (dec_dyn) {
         if (STRAT == STRAT_LBG3D) encode_heightmap_3d(c, lane, e.x, e.y, e.h, dec_dyn + (size_t)b * c.enc_len);
         else encode_heightmap_2d(c, lane, e.h, dec_dyn + (size_t)b * c.enc_len);
+    }
+    if (reward) {                // Container.calc_ratio on the state this step leaves behind (model.py:509-510 after the last step)
+        const int height = warp_max(lane < cells ? e.h : 0);
+        const int knew = e.sc.k >= c.cap ? e.sc.k : e.sc.k + 1;
+        if (lane == 0) reward[b] = (float)calc_ratio_dev(c, e.sc.valid, e.sc.empty, e.sc.nstable, knew, height);
     }
 }
 
@@ -535,7 +561,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, MINB > 0 ? MINB : (STRAT ==
 step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
             const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
             float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
-            float *__restrict__ dec_dyn) {
+            float *__restrict__ dec_dyn, float *__restrict__ reward) {
     constexpr int DIMC = STRAT == STRAT_LBG3D ? 3 : 2;
     typedef Shape<NT, RT, DIMC> SH;
     __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
@@ -580,7 +606,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
         if (lane == 0 && badp) st.flags[b] |= 4;
     }
     if (PLACE_FIRST && STRAT != STRAT_LB)
-        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0, reward);
 
     // (4) masked copy + column reductions of the precedence tensor
     BandBits bits;
@@ -592,33 +618,12 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
                   env_ptr(mask_out, b, (unsigned)S));
 
     if (!PLACE_FIRST && STRAT != STRAT_LB)
-        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0, reward);
 }
 
 // ------------------------------------------------------------------------------------
 // K6 reward: Container.calc_CPS / calc_ratio (tools.py:3887-3966), one thread per env
 // ------------------------------------------------------------------------------------
-// Container.calc_CPS + calc_ratio (tools.py:3887-3966) in IEEE fp64, operation for operation
-__device__ __forceinline__ double calc_ratio_dev(const DevCfg &c, int valid, int empty, int nstable, int k, int height) {
-    const int cells = c.dim == 2 ? c.W : c.W * c.L;
-    double C = 0.0, P = 0.0, S = 0.0;              // current_blocks_num == 0 -> 0, 0, 0 (tools.py:3888-3889)
-    if (k != 0) {
-        C = __ddiv_rn((double)valid, (double)(cells * height));
-        P = __ddiv_rn((double)valid, (double)(empty + valid));
-        S = __ddiv_rn((double)nstable, (double)k);
-    }
-    switch (c.ratio_mode) {
-        case TAPENV_RATIO_C: return __ddiv_rn(C, 3.0);
-        case TAPENV_RATIO_CS: return __ddiv_rn(__dmul_rn(C, S), 3.0);
-        case TAPENV_RATIO_C_P: return __ddiv_rn(__dadd_rn(C, P), 3.0);
-        case TAPENV_RATIO_CP_S: return __ddiv_rn(__dmul_rn(__dadd_rn(C, P), S), 3.0);
-        case TAPENV_RATIO_2C_SUM: return __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, C), P), S), 3.0);
-        case TAPENV_RATIO_CPS: return __ddiv_rn(__dmul_rn(__dmul_rn(C, P), S), 3.0);
-        case TAPENV_RATIO_CP_HALF: return __ddiv_rn(__dadd_rn(C, P), 2.0);
-        default: return __ddiv_rn(__dadd_rn(__dadd_rn(C, P), S), 3.0);
-    }
-}
-
 __global__ void reward_kernel(DevCfg c, StatePtrs st, float *__restrict__ reward) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     grid_dependency_sync();
@@ -1213,9 +1218,9 @@ int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks
     return launch_status();
 }
 
-int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
-                const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
-                float *mask_out, float *dec_static_out, float *dec_dynamic_out, void *stream) {
+static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
+                     const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                     float *mask_out, float *dec_static_out, float *dec_dynamic_out, float *reward_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
     if (strat < 0) return TAPENV_EUNSUPPORTED;
@@ -1224,7 +1229,7 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
     const bool fast = fast_ok(d, dynamic_in, dynamic_out);
-#define TAPENV_STEP_ARGS d, st, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out, dec_dynamic_out
+#define TAPENV_STEP_ARGS d, st, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out, dec_dynamic_out, reward_out
     // shapes with a fully unrolled instantiation ('bot'-like inputs: 3 bands, all updated); anything else runs generic
     const bool bot = d.dyn_rows == 3 * d.n && d.update_time == 3 && d.static_rows == 1 + d.dim;
     // one resident wave: 148 SMs x (64 regs -> 32 warps) ; PLACE_FIRST only pays off then (profiles/r01_sweep*.json)
@@ -1245,12 +1250,13 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
     } while (0)
     if (strat == STRAT_LB || strat == STRAT_MACS3D) { // tensor pass (no placement) + the thread-per-environment placement kernel
         if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
-                         dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
+                         dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr, (float *)nullptr);
         else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
-                    dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr);
+                    dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr, (float *)nullptr);
         if (strat == STRAT_MACS3D) launch(macs3d_kernel, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
         else if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
         else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
+        if (reward_out) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
     } else if (strat == STRAT_LBG2D) {
         if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 10, 2);
         else if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 20, 2);
@@ -1265,6 +1271,38 @@ int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const
         else if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE_HEAVY(STRAT_MACS2D, 10, 2);
         else if (fast) TAPENV_STEP_SHAPE_HEAVY(STRAT_MACS2D, 0, 0);
         else launch(step_kernel<STRAT_MACS2D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
+    }
+    return launch_status();
+}
+
+int tapenv_step(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
+                const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                float *mask_out, float *dec_static_out, float *dec_dynamic_out, void *stream) {
+    return step_impl(cfg, state, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out,
+                     dec_dynamic_out, nullptr, stream);
+}
+
+int tapenv_step_reward(const tapenv_config *cfg, void *state, const int64_t *ptr, const float *static_,
+                       const float *dynamic_in, const float *mask_in, float *dynamic_out, float *cur_mask_out,
+                       float *mask_out, float *dec_static_out, float *dec_dynamic_out, float *reward_out, void *stream) {
+    if (!reward_out && cfg && cfg->batch > 0) return TAPENV_EINVAL;
+    return step_impl(cfg, state, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out,
+                     dec_dynamic_out, reward_out, stream);
+}
+
+int tapenv_reward_sums(const tapenv_config *cfg, const float *reward, double *partial_sums_out, double *total_sums_out,
+                       const tapenv_peer_comm *comm, void *stream) {
+    int rc_ = check_cfg(cfg);
+    if (rc_ != TAPENV_OK) return rc_;
+    if ((cfg->batch > 0 && !reward) || (!partial_sums_out && !comm)) return TAPENV_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (comm) {
+        if (comm->world < 1 || comm->world > TAPENV_COMM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world || !total_sums_out)
+            return TAPENV_EINVAL;
+        for (int r = 0; r < comm->world; ++r) if (!comm->peer[r]) return TAPENV_EINVAL;
+        launch(reward_sums_exchange_kernel, 1, 1024, s, (int)cfg->batch, reward, partial_sums_out, total_sums_out, *comm);
+    } else {
+        launch(reward_sums_kernel, 1, 1024, s, (int)cfg->batch, reward, partial_sums_out);
     }
     return launch_status();
 }

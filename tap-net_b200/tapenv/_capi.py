@@ -56,6 +56,8 @@ SYMBOLS = {
     "tapenv_update_mask": (c_int, [CFG, P, P, P, P, P, P]),
     "tapenv_add_blocks": (c_int, [CFG, P, P, P, P]),
     "tapenv_step": (c_int, [CFG, P, P, P, P, P, P, P, P, P, P, P]),
+    "tapenv_step_reward": (c_int, [CFG, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "tapenv_reward_sums": (c_int, [CFG, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_reward": (c_int, [CFG, P, P, P, P]),
     "tapenv_comm_bytes": (c_size_t, []),
     "tapenv_reward_allreduce": (c_int, [CFG, P, P, P, P, C.POINTER(PeerComm), P]),

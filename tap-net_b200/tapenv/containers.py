@@ -182,9 +182,11 @@ class BatchedContainers(object):
                         "add_blocks")
         return self._shape_enc(out)
 
-    def step(self, ptr, static, dynamic, mask, out=None):
+    def step(self, ptr, static, dynamic, mask, out=None, reward_out=None):
         """The fused decode-step transition (model.py:376-458 env part) in ONE launch:
-        returns (dynamic', current_mask, mask', decoder_static [B,dim], decoder_dynamic)."""
+        returns (dynamic', current_mask, mask', decoder_static [B,dim], decoder_dynamic).
+        reward_out (f32 [B], optional): also receives calc_ratio() of the state this step leaves behind -- pass it on the
+        LAST decode step instead of calling calc_ratio() afterwards (model.py:499-515)."""
         ptr = _dev(ptr, "ptr", torch.int64)
         static = _dev(static, "static", torch.float32)
         dynamic = _dev(dynamic, "dynamic", torch.float32)
@@ -203,10 +205,27 @@ class BatchedContainers(object):
             dyn_out, cur, mask_out, dec_static, dec_dyn = out
         self._version += 1
         with torch.cuda.device(self.device):
-            _capi.check(_capi.lib.tapenv_step(C.byref(self.cfg), _p(self.state), _p(ptr), _p(static), _p(dynamic),
-                                              _p(mask), _p(dyn_out), _p(cur), _p(mask_out), _p(dec_static), _p(dec_dyn),
-                                              _stream()), "step")
+            if reward_out is None:
+                _capi.check(_capi.lib.tapenv_step(C.byref(self.cfg), _p(self.state), _p(ptr), _p(static), _p(dynamic),
+                                                  _p(mask), _p(dyn_out), _p(cur), _p(mask_out), _p(dec_static), _p(dec_dyn),
+                                                  _stream()), "step")
+            else:
+                if reward_out.dtype != torch.float32 or tuple(reward_out.shape) != (B,) or not reward_out.is_cuda:
+                    raise _capi.TapEnvError(_capi.ESHAPE, "reward_out")
+                _capi.check(_capi.lib.tapenv_step_reward(C.byref(self.cfg), _p(self.state), _p(ptr), _p(static), _p(dynamic),
+                                                         _p(mask), _p(dyn_out), _p(cur), _p(mask_out), _p(dec_static),
+                                                         _p(dec_dyn), _p(reward_out), _stream()), "step_reward")
         return dyn_out, cur, mask_out, dec_static, self._shape_enc(dec_dyn)
+
+    def reward_sums(self, reward, exchange=None):
+        """(sum r, sum r^2, B) of a reward vector produced by step(..., reward_out=) -> f64 [3]; with exchange=PeerExchange
+        -> (local sums, global sums), the cross-GPU reduction in the same launch (see calc_ratio)."""
+        sums = torch.empty(3, dtype=torch.float64, device=self.device)
+        total = torch.empty(3, dtype=torch.float64, device=self.device) if exchange is not None else None
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.tapenv_reward_sums(C.byref(self.cfg), _p(reward), _p(sums), _p(total),
+                                                     C.byref(exchange.comm) if exchange is not None else None, _stream()), "reward_sums")
+        return sums if exchange is None else (sums, total)
 
     def calc_ratio(self, partial_sums=False, exchange=None):
         """Container.calc_ratio for every environment -> f32 [B] (tools.py:3908-3966, model.py:509-510).

@@ -175,8 +175,10 @@ class RollingRunner(object):
         self.partial_sums = partial_sums
         self.exchange = exchange
         self.reward = self.sums = self.total_sums = None
+        self.reward_buf = None
         # clear + window reset + first window + T steps + reward (+ sums)
-        self.launches_per_episode = 3 + self.total + 1 + (1 if (partial_sums or exchange is not None) else 0)
+        # clear + window reset + first window, T steps (the last also emits the rewards), the sums (+ exchange) launch
+        self.launches_per_episode = 3 + self.total + (1 if (partial_sums or exchange is not None) else 0)
         self.graph = None
         if use_graph:
             assert ptr_seq is not None
@@ -194,9 +196,9 @@ class RollingRunner(object):
         self.win.convert_to_input(out=(self.static[0], self.dynamic[0]), masks=(self.cur[0], self.mask[0]))
         return self.static[0], self.dynamic[0], self.cur[0]
 
-    def step(self, ptr):
+    def step(self, ptr, reward_out=None):
         """One decode step for every instance; returns (static, dynamic, cur_mask, decoder_static, decoder_dynamic)
-        the network sees next."""
+        the network sees next.  reward_out (f32 [B]): on the LAST step, also receive calc_ratio()."""
         env, win = self.env, self.win
         ptr = _dev(ptr, "ptr", torch.int64)
         n, T = win.child_graph_size, self.total
@@ -225,7 +227,7 @@ class RollingRunner(object):
         else:                                          # last window: the ordinary fused decode step
             o = s ^ 1
             env.step(ptr, self.static[self.sslot], self.dynamic[s], self.mask[s],
-                     out=(self.dynamic[o], self.cur[o], self.mask[o], self.dec_static, self.dec_dyn))
+                     out=(self.dynamic[o], self.cur[o], self.mask[o], self.dec_static, self.dec_dyn), reward_out=reward_out)
             self.slot = o
         self.t += 1
         o = self.slot
@@ -233,13 +235,17 @@ class RollingRunner(object):
 
     def _episode(self):
         self.begin()
+        if self.reward_buf is None:
+            self.reward_buf = torch.empty(self.env.batch_size, dtype=torch.float32, device=self.env.device)
         for t in range(self.total):
-            self.step(self.ptr_seq[t])
+            self.step(self.ptr_seq[t], reward_out=self.reward_buf if t == self.total - 1 else None)   # calc_ratio rides on the last step
+        self.reward = self.reward_buf
         if self.exchange is not None:
-            self.reward, self.sums, self.total_sums = self.env.calc_ratio(exchange=self.exchange)
+            self.sums, self.total_sums = self.env.reward_sums(self.reward, exchange=self.exchange)
+        elif self.partial_sums:
+            self.sums = self.env.reward_sums(self.reward)
         else:
-            res = self.env.calc_ratio(partial_sums=self.partial_sums)
-            self.reward, self.sums = res if self.partial_sums else (res, None)
+            self.sums = None
 
     def _capture(self):
         dev = self.env.device

@@ -38,10 +38,12 @@ class EpisodeRunner(object):
         self.mask_buf = [torch.empty(B, S, **f32), torch.empty(B, S, **f32)]
         self.dec_static = torch.empty(B, env.cfg.static_rows - 1, **f32)
         self.dec_dyn = torch.empty(B, env.enc_len, **f32)
+        self.reward_buf = torch.empty(B, **f32)
         self.reward = None
         self.sums = None
         self.partial_sums = partial_sums
-        self.launches_per_episode = self.windows * (1 + self.steps) + 1 + (1 if partial_sums else 0)
+        # reset / initial mask + fused steps per window (the last one also emits the rewards) + the sums (+ exchange) launch
+        self.launches_per_episode = self.windows * (1 + self.steps) + (1 if (partial_sums or exchange is not None) else 0)
         self.graph = None
         if use_graph:
             self._capture()
@@ -58,12 +60,18 @@ class EpisodeRunner(object):
             dyn = self.dynamic[w]
             for t in range(self.steps):
                 out = (self.dyn_buf[t & 1], self.cur_buf[t & 1], self.mask_buf[t & 1], self.dec_static, self.dec_dyn)
-                dyn, cur, mask, _, _ = env.step(self.ptr_seq[w, t], self.static[w], dyn, mask, out=out)
+                last = w == self.windows - 1 and t == self.steps - 1          # calc_ratio rides on the last decode step
+                dyn, cur, mask, _, _ = env.step(self.ptr_seq[w, t], self.static[w], dyn, mask, out=out,
+                                                reward_out=self.reward_buf if last else None)
+        self.reward = self.reward_buf
+        if self.steps == 0:
+            self.reward = env.calc_ratio()
         if self.exchange is not None:
-            self.reward, self.sums, self.total = env.calc_ratio(exchange=self.exchange)
+            self.sums, self.total = env.reward_sums(self.reward, exchange=self.exchange)
+        elif self.partial_sums:
+            self.sums = env.reward_sums(self.reward)
         else:
-            res = env.calc_ratio(partial_sums=self.partial_sums)
-            self.reward, self.sums = res if self.partial_sums else (res, None)
+            self.sums = None
         self.final = (dyn, cur, mask)
 
     def _capture(self):

@@ -673,3 +673,30 @@ def test_host_pipeline_uploads(packed, use_graph):
     assert len(got) == len(order)
     for i, r in zip(order, got):
         assert np.array_equal(r.numpy(), want[i]), i
+
+
+@pytest.mark.parametrize("fixture,size,strat,rt", [("rand2d_n10.npz", [5, 50], "LB_GREEDY", "C+P+S-lb-soft"),
+                                                   ("rand3d_n10.npz", [5, 5, 50], "LB_GREEDY", "C+P+S-lb-hard"),
+                                                   ("ppsg2d_n20.npz", [7, 100], "MACS", "C+P+S-mcs-hard"),
+                                                   ("rand2d_n10.npz", [5, 50], "LB", "C+P+S-lb-soft"),
+                                                   ("rand3d_n10.npz", [5, 5, 50], "MACS", "C+P+S-mcs-soft")])
+def test_reward_rides_on_the_last_step(fixture, size, strat, rt):
+    """tapenv_step_reward: calc_ratio emitted by the decode step itself (any step, not only the last) equals the separate
+    tapenv_reward launch bit for bit; tapenv_reward_sums equals the sums tapenv_reward produces."""
+    torch = _torch()
+    import tapenv
+    B = 257
+    static, dynamic = load_inputs(fixture, B)
+    n = static.shape[2] // (2 if len(size) == 2 else 6)
+    ptrs = random_valid_ptrs(static, dynamic, size, seed=4)
+    env = tapenv.BatchedContainers(size, n, rt, "diff", packing_strategy=strat, batch_size=B)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    cur, mask = env.reset(dyn)
+    rbuf = torch.full((B,), -7.0, device="cuda")
+    for t in range(n):
+        dyn, cur, mask, _, _ = env.step(torch.from_numpy(ptrs[t]).cuda(), st, dyn, mask, reward_out=rbuf if t in (2, n - 1) else None)
+        if t in (2, n - 1):
+            want, sums = env.calc_ratio(partial_sums=True)
+            assert torch.equal(rbuf, want), t
+            assert torch.equal(env.reward_sums(rbuf), sums)
+    env.check_flags()
