@@ -13,7 +13,7 @@ from .config import make_config, rotate_types
 from .ops import update_dynamic, update_mask
 from .containers import BatchedContainers, BatchedContainerPairs, Container
 from .runner import EpisodeRunner, HostPipeline
-from .decode import DecodeLoop
+from .decode import DecodeLoop, RollingDecodeLoop
 from . import dist
 from .dataset import PACKDataset, pack_inputs
 from .episode import calc_positions_lb_greedy, calc_positions_mcs, reward
@@ -21,5 +21,5 @@ from .dropin import install, uninstall
 from .rolling import BatchedInitialContainers, RollingRunner, RollingHostPipeline, pack_graphs
 
 __all__ = ["PACKDataset", "pack_inputs", "reward", "calc_positions_lb_greedy", "calc_positions_mcs", "install", "uninstall",
-           "update_dynamic", "update_mask", "Container", "BatchedContainers", "BatchedContainerPairs", "EpisodeRunner", "DecodeLoop", "HostPipeline", "make_config", "rotate_types",
+           "update_dynamic", "update_mask", "Container", "BatchedContainers", "BatchedContainerPairs", "EpisodeRunner", "DecodeLoop", "RollingDecodeLoop", "HostPipeline", "make_config", "rotate_types",
            "TapEnvError", "BatchedInitialContainers", "RollingRunner", "RollingHostPipeline", "pack_graphs"]

@@ -75,3 +75,39 @@ class DecodeLoop(object):
         self._dynamic_in.copy_(dynamic)
         self._graph.replay()
         return self._out
+
+
+class RollingDecodeLoop(object):
+    """rolling.validate's loop (rolling.py:589-640) for a batch with the network as a callback: every step the actor sees
+    the CURRENT window (static, dynamic) and the decoder inputs of the previous placement, picks a candidate (greedy like
+    actor.eval(), or sampled), and ONE launch places the block and rebuilds the window (RollingRunner.step).
+
+        loop = tapenv.RollingDecodeLoop(tapenv.RollingRunner(env, windows), actor_step)
+        tour_idx, tour_logp, reward = loop.run()          # tour_idx[:, t] = pointer into the window of step t
+    """
+
+    def __init__(self, runner, actor_step, greedy=True, generator=None):
+        self.runner, self.actor_step, self.greedy, self.generator = runner, actor_step, greedy, generator
+
+    def run(self):
+        run = self.runner
+        env = run.env
+        B = env.batch_size
+        static, dynamic, current_mask = run.begin()
+        dec_static = torch.zeros(B, env.block_dim, device=env.device)            # RollingDataset's zero decoder inputs (rolling.py:521-533)
+        dec_dyn = env._shape_enc(torch.zeros(B, env.enc_len, device=env.device))
+        state = None
+        idx, logps = [], []
+        for _ in range(run.total):
+            logits, state = self.actor_step(static, dynamic, dec_static, dec_dyn, state)
+            probs = torch.softmax(logits + current_mask.log(), dim=1)            # rolling.py:389
+            if self.greedy:
+                prob, ptr = torch.max(probs, 1)                                  # rolling.py:399-400
+                logp = prob.log()
+            else:
+                ptr = torch.multinomial(probs, 1, generator=self.generator).squeeze(1)
+                logp = torch.log(torch.gather(probs, 1, ptr.unsqueeze(1)).squeeze(1))
+            static, dynamic, current_mask, dec_static, dec_dyn = run.step(ptr)
+            idx.append(ptr)
+            logps.append(logp)
+        return torch.stack(idx, 1), torch.stack(logps, 1), env.calc_ratio()

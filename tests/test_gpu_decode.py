@@ -94,3 +94,53 @@ def test_sampling_decode_loop_is_valid_and_reproducible():
     # replaying the sampled tour through the oracle reproduces the reward
     ref = oracle.episode_batch(static, dynamic, tour.T.copy(), [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", want=("reward",))
     assert np.array_equal(ref["reward"], outs[0][2].cpu().numpy())
+
+
+def test_rolling_decode_loop_matches_cpu_replica():
+    """tapenv.RollingDecodeLoop (rolling.validate's loop, greedy like actor.eval()) against a CPU replica on the oracle's
+    InitialContainer + Container with the same integer-logit actor: identical pointers, windows and rewards."""
+    import tapenv
+    from tests.golden_io import load_rolling
+    B, T, n, dim = 24, 50, 10, 3
+    z = load_rolling("rolling3d_t50.npz", B)
+    size, rt = [5, 5, 250], "C+P+S-lb-soft"
+    S = n * 6
+    actor = make_actor(S)
+    # ---- CPU replica ----
+    ics = [oracle.InitialContainer(z["adj"][b], z["blocks"][b], T, n, dim) for b in range(B)]
+    conts = [oracle.Container(size, T, rt, "diff") for _ in range(B)]
+    dec_static = np.zeros((B, dim), np.float32)
+    dec_dyn = np.zeros((B, 2 * 25), np.float32)
+    state, want_idx = None, []
+    t = 0
+    while t < T:
+        outs = [ic.convert_to_input() for ic in ics]
+        static = np.stack([o[0] for o in outs]); dyn = np.stack([o[1] for o in outs])
+        last = ics[0].is_last_graph()
+        mask = np.ones((B, S), np.float32)
+        cur = oracle.initial_mask(dyn, n, 6)
+        for _ in range(n if last else 1):
+            logits, state = actor(torch.from_numpy(static), torch.from_numpy(dyn), torch.from_numpy(dec_static),
+                                  torch.from_numpy(dec_dyn), state)
+            probs = torch.softmax(logits + torch.from_numpy(cur).log(), dim=1)
+            ptr = torch.max(probs, 1)[1].numpy().astype(np.int64)
+            want_idx.append(ptr)
+            dec_static = static[np.arange(B)[:, None], 1 + np.arange(dim)[None, :], ptr[:, None]]
+            dec_dyn = np.stack([np.asarray(conts[b].add_new_block(dec_static[b])).reshape(-1) for b in range(B)]).astype(np.float32)
+            if last:
+                dyn = oracle.update_dynamic(dyn, static, ptr)
+                cur, mask = oracle.update_mask(mask, dyn, static, ptr)
+            t += 1
+        for b, ic in enumerate(ics):
+            ic.remove_block(ic.sub_graph_nodes[int(ptr[b]) % n])
+    want_idx = np.stack(want_idx, 1)
+    want_r = np.array([c.calc_ratio() for c in conts])
+    # ---- device loop ----
+    env = tapenv.BatchedContainers(size, T, rt, "diff", batch_size=B, window=n)
+    win = tapenv.BatchedInitialContainers(z["adj"], z["blocks"], T, n, dim)
+    loop = tapenv.RollingDecodeLoop(tapenv.RollingRunner(env, win), actor)
+    tour_idx, tour_logp, reward = loop.run()
+    assert np.array_equal(tour_idx.cpu().numpy(), want_idx)
+    assert np.abs(reward.cpu().numpy().astype(np.float64) - want_r).max() <= 1e-6
+    assert torch.isfinite(tour_logp).all()
+    env.check_flags(); win.check_flags()
