@@ -421,6 +421,40 @@ def make_reward_kat():
     print("reward_kat.npz", {k: float(v.mean()) for k, v in out.items() if k.endswith("_reward")})
 
 
+def make_g6():
+    """G6 of SURVEY.md section 4: the UNMODIFIED reference model.DRL with the shipped pretrained actors
+    (pretrain_model/{2d,3d}-bot-C+P+S-lb-soft-width-5-note-sh-R-diff/actor.pt), eval() = greedy decode, on fixture inputs;
+    the environment inside is the reference's tools.Container.  Recorded: the tours the network chose and the rewards
+    DRL.forward returned (-calc_ratio).  A network-in-the-loop pin of the env path: replaying the tours must reproduce the
+    rewards (the tours themselves are argmax outputs of an fp32 CPU network and are data here, not something to re-derive)."""
+    import io
+    import contextlib
+    import torch
+    from tests.golden_io import load_inputs
+    mods = refshim.load(("tools", "generate", "pack", "model"))
+    pack, model = mods["pack"], mods["model"]
+    out = {}
+    for dim, src, num, ck in ((2, "rand2d_n10.npz", 64, "2d-bot-C+P+S-lb-soft-width-5-note-sh-R-diff"),
+                              (3, "rand3d_n10.npz", 32, "3d-bot-C+P+S-lb-soft-width-5-note-sh-R-diff")):
+        static, dynamic = load_inputs(os.path.join(HERE, src), num)
+        with contextlib.redirect_stdout(io.StringIO()):
+            actor = model.DRL(dim, 30, 128, 256, False, "bot", True, 5, 50, dim, "C+P+S-lb-soft", "shape_heightmap", "diff",
+                              "LB_GREEDY", pack.update_dynamic, pack.update_mask, 1, 0.1, 1.0)
+        sd = torch.load(os.path.join(refshim.REFERENCE_DIR, "pretrain_model", ck, "actor.pt"), map_location="cpu")
+        missing = actor.load_state_dict(sd)
+        actor.eval()
+        st, dy = torch.from_numpy(static), torch.from_numpy(dynamic)
+        dec_static = torch.zeros(num, dim, 1)
+        dec_dyn = torch.zeros(num, 4, 1) if dim == 2 else torch.zeros(num, 2, 5, 5)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            tour_idx, tour_logp, _, R = actor(st, dy, [dec_static, dec_dyn])
+        out["g6_%dd_tour" % dim] = tour_idx.numpy().astype(np.int64)
+        out["g6_%dd_reward" % dim] = R.numpy().astype(np.float32)
+        out["g6_%dd_num" % dim] = num
+        print("G6 %dD:" % dim, str(missing), "first tour", tour_idx[0].tolist(), "mean reward %.5f" % float(R.mean()))
+    np.savez_compressed(os.path.join(HERE, "g6_tours.npz"), **out)
+
+
 def make_kat():
     """Known-answer vectors (G1-G4 sequences, doc/data.md, visual/draw_result.py),
     outputs re-derived here from the live reference."""
@@ -456,7 +490,7 @@ def make_kat():
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj,mul,reward")
+    ap.add_argument("--only", default="rand2d,rand3d,ppsg,traj,kat,rolling,rolltraj,mul,reward,g6")
     ap.add_argument("--ppsg-num", type=int, default=512)
     a = ap.parse_args()
     only = a.only.split(",")
@@ -471,3 +505,4 @@ if __name__ == "__main__":
     if "rolltraj" in only: make_rolling_traj()
     if "mul" in only: make_traj_mul()
     if "reward" in only: make_reward_kat()
+    if "g6" in only: make_g6()

@@ -700,3 +700,31 @@ def test_reward_rides_on_the_last_step(fixture, size, strat, rt):
             assert torch.equal(rbuf, want), t
             assert torch.equal(env.reward_sums(rbuf), sums)
     env.check_flags()
+
+
+@pytest.mark.parametrize("dim,fixture,size", [(2, "rand2d_n10.npz", [5, 50]), (3, "rand3d_n10.npz", [5, 5, 50])])
+def test_g6_pretrained_network_tours_on_gpu(dim, fixture, size):
+    """G6: the tours the unmodified reference network (pretrained actor, greedy) chose, replayed through the fused step, the
+    whole-episode kernel and the decode loop driven by a tour-replaying actor: rewards equal the ones DRL.forward returned."""
+    torch = _torch()
+    import tapenv
+    z = np.load(golden_path("g6_tours.npz"))
+    num = int(z["g6_%dd_num" % dim])
+    static, dynamic = load_inputs(fixture, num)
+    tour = z["g6_%dd_tour" % dim]
+    want = -z["g6_%dd_reward" % dim].astype(np.float64)
+    env = tapenv.BatchedContainers(size, 10, "C+P+S-lb-soft", "diff", batch_size=num)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    tq = torch.from_numpy(tour.T.copy()).cuda()
+    run = tapenv.EpisodeRunner(env, st, dyn, tq, use_graph=False)
+    assert np.abs(run.run().cpu().numpy().astype(np.float64) - want).max() <= 1e-6
+    assert np.abs(env.episode(st, dyn, tq)[0].cpu().numpy().astype(np.float64) - want).max() <= 1e-6
+    S = static.shape[2]
+
+    def replay_actor(static_, dynamic_, dec_static, dec_dyn, state):          # logits that make the greedy loop follow the recorded tour
+        t = 0 if state is None else state
+        return torch.nn.functional.one_hot(tq[t], S).float() * 50.0, t + 1
+
+    tour_idx, _, reward = tapenv.DecodeLoop(env, replay_actor, greedy=True).run(st, dyn)
+    assert np.array_equal(tour_idx.cpu().numpy(), tour)
+    assert np.abs(reward.cpu().numpy().astype(np.float64) - want).max() <= 1e-6

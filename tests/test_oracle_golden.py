@@ -126,3 +126,16 @@ def test_two_container_inputs_golden(name):
     assert np.array_equal(o["scores"], t["scores"])
     fin = np.unpackbits(t["dynamic_final"], axis=1)[:, :dynamic[0].size].reshape(dynamic.shape).astype(np.float32)
     assert np.array_equal(o["dynamic"][-1], fin)
+
+
+@pytest.mark.parametrize("dim,fixture,size", [(2, "rand2d_n10.npz", [5, 50]), (3, "rand3d_n10.npz", [5, 5, 50])])
+def test_g6_pretrained_network_tours(dim, fixture, size):
+    """G6: tours chosen by the UNMODIFIED reference model.DRL + shipped pretrained actor (greedy), with
+    the rewards DRL.forward returned; the oracle replaying those tours must reproduce the rewards (network-in-the-loop pin)."""
+    z = np.load(golden_path("g6_tours.npz"))
+    num = int(z["g6_%dd_num" % dim])
+    static, dynamic = load_inputs(fixture, num)
+    tour = z["g6_%dd_tour" % dim]
+    o = oracle.episode_batch(static, dynamic, tour.T.copy(), size, "C+P+S-lb-soft", "diff", "LB_GREEDY", want=("reward", "mask"))
+    assert o["status"] == 0 and float(o["mask"].sum()) == 0.0            # the network's tours visit every block exactly once
+    assert np.abs(o["reward"].astype(np.float64) + z["g6_%dd_reward" % dim].astype(np.float64)).max() <= 1e-6
