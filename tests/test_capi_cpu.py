@@ -124,3 +124,24 @@ def test_pack_inputs_layout():
     import tapenv
     cfg = tapenv.make_config(B, 10, [5, 5, 50])
     assert int(tapenv._capi.lib.tapenv_packed_words(C.byref(cfg))) == bits.shape[1]
+
+
+def test_host_batch_layout_is_aligned_and_disjoint():
+    """The staging layout shared by HostPipeline's device buffers and HostBatch (one contiguous upload): 256-byte aligned
+    sections, disjoint, exact views."""
+    import torch
+    from tapenv.runner import _carve, _carve_bytes
+    specs = [(torch.float32, (1, 7, 3, 20)), (torch.float32, (1, 7, 30, 20)), (torch.int64, (1, 10, 7)), (torch.uint8, (7, 3, 20))]
+    nbytes = _carve_bytes(specs)
+    buf = torch.zeros(nbytes, dtype=torch.uint8)
+    views = _carve(buf, specs)
+    base = buf.data_ptr()
+    spans = []
+    for v, (dt, shape) in zip(views, specs):
+        assert v.dtype == dt and tuple(v.shape) == tuple(shape) and v.is_contiguous()
+        off = v.data_ptr() - base
+        assert off % 256 == 0 and off + v.numel() * v.element_size() <= nbytes
+        spans.append((off, off + v.numel() * v.element_size()))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    views[2].fill_(5)
+    assert int(buf.sum()) == 5 * 70 and int(views[0].abs().sum()) == 0      # writes land only in their own section
