@@ -241,6 +241,13 @@ typedef struct tapenv_peer_comm {
     void *peer[TAPENV_COMM_MAX_RANKS];
 } tapenv_peer_comm;
 size_t tapenv_comm_bytes(void);
+/* Byte offset, inside every rank's exchange buffer, of two u64 words: a STICKY status (0 = healthy; bit 0 = a call gave up
+ * polling for a peer -- its total_sums_out are NaN) followed by the number of the first call that failed.  A call polls
+ * for at most TAPENV_EXCHANGE_TIMEOUT_MS (environment, default 10000 ms, measured on %globaltimer): the bound must exceed the
+ * worst rank skew of the job (checkpointing / logging on one rank, a loader stall, first-iteration warm-up); it exists so
+ * that a peer which never calls cannot hang the GPU.  After a timeout the ranks' call counters may disagree: treat the
+ * status as fatal for the exchange (re-create the buffers, or fall back to an NCCL all-gather of the triples). */
+size_t tapenv_comm_status_offset(void);
 int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *reward_out, double *partial_sums_out,
                             double *total_sums_out, const tapenv_peer_comm *comm, void *stream);
 

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* Python reference.
 
-Imports /root/reference's ``tools``/``pack``/``generate`` modules in THIS
-container so that (a) the C restatement in ``oracle/tap_oracle.c`` can be
-validated against the real thing and (b) golden vectors can be generated
-(``tests/golden/make_golden.py``).  The reference cannot travel to the GPU box,
-so nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this.
+Imports the reference's ``tools``/``pack``/``generate``/``model`` modules so that (a) the C restatement in
+``oracle/tap_oracle.c`` can be validated against the real thing, (b) golden vectors can be generated
+(``tests/golden/make_golden.py``), (c) the model-in-the-loop GPU tests and bench.py's reference arm can run the real
+``model.DRL`` / ``tools.Container``.  Where the modules come from: ``$TAPNET_REFERENCE`` if set, else /root/reference (the
+build container), else oracle/_ref/ -- the byte-for-byte staged copy ``oracle/stage_ref.py`` makes (git-ignored; it is what
+travels to the GPU box, where /root/reference does not exist).  Nothing under tap-net_b200/ imports this.
 
 Three shims are needed:
   1. ``numpy.math`` was removed in NumPy 2 (used at pack.py:109,309,365).
@@ -19,7 +20,30 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("TAPNET_REFERENCE", "/root/reference")
+STAGED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve():
+    env = os.environ.get("TAPNET_REFERENCE")
+    if env:
+        return env
+    for cand in ("/root/reference", STAGED_DIR):
+        if os.path.isfile(os.path.join(cand, "tools.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_DIR = _resolve()
+
+
+def staged():
+    """True when the modules come from the staged copy (oracle/_ref/), i.e. on the GPU box."""
+    return os.path.abspath(REFERENCE_DIR) == os.path.abspath(STAGED_DIR)
+
+
+def checkpoint(name):
+    """Path of a shipped pretrained actor, e.g. '2d-bot-C+P+S-lb-soft-width-5-note-sh-R-diff'."""
+    return os.path.join(REFERENCE_DIR, "pretrain_model", name, "actor.pt")
 
 
 def available():

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stddef.h>
 
 #include "../../include/tapenv.h"
 #include "tapenv_common.cuh"
@@ -878,10 +879,31 @@ __global__ void reward_sums_kernel(int B, const float *__restrict__ reward, doub
 constexpr int kCommDepth = 4;
 constexpr int kCommWords = 6;
 struct CommSlot { unsigned long long w[8]; };           // 6 used; 64-byte stride
-struct CommBuf { CommSlot slot[kCommDepth][TAPENV_COMM_MAX_RANKS]; unsigned long long calls; unsigned long long pad[7]; };
+// status: sticky, 0 = healthy; bit 0 = a call gave up waiting for a peer (its totals are NaN).  failed_seq: first such call.
+struct CommBuf { CommSlot slot[kCommDepth][TAPENV_COMM_MAX_RANKS]; unsigned long long calls, status, failed_seq; unsigned long long pad[5]; };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// How long a call polls for its peers before it gives up (TAPENV_EXCHANGE_TIMEOUT_MS, default 10 s).  The bound exists so that
+// a peer that never calls cannot hang the GPU; it must exceed the worst rank skew of the job (checkpointing or logging on
+// one rank, a data-loader stall, first-iteration warm-up).  A timeout is NOT silent: the call writes NaN totals AND sets the
+// sticky status word of this rank's exchange buffer (tapenv_comm_status_offset; PeerExchange.check() raises).
+static long long exchange_timeout_ns() {
+    static const long long ns = [] {
+        const char *e = getenv("TAPENV_EXCHANGE_TIMEOUT_MS");
+        long long ms = e ? atoll(e) : 10000;
+        if (ms < 1) ms = 1;
+        return ms * 1000000ll;
+    }();
+    return ns;
+}
 
 __global__ void reward_sums_exchange_kernel(int B, const float *__restrict__ reward, double *__restrict__ out,
-                                            double *__restrict__ total, tapenv_peer_comm comm) {
+                                            double *__restrict__ total, tapenv_peer_comm comm, long long timeout_ns) {
     __shared__ double s1[1024], s2[1024];
     __shared__ unsigned long long seq_sh;
     __shared__ unsigned got[TAPENV_COMM_MAX_RANKS][kCommWords];
@@ -915,20 +937,32 @@ __global__ void reward_sums_exchange_kernel(int B, const float *__restrict__ rew
         // wait for word wq of peer r's triple in MY buffer
         volatile unsigned long long *src = mine->slot[seq % kCommDepth][r].w;
         unsigned long long v = src[wq];
-        for (long long spins = 0; (unsigned)v != tag && spins < (1ll << 24); ++spins) v = src[wq];   // seconds: a peer that never calls must not hang the GPU
+        if ((unsigned)v != tag) {
+            const unsigned long long t0 = global_timer_ns();
+            for (;;) {
+                for (int spins = 0; (unsigned)v != tag && spins < 256; ++spins) v = src[wq];
+                if ((unsigned)v == tag || (long long)(global_timer_ns() - t0) > timeout_ns) break;
+            }
+        }
         if ((unsigned)v != tag) okf = 0;
         got[r][wq] = (unsigned)(v >> 32);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && total) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int k = 0; k < comm.world; ++k) {                               // rank order
-            t0 += __hiloint2double((int)got[k][1], (int)got[k][0]);
-            t1 += __hiloint2double((int)got[k][3], (int)got[k][2]);
-            t2 += __hiloint2double((int)got[k][5], (int)got[k][4]);
+    if (threadIdx.x == 0) {
+        if (!okf) {                                                          // sticky: the host side raises on it
+            if (mine->status == 0ull) mine->failed_seq = seq;
+            mine->status |= 1ull;
         }
-        const double bad = nan("");
-        total[0] = okf ? t0 : bad; total[1] = okf ? t1 : bad; total[2] = okf ? t2 : bad;
+        if (total) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int k = 0; k < comm.world; ++k) {                           // rank order
+                t0 += __hiloint2double((int)got[k][1], (int)got[k][0]);
+                t1 += __hiloint2double((int)got[k][3], (int)got[k][2]);
+                t2 += __hiloint2double((int)got[k][5], (int)got[k][4]);
+            }
+            const double bad = nan("");
+            total[0] = okf ? t0 : bad; total[1] = okf ? t1 : bad; total[2] = okf ? t2 : bad;
+        }
     }
 }
 
@@ -1300,7 +1334,7 @@ int tapenv_reward_sums(const tapenv_config *cfg, const float *reward, double *pa
         if (comm->world < 1 || comm->world > TAPENV_COMM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world || !total_sums_out)
             return TAPENV_EINVAL;
         for (int r = 0; r < comm->world; ++r) if (!comm->peer[r]) return TAPENV_EINVAL;
-        launch(reward_sums_exchange_kernel, 1, 1024, s, (int)cfg->batch, reward, partial_sums_out, total_sums_out, *comm);
+        launch(reward_sums_exchange_kernel, 1, 1024, s, (int)cfg->batch, reward, partial_sums_out, total_sums_out, *comm, exchange_timeout_ns());
     } else {
         launch(reward_sums_kernel, 1, 1024, s, (int)cfg->batch, reward, partial_sums_out);
     }
@@ -1320,6 +1354,7 @@ int tapenv_reward(const tapenv_config *cfg, const void *state, float *reward_out
 }
 
 size_t tapenv_comm_bytes(void) { return sizeof(CommBuf); }
+size_t tapenv_comm_status_offset(void) { return offsetof(CommBuf, status); }
 
 int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *reward_out, double *partial_sums_out,
                             double *total_sums_out, const tapenv_peer_comm *comm, void *stream) {
@@ -1333,7 +1368,7 @@ int tapenv_reward_allreduce(const tapenv_config *cfg, const void *state, float *
     const DevCfg d = devcfg_of(cfg);
     const StatePtrs st = stateptrs_of(cfg, const_cast<void *>(state));
     if (d.B > 0) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
-    launch(reward_sums_exchange_kernel, 1, 1024, s, d.B, reward_out, partial_sums_out, total_sums_out, *comm);
+    launch(reward_sums_exchange_kernel, 1, 1024, s, d.B, reward_out, partial_sums_out, total_sums_out, *comm, exchange_timeout_ns());
     return launch_status();
 }
 

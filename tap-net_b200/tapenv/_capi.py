@@ -60,6 +60,7 @@ SYMBOLS = {
     "tapenv_reward_sums": (c_int, [CFG, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_reward": (c_int, [CFG, P, P, P, P]),
     "tapenv_comm_bytes": (c_size_t, []),
+    "tapenv_comm_status_offset": (c_size_t, []),
     "tapenv_reward_allreduce": (c_int, [CFG, P, P, P, P, C.POINTER(PeerComm), P]),
     "tapenv_episode": (c_int, [CFG, P, P, P, P, c_int32, P, P, P, P, P]),
     "tapenv_packed_words": (c_int32, [CFG]),

@@ -217,11 +217,15 @@ class BatchedContainers(object):
                                                          _p(dec_dyn), _p(reward_out), _stream()), "step_reward")
         return dyn_out, cur, mask_out, dec_static, self._shape_enc(dec_dyn)
 
-    def reward_sums(self, reward, exchange=None):
+    def reward_sums(self, reward, exchange=None, out=None):
         """(sum r, sum r^2, B) of a reward vector produced by step(..., reward_out=) -> f64 [3]; with exchange=PeerExchange
-        -> (local sums, global sums), the cross-GPU reduction in the same launch (see calc_ratio)."""
-        sums = torch.empty(3, dtype=torch.float64, device=self.device)
-        total = torch.empty(3, dtype=torch.float64, device=self.device) if exchange is not None else None
+        -> (local sums, global sums), the cross-GPU reduction in the same launch (see calc_ratio).
+        out=(sums, total) preallocated f64 [3] buffers (total ignored without an exchange)."""
+        if out is not None:
+            sums, total = out[0], (out[1] if exchange is not None else None)
+        else:
+            sums = torch.empty(3, dtype=torch.float64, device=self.device)
+            total = torch.empty(3, dtype=torch.float64, device=self.device) if exchange is not None else None
         with torch.cuda.device(self.device):
             _capi.check(_capi.lib.tapenv_reward_sums(C.byref(self.cfg), _p(reward), _p(sums), _p(total),
                                                      C.byref(exchange.comm) if exchange is not None else None, _stream()), "reward_sums")

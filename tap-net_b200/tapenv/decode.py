@@ -50,6 +50,8 @@ class DecodeLoop(object):
                 ptr = torch.multinomial(probs, 1, generator=self.generator).squeeze(1)     # Categorical(probs).sample(), model.py:362-364
                 logp = torch.log(torch.gather(probs, 1, ptr.unsqueeze(1)).squeeze(1))      # m.log_prob(ptr), model.py:368
             dynamic, current_mask, mask, dec_static, dec_dyn = env.step(ptr, static, dynamic, mask)   # model.py:376-463
+            if hasattr(state, "last_ptr"):
+                state.last_ptr = ptr                                             # tapenv.adapters: rows zeroed by this step
             idx.append(ptr)
             logps.append(logp)
         reward = env.calc_ratio()                                                # model.py:499-515

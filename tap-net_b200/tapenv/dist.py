@@ -90,7 +90,13 @@ class RewardReducer(object):
 class PeerExchange(object):
     """Peer-mapped exchange buffers for tapenv_reward_allreduce (the reward-statistics reduction fused behind the
     reward kernel, over NVLink peer memory).  One per process group; needs torch symmetric memory (CUDA P2P between
-    the ranks' GPUs on one node).  Raises if that is unavailable -- callers then use combine_partial_sums (NCCL)."""
+    the ranks' GPUs on one node).  Raises if that is unavailable -- callers then use combine_partial_sums (NCCL).
+
+    `stream`: a high-priority side stream the runners launch the exchange on, so that the poll for the slowest rank sits
+    BESIDE the next episode's kernels instead of in front of them (nothing on the environment path consumes the totals;
+    the trainer's loss does, trainer.py:216-225).
+    Rank skew: a call polls for its peers for at most TAPENV_EXCHANGE_TIMEOUT_MS (default 10 s); a timeout yields NaN totals
+    and a sticky status that `check()` (called by the runners' / pipelines' result paths) turns into a RuntimeError."""
 
     def __init__(self, device, group=None):
         import ctypes as C
@@ -113,3 +119,20 @@ class PeerExchange(object):
             comm.peer[r] = C.c_void_p(int(ptrs[r]))
         self.comm = comm
         self.world, self.rank = world, rank
+        self.device = torch.device(device)
+        lo, hi = torch.cuda.Stream.priority_range()            # (lowest, highest): numerically larger = lower priority
+        self.stream = torch.cuda.Stream(device=self.device, priority=hi)
+        off = int(_capi.lib.tapenv_comm_status_offset())
+        self._status = self.buf[off: off + 16].view(torch.int64)   # [status, first failed call]
+
+    def status(self):
+        """(status, first_failed_call) of this rank's buffer; synchronises with the device."""
+        st = self._status.cpu()
+        return int(st[0]), int(st[1])
+
+    def check(self):
+        st, seq = self.status()
+        if st != 0:
+            raise RuntimeError("tapenv: the NVLink reward exchange timed out waiting for a peer (rank %d, first failed call %d): "
+                               "its totals are NaN.  Raise TAPENV_EXCHANGE_TIMEOUT_MS above the job's worst rank skew, or "
+                               "use tapenv.dist.combine_partial_sums (NCCL)." % (self.rank, seq))

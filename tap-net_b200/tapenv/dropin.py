@@ -7,12 +7,33 @@
     tapenv.uninstall()
 
 Replaces exactly the hot-path symbols: pack.update_dynamic, pack.update_mask, pack.reward,
-tools.Container, tools.calc_positions_lb_greedy (and generate.InitialContainer when `generate` is passed).  Everything else of the reference keeps running as it is."""
+tools.Container, tools.calc_positions_lb_greedy, tools.calc_positions_mcs (and generate.InitialContainer when `generate` is
+passed).  Everything else of the reference keeps running as it is.  The two whole-episode functions fall back to the saved
+reference function for shapes beyond the compiled limits (e.g. the 7x7 initial container of the 3D generators has 49 cells,
+tapenv_limits.max_cells_3d is 32) -- the dataset generators call them with containers the network never sees."""
+import functools
 import sys
 
-from . import containers, episode, ops, rolling
+from . import _capi, containers, episode, ops, rolling
 
 _saved = []
+
+
+def _with_fallback(ours, original):
+    """ours(...) unless the configuration is outside the compiled limits / unsupported; then the reference's own function."""
+    if original is None:
+        return ours
+
+    @functools.wraps(ours)
+    def call(blocks, container_size, reward_type):
+        try:
+            return ours(blocks, container_size, reward_type)
+        except _capi.TapEnvError as e:
+            if e.code in (_capi.ELIMIT, _capi.EUNSUPPORTED):
+                return original(blocks, container_size, reward_type)
+            raise
+    call.tapenv_original = original
+    return call
 
 
 def install(pack=None, tools=None, generate=None):
@@ -28,7 +49,10 @@ def install(pack=None, tools=None, generate=None):
                  (pack, "reward", episode.reward)]
     if tools is not None:
         repl += [(tools, "Container", containers.Container),
-                 (tools, "calc_positions_lb_greedy", episode.calc_positions_lb_greedy)]
+                 (tools, "calc_positions_lb_greedy",
+                  _with_fallback(episode.calc_positions_lb_greedy, getattr(tools, "calc_positions_lb_greedy", None))),
+                 (tools, "calc_positions_mcs",
+                  _with_fallback(episode.calc_positions_mcs, getattr(tools, "calc_positions_mcs", None)))]
     if generate is not None:
         repl += [(generate, "InitialContainer", rolling.InitialContainer)]
     for mod, name, new in repl:

@@ -28,6 +28,32 @@ def _pack_sequence(blocks, container_size, reward_type, packing_strategy):
     return env, single
 
 
+def voxel_container(positions, blocks, container_size):
+    """The reference's voxel grid (0 empty / -1 "empty under a block" / k+1 block id) that calc_positions_* return in
+    second place, rebuilt on the host from the placements the kernels recorded: block k writes k+1 into its extent and -1
+    into the still-empty cells below it (tools.py:2168-2169, :2661-2665, :3045-3049), in arrival order.  A block that was
+    not placed (its position stays at the origin, tools.py:2084-2087) is recognised by replaying the heightmap: a placed
+    block always sits exactly on the highest column under its footprint."""
+    size = [int(v) for v in container_size]
+    dim = len(size)
+    grid = np.zeros(size, dtype=int)
+    h = np.zeros(size[:-1], dtype=int)
+    for k in range(len(blocks)):
+        b = [int(v) for v in blocks[k]]
+        p = [int(v) for v in positions[k]]
+        foot = tuple(slice(p[d], p[d] + b[d]) for d in range(dim - 1))
+        if any(b[d] < 1 or p[d] + b[d] > size[d] for d in range(dim - 1)) or b[-1] < 1:
+            continue                                   # no EMS for this block: not placed
+        if int(h[foot].max()) != p[-1]:
+            continue                                   # not resting on its footprint: not placed
+        z = p[-1]
+        under = grid[foot + (slice(0, z),)]
+        under[under == 0] = -1
+        grid[foot + (slice(z, z + b[-1]),)] = k + 1
+        h[foot] = z + b[-1]
+    return grid
+
+
 def _result(env, single):
     sc = env.scalars.to(torch.float64)
     valid, empty, nstable = sc[:, 0], sc[:, 1], sc[:, 2]
@@ -38,17 +64,18 @@ def _result(env, single):
     ratio = valid / box + valid / (empty + valid) + nstable / n          # C + P + S, NOT divided by 3 (tools.py:2438-2446)
     scores = torch.stack([sc[:, 0], box, sc[:, 1], sc[:, 2], hmax.to(torch.float64)], 1).to(torch.int64)
     positions, stable, heightmap = env.positions.clone(), env.stable.bool(), env.heightmap.clone()
-    if single:
-        return (positions[0].cpu().numpy().astype(np.int64), heightmap[0].cpu().numpy().astype(np.int64),
-                [bool(v) for v in stable[0].tolist()], float(ratio[0].item()), [int(v) for v in scores[0].tolist()])
+    if single:                                         # the reference's call form: the voxel `container` in second place
+        pos = positions[0].cpu().numpy().astype(np.int64)
+        grid = voxel_container(pos, env.blocks[0].cpu().numpy(), env.container_size)
+        return (pos, grid, [bool(v) for v in stable[0].tolist()], float(ratio[0].item()), [int(v) for v in scores[0].tolist()])
     return positions, heightmap, stable, ratio, scores
 
 
 def calc_positions_lb_greedy(blocks, container_size, reward_type):
-    """blocks [n,dim] (reference form) or [B,n,dim] (batched).  Returns (positions, heightmap, stable, ratio, scores)
-    with ratio = C+P+S and scores = [valid_size, box_size, empty_size, stable_num, packing_height].
-    The reference returns its voxel `container` in second place; the heightmap carries the same information
-    (cell != 0 <=> z < heightmap) and is what is returned here."""
+    """blocks [n,dim] (reference form) -> (positions, container, stable, ratio, scores) exactly as tools.py:2393-2449:
+    `container` is the voxel grid (generate.calc_dependent indexes it, generate.py:112,:908), ratio = C+P+S and
+    scores = [valid_size, box_size, empty_size, stable_num, packing_height].
+    blocks [B,n,dim] (batched extension, device tensors out) -> the heightmap [B,W(,L)] stands in second place."""
     env, single = _pack_sequence(blocks, container_size, reward_type, "LB_GREEDY")
     return _result(env, single)
 

@@ -152,7 +152,8 @@ class RollingRunner(object):
     (one_step=True), the last completely.  `step(ptr)` is one launch while windows remain, the fused decode step
     (tapenv_step) inside the last window."""
 
-    def __init__(self, env, windows, ptr_seq=None, use_graph=False, partial_sums=True, exchange=None):
+    def __init__(self, env, windows, ptr_seq=None, use_graph=False, partial_sums=True, exchange=None, overlap_exchange=None):
+        from .runner import RewardTail
         assert isinstance(env, BatchedContainers) and isinstance(windows, BatchedInitialContainers)
         assert env.batch_size == windows.batch_size and env.window == windows.child_graph_size
         assert env.blocks_num >= windows.blocks_num, "the container must hold total_blocks_num blocks (rolling.py:702-703)"
@@ -174,11 +175,11 @@ class RollingRunner(object):
         self.ptr_seq = ptr_seq
         self.partial_sums = partial_sums
         self.exchange = exchange
-        self.reward = self.sums = self.total_sums = None
+        self.tail = RewardTail(env, partial_sums, exchange, overlap_exchange)
+        self.reward = None
         self.reward_buf = None
-        # clear + window reset + first window + T steps + reward (+ sums)
         # clear + window reset + first window, T steps (the last also emits the rewards), the sums (+ exchange) launch
-        self.launches_per_episode = 3 + self.total + (1 if (partial_sums or exchange is not None) else 0)
+        self.launches_per_episode = 3 + self.total + self.tail.launches
         self.graph = None
         if use_graph:
             assert ptr_seq is not None
@@ -240,12 +241,15 @@ class RollingRunner(object):
         for t in range(self.total):
             self.step(self.ptr_seq[t], reward_out=self.reward_buf if t == self.total - 1 else None)   # calc_ratio rides on the last step
         self.reward = self.reward_buf
-        if self.exchange is not None:
-            self.sums, self.total_sums = self.env.reward_sums(self.reward, exchange=self.exchange)
-        elif self.partial_sums:
-            self.sums = self.env.reward_sums(self.reward)
-        else:
-            self.sums = None
+        self.tail.inline(self.reward)
+
+    @property
+    def sums(self):
+        return self.tail.sums
+
+    @property
+    def total_sums(self):
+        return self.tail.total
 
     def _capture(self):
         dev = self.env.device
@@ -266,10 +270,12 @@ class RollingRunner(object):
         if ptr_seq is not None:
             assert self.graph is None, "a captured runner replays its own ptr_seq buffer"
             self.ptr_seq = ptr_seq
+        self.tail.before_episode()
         if self.graph is not None:
             self.graph.replay()
         else:
             self._episode()
+        self.tail.after_episode(self.reward)
         return self.reward
 
 
@@ -321,8 +327,13 @@ class RollingHostPipeline(object):
         if after_episode is not None:
             after_episode(s["runner"])
         s["reward"].copy_(r, non_blocking=True)
-        run = s["runner"]
-        s["sums"].copy_(run.total_sums if run.total_sums is not None else run.sums, non_blocking=True)
+        tail = s["runner"].tail
+        if tail.overlap:                                         # the totals arrive on the exchange's side stream
+            with torch.cuda.stream(tail.exchange.stream):
+                s["sums"].copy_(tail.total, non_blocking=True)
+                tail.reduced.record(tail.exchange.stream)
+        else:
+            s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
         s["done"].record(compute)
         s["busy"] = True
         self.head = (self.head + 1) % self.depth
@@ -333,6 +344,11 @@ class RollingHostPipeline(object):
             raise RuntimeError("nothing in flight")
         s = self.slots[self.tail]
         s["done"].synchronize()
+        tail = s["runner"].tail
+        if tail.overlap:
+            tail.reduced.synchronize()
+        if tail.exchange is not None and s["sums"][0] != s["sums"][0]:      # NaN totals: the exchange timed out on a peer
+            tail.exchange.check()
         self.tail = (self.tail + 1) % self.depth
         self.inflight -= 1
         return s["reward"], s["sums"]

@@ -9,20 +9,75 @@ import torch
 from .containers import BatchedContainers
 
 
+class RewardTail(object):
+    """The end of an episode: the deterministic (sum r, sum r^2, B) of the reward vector and, on several GPUs, the exchange
+    of those triples (tapenv_reward_sums / PeerExchange) -- the operand of the critic-baseline statistics
+    (trainer.py:216-225).
+
+    overlap=False: one launch at the tail of the episode (captured in its CUDA graph).
+    overlap=True (default with an exchange): the launch goes to the exchange's high-priority side stream right behind the
+    last decode step; the next episode's reset does NOT wait for the poll on the slowest rank (r01: the in-stream poll
+    cost ~4 us per 62 us episode at 8 GPUs).  `sums` / `total` are then valid after `reduced` (wait_total())."""
+
+    def __init__(self, env, partial_sums=True, exchange=None, overlap=None):
+        self.env, self.exchange = env, exchange
+        self.enabled = bool(partial_sums) or exchange is not None
+        self.overlap = (exchange is not None) if overlap is None else (bool(overlap) and exchange is not None)
+        dev = env.device
+        self.sums = torch.zeros(3, dtype=torch.float64, device=dev) if self.enabled else None
+        self.total = torch.zeros(3, dtype=torch.float64, device=dev) if exchange is not None else None
+        self.posted = torch.cuda.Event()
+        self.reduced = torch.cuda.Event()
+        self.pending = False
+
+    @property
+    def launches(self):
+        return 1 if self.enabled else 0
+
+    def inline(self, reward):
+        """Inside the episode's launch sequence (graph-capturable)."""
+        if self.enabled and not self.overlap:
+            self.env.reward_sums(reward, exchange=self.exchange, out=(self.sums, self.total))
+
+    def before_episode(self):
+        """The previous use of this runner's reward / sums buffers must have been consumed by its exchange."""
+        if self.overlap and self.pending:
+            torch.cuda.current_stream(self.env.device).wait_event(self.reduced)
+            self.pending = False
+
+    def after_episode(self, reward):
+        if not (self.enabled and self.overlap):
+            return
+        cur = torch.cuda.current_stream(self.env.device)
+        xs = self.exchange.stream
+        self.posted.record(cur)
+        xs.wait_event(self.posted)
+        with torch.cuda.stream(xs):
+            self.env.reward_sums(reward, exchange=self.exchange, out=(self.sums, self.total))
+            self.reduced.record(xs)
+        self.pending = True
+
+    def wait_total(self):
+        """Make the current stream wait for the (overlapped) exchange of the last episode."""
+        if self.overlap and self.pending:
+            torch.cuda.current_stream(self.env.device).wait_event(self.reduced)
+
+
 class EpisodeRunner(object):
     """static [B,rows,S] / dynamic [B,3n,S] / ptr_seq [steps,B]  -- one window per episode (training), or the same
     tensors with a leading window axis ([Wn,B,...], [Wn,B,...], [Wn,steps,B]) for rolling-style episodes in which ONE
     container keeps filling while the network window is refilled Wn times (rolling.py:575-658): the container
     is cleared once, every later window only recomputes the masks (BatchedContainers.initial_mask)."""
 
-    def __init__(self, env, static, dynamic, ptr_seq, use_graph=False, partial_sums=True, exchange=None, packed=None):
+    def __init__(self, env, static, dynamic, ptr_seq, use_graph=False, partial_sums=True, exchange=None, packed=None,
+                 overlap_exchange=None):
         assert isinstance(env, BatchedContainers)
         self.env = env
+        self.tail = RewardTail(env, partial_sums, exchange, overlap_exchange)
         # packed = (static_u8 [B,rows,S] uint8, dynamic_bits [B,words] int32) device buffers in the compact upload format
         # (tapenv.pack_inputs): the episode then starts with reset_packed, which fills `static` / `dynamic` from them
         self.packed = packed
         self.exchange = exchange                      # tapenv.dist.PeerExchange: fuse the cross-GPU reward reduction
-        self.total = None
         dev = env.device
         B, S = env.batch_size, env.S
         if static.dim() == 3:
@@ -40,10 +95,9 @@ class EpisodeRunner(object):
         self.dec_dyn = torch.empty(B, env.enc_len, **f32)
         self.reward_buf = torch.empty(B, **f32)
         self.reward = None
-        self.sums = None
         self.partial_sums = partial_sums
         # reset / initial mask + fused steps per window (the last one also emits the rewards) + the sums (+ exchange) launch
-        self.launches_per_episode = self.windows * (1 + self.steps) + (1 if (partial_sums or exchange is not None) else 0)
+        self.launches_per_episode = self.windows * (1 + self.steps) + self.tail.launches
         self.graph = None
         if use_graph:
             self._capture()
@@ -66,13 +120,16 @@ class EpisodeRunner(object):
         self.reward = self.reward_buf
         if self.steps == 0:
             self.reward = env.calc_ratio()
-        if self.exchange is not None:
-            self.sums, self.total = env.reward_sums(self.reward, exchange=self.exchange)
-        elif self.partial_sums:
-            self.sums = env.reward_sums(self.reward)
-        else:
-            self.sums = None
+        self.tail.inline(self.reward)
         self.final = (dyn, cur, mask)
+
+    @property
+    def sums(self):
+        return self.tail.sums
+
+    @property
+    def total(self):
+        return self.tail.total
 
     def _capture(self):
         s = torch.cuda.Stream(device=self.env.device)
@@ -87,11 +144,14 @@ class EpisodeRunner(object):
         self.graph = g
 
     def run(self):
-        """One episode for the whole batch; returns the f32 [B] reward tensor (calc_ratio, not negated)."""
+        """One episode for the whole batch; returns the f32 [B] reward tensor (calc_ratio, not negated).
+        With an overlapped exchange `sums` / `total` belong to the exchange's side stream: tail.wait_total() first."""
+        self.tail.before_episode()
         if self.graph is not None:
             self.graph.replay()
         else:
             self._episode()
+        self.tail.after_episode(self.reward)
         return self.reward
 
 
@@ -204,7 +264,13 @@ class HostPipeline(object):
         if after_episode is not None:
             after_episode(s["runner"])                           # e.g. the cross-rank reduction of runner.sums
         s["reward"].copy_(r, non_blocking=True)
-        s["sums"].copy_(s["runner"].total if s["runner"].total is not None else s["runner"].sums, non_blocking=True)
+        tail = s["runner"].tail
+        if tail.overlap:                                         # the totals arrive on the exchange's side stream
+            with torch.cuda.stream(tail.exchange.stream):
+                s["sums"].copy_(tail.total, non_blocking=True)
+                tail.reduced.record(tail.exchange.stream)        # "consumed" now includes the D2H read of the totals
+        else:
+            s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
         s["done"].record(compute)
         s["busy"] = True
         self.head = (self.head + 1) % self.depth
@@ -215,6 +281,11 @@ class HostPipeline(object):
             raise RuntimeError("nothing in flight")
         s = self.slots[self.tail]
         s["done"].synchronize()
+        tail = s["runner"].tail
+        if tail.overlap:
+            tail.reduced.synchronize()
+        if tail.exchange is not None and s["sums"][0] != s["sums"][0]:      # NaN totals: the exchange timed out on a peer
+            tail.exchange.check()
         self.tail = (self.tail + 1) % self.depth
         self.inflight -= 1
         return s["reward"], s["sums"]
