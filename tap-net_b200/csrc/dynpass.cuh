@@ -34,27 +34,35 @@ __device__ __forceinline__ unsigned nz_bits(unsigned w) { return (w & 0x7fffffff
 // CHP = passes per chunk: all loads of a chunk (CHP * 3 vectors per lane) are issued before the first use.
 // load() and process() are separate so that a kernel can put chunk 0 in flight BEFORE it waits for the
 // pointer / block id it needs to process it.
-template <class SH, int CHP>
+// TPE = threads that share one environment's tensor (32: one warp per environment, `lane` is the lane; 32*CW: the CW copy
+// warps of a CTA-per-environment launch, `lane` is the thread index inside that group -- a row pass then covers
+// TPE/SV rows, so the same tensor needs proportionally fewer dependent chunks per thread).
+template <class SH, int CHP, int TPE = 32>
 struct DynPassFast {
     uint4 acc[3];
     uint4 v[CHP][3];
     int rsub, cv;
     bool lane_on;
 
+    __device__ __forceinline__ static int RPg(const DevCfg &c) { return TPE == 32 ? SH::RP(c) : (SH::fixed ? TPE / SH::SVc : TPE / c.SV); }
+    __device__ __forceinline__ static int PBg(const DevCfg &c) {
+        return TPE == 32 ? SH::PB(c) : (SH::fixed ? (SH::NTc + TPE / SH::SVc - 1) / (TPE / SH::SVc) : (c.n + RPg(c) - 1) / RPg(c));
+    }
+
     __device__ __forceinline__ void init(const DevCfg &c, int lane) {
         acc[0] = acc[1] = acc[2] = make_uint4(0u, 0u, 0u, 0u);
         rsub = SH::div_SV(c, lane);
         cv = lane - rsub * SH::SV(c);              // vector index of (band 0, pass 0) for this lane == lane
-        lane_on = rsub < SH::RP(c);
+        lane_on = rsub < RPg(c);
     }
 
     __device__ __forceinline__ bool on(const DevCfg &c, int p) const {
-        return lane_on && p * SH::RP(c) + rsub < SH::n(c) && p < SH::PB(c);
+        return lane_on && p * RPg(c) + rsub < SH::n(c) && p < PBg(c);
     }
 
     __device__ __forceinline__ void load(const DevCfg &c, const float *din, int lane, int p0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(din) + lane;
-        const int pstride = SH::RP(c) * SH::SV(c), bstride = SH::n(c) * SH::SV(c), nb = SH::nbands(c);
+        const int pstride = RPg(c) * SH::SV(c), bstride = SH::n(c) * SH::SV(c), nb = SH::nbands(c);
 #pragma unroll
         for (int i = 0; i < CHP; ++i) {
             const bool o = on(c, p0 + i);
@@ -69,7 +77,7 @@ struct DynPassFast {
     // real < 0: no row is zeroed.  dout == nullptr: no copy is written.
     __device__ __forceinline__ void process(const DevCfg &c, float *dout, int lane, int p0, int real) {
         uint4 *dst = reinterpret_cast<uint4 *>(dout) + lane;
-        const int RP = SH::RP(c), nb = SH::nbands(c), ut = SH::update_time(c);
+        const int RP = RPg(c), nb = SH::nbands(c), ut = SH::update_time(c);
         const int pstride = RP * SH::SV(c), bstride = SH::n(c) * SH::SV(c);
         const int zrow = real - rsub;                        // pass p zeroes this lane's row iff p*RP == zrow
 #pragma unroll
@@ -89,7 +97,7 @@ struct DynPassFast {
     __device__ __forceinline__ void finish(const DevCfg &c, const float *din, float *dout, int lane, int real) {
         process(c, dout, lane, 0, real);
 #pragma unroll
-        for (int p0 = CHP; p0 < SH::PB(c); p0 += CHP) {
+        for (int p0 = CHP; p0 < PBg(c); p0 += CHP) {
             load(c, din, lane, p0);
             process(c, dout, lane, p0, real);
         }

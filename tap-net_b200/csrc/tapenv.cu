@@ -623,6 +623,73 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
 }
 
 // ------------------------------------------------------------------------------------
+// The fused decode step, CTA-per-environment form: CW "copy" warps share the precedence tensor of ONE environment (a row
+// pass covers 32*CW/SV rows, so every thread has its whole share in flight at once) while ONE more warp runs the
+// placement on the register-resident heightmap at the same time; the column bits meet in shared memory for the masks.
+// Chosen when a warp-per-environment grid would leave the machine mostly empty (BASELINE C4: 1 024 environments per GPU =
+// 7 warps per SM, 9.6 kB of `dynamic` each, four dependent load chunks per lane and the serial MACS scan behind them:
+// r01 10.5 us per launch, 0.31 of the HBM roofline, 10 % warps active).
+// ------------------------------------------------------------------------------------
+#ifndef TAPENV_SPLIT_CW
+#define TAPENV_SPLIT_CW 4
+#endif
+template <int STRAT, int NT, int RT, int CW>
+__global__ void __launch_bounds__(32 * (CW + 1))
+step_split_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float *__restrict__ static_,
+                  const float *__restrict__ dynamic_in, const float *__restrict__ mask_in, float *__restrict__ dynamic_out,
+                  float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static,
+                  float *__restrict__ dec_dyn, float *__restrict__ reward) {
+    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    constexpr int TPE = 32 * CW;
+    typedef Shape<NT, RT, DIM> SH;
+    __shared__ unsigned long long sbits[CW][3];
+    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    grid_dependency_sync();
+    const int S = SH::S(c);
+    const float *srow = env_ptr(static_, b, SH::static_env(c));
+    const long long p64 = ptr[b];
+    const bool badp = p64 < 0 || p64 >= S;           // the reference's gather would raise
+    const int p = badp ? 0 : (int)p64;
+    unsigned long long blocked = 0ull;
+    float m0 = 0.f, m1 = 0.f;
+    if (warp < CW) {
+        // ---- copy warps: masked out-of-place copy + column reductions of the precedence tensor (pack.py:333-376, :323-329)
+        const float *din = env_ptr(dynamic_in, b, SH::dyn_env(c));
+        float *dout = env_ptr(dynamic_out, b, SH::dyn_env(c));
+        DynPassFast<SH, 2, TPE> pass;
+        pass.init(c, (int)threadIdx.x);
+        pass.load(c, din, (int)threadIdx.x, 0);      // in flight before the block id is known
+        const int real = (int)srow[p];               // pack.py:347
+        pass.finish(c, din, dout, (int)threadIdx.x, real);
+        const BandBits bits = pass.combine(c);
+        if (lane == 0) { sbits[warp][0] = bits.move; sbits[warp][1] = bits.small; sbits[warp][2] = bits.large; }
+    } else {
+        // ---- placement warp: gather of the chosen block (model.py:404-406) + Container.add_new_block
+        const float *min_ = env_ptr(mask_in, b, (unsigned)S);
+        m0 = lane < S ? min_[lane] : 0.f;
+        m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
+        EnvRegs<STRAT> e; e.load(c, st, b, lane);
+        float dimv = 0.f;
+        if (lane < DIM) dimv = srow[(1 + lane) * S + p];
+        if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
+        const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+        const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+        const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
+        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys, badp ? 4 : 0, reward);
+    }
+    __syncthreads();
+    if (warp == CW) {                                // masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
+        BandBits bits; bits.move = bits.small = bits.large = 0ull;
+#pragma unroll
+        for (int w = 0; w < CW; ++w) { bits.move |= sbits[w][0]; bits.small |= sbits[w][1]; bits.large |= sbits[w][2]; }
+        blocked = bits.blocked();
+        mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), blocked, env_ptr(cur_mask_out, b, (unsigned)S),
+                      env_ptr(mask_out, b, (unsigned)S));
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // K6 reward: Container.calc_CPS / calc_ratio (tools.py:3887-3966), one thread per env
 // ------------------------------------------------------------------------------------
 __global__ void reward_kernel(DevCfg c, StatePtrs st, float *__restrict__ reward) {
@@ -1266,15 +1333,15 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
 #define TAPENV_STEP_ARGS d, st, ptr, static_, dynamic_in, mask_in, dynamic_out, cur_mask_out, mask_out, dec_static_out, dec_dynamic_out, reward_out
     // shapes with a fully unrolled instantiation ('bot'-like inputs: 3 bands, all updated); anything else runs generic
     const bool bot = d.dyn_rows == 3 * d.n && d.update_time == 3 && d.static_rows == 1 + d.dim;
-    // one resident wave: 148 SMs x (64 regs -> 32 warps) ; PLACE_FIRST only pays off then (profiles/r01_sweep*.json)
-    const bool pf = d.B <= 148 * 32;
+    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    // one resident wave: SMs x (64 regs -> 32 warps) ; PLACE_FIRST only pays off then (profiles/r01_sweep*.json)
+    const bool pf = d.B <= sms * 32;
 #define TAPENV_STEP_SHAPE(STRAT, N, R)                                                                     \
     do {                                                                                                   \
         if (pf) launch(step_kernel<STRAT, true, N, R, true>, grid, block, s, TAPENV_STEP_ARGS);            \
         else launch(step_kernel<STRAT, true, N, R, false>, grid, block, s, TAPENV_STEP_ARGS);              \
     } while (0)
     // heavy placements (3D, MACS): the 72-register build when it turns a 1.x-wave launch into a single wave
-    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     const int kdef = strat == STRAT_LBG3D ? 5 : 4;          // resident CTAs per SM of the default build (88 / 106 registers)
     const bool lowreg = (int)grid.x > sms * kdef && (int)grid.x <= sms * 7;
 #define TAPENV_STEP_SHAPE_HEAVY(STRAT, N, R)                                                               \
@@ -1282,6 +1349,20 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
         if (lowreg) launch(step_kernel<STRAT, true, N, R, true, 7>, grid, block, s, TAPENV_STEP_ARGS);     \
         else TAPENV_STEP_SHAPE(STRAT, N, R);                                                               \
     } while (0)
+    // CTA-per-environment form (step_split_kernel) when the warp-per-environment grid would underfill the machine.
+    // TAPENV_SPLIT=0/1 forces it off/on (tuning); default: fewer than 12 warps per SM in the warp-per-environment form.
+    const char *split_env = getenv("TAPENV_SPLIT");          // read per call: the tests flip it to cover both forms
+    const int split_mode = split_env && split_env[0] ? atoi(split_env) : -1;
+    const bool split = fast && bot && d.SV <= 32 * TAPENV_SPLIT_CW && strat != STRAT_LB && strat != STRAT_MACS3D &&
+                       (split_mode == 1 || (split_mode != 0 && d.B <= sms * 12));
+    if (split) {
+        const dim3 sgrid(d.B), sblock(32 * (TAPENV_SPLIT_CW + 1));
+#define TAPENV_SPLIT_LAUNCH(STRAT, N, R) launch(step_split_kernel<STRAT, N, R, TAPENV_SPLIT_CW>, sgrid, sblock, s, TAPENV_STEP_ARGS)
+        if (strat == STRAT_LBG2D) { if (d.n == 10 && d.R == 2) TAPENV_SPLIT_LAUNCH(STRAT_LBG2D, 10, 2); else TAPENV_SPLIT_LAUNCH(STRAT_LBG2D, 0, 0); }
+        else if (strat == STRAT_LBG3D) { if (d.n == 10 && d.R == 6) TAPENV_SPLIT_LAUNCH(STRAT_LBG3D, 10, 6); else TAPENV_SPLIT_LAUNCH(STRAT_LBG3D, 0, 0); }
+        else { if (d.n == 20 && d.R == 2) TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 20, 2); else TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 0, 0); }
+        return launch_status();
+    }
     if (strat == STRAT_LB || strat == STRAT_MACS3D) { // tensor pass (no placement) + the thread-per-environment placement kernel
         if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
                          dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr, (float *)nullptr);

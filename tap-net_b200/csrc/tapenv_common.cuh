@@ -43,6 +43,7 @@ struct DevCfg {  // by-value kernel argument, derived from tapenv_config on the 
 template <int NT, int RT, int DIM>
 struct Shape {
     static constexpr bool fixed = NT > 0;
+    static constexpr int NTc = NT;
     static constexpr int SVc = fixed ? (NT * RT) / 4 : 1;
     __device__ __forceinline__ static int n(const DevCfg &c) { return fixed ? NT : c.n; }
     __device__ __forceinline__ static int R(const DevCfg &c) { return fixed ? RT : c.R; }

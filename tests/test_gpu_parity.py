@@ -126,11 +126,27 @@ CASES = [
 ]
 
 
+@pytest.fixture
+def step_form(request):
+    """The fused step exists in two launch forms -- one warp per environment (step_kernel) and one CTA per environment
+    (step_split_kernel: copy warps + a placement warp); tapenv_step picks by batch size.  TAPENV_SPLIT=0/1 forces one."""
+    old = os.environ.get("TAPENV_SPLIT")
+    os.environ["TAPENV_SPLIT"] = {"warp": "0", "cta": "1"}[request.param]
+    yield request.param
+    if old is None:
+        os.environ.pop("TAPENV_SPLIT", None)
+    else:
+        os.environ["TAPENV_SPLIT"] = old
+
+
+@pytest.mark.parametrize("step_form", ["warp", "cta"], indirect=True)
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s-%s-%s" % (c[0].split("_")[0], "x".join(map(str, c[2])), c[3], c[4]))
-def test_fused_step_matches_oracle_every_step(case):
+def test_fused_step_matches_oracle_every_step(case, step_form):
     src, num, size, rt, hm, strat = case
     if not os.path.exists(golden_path(src)):
         pytest.skip("fixture not generated")
+    if step_form == "cta" and (strat in ("LB", "MUL") or (strat == "MACS" and len(size) == 3)):
+        pytest.skip("voxel-state strategies have no CTA-per-environment form")
     static, dynamic = load_inputs(src, num)
     r = oracle_rollout(static, dynamic, size, rt, hm, strat, seed=7)
     g = gpu_rollout(static, dynamic, r["ptr"], size, rt, hm, strat, fused=True)
@@ -321,9 +337,11 @@ def test_whole_episode_wrappers_known_answers():
     """tools.calc_positions_lb_greedy / pack.reward signatures: visual/draw_result.py:14-34 and SURVEY G1/G3."""
     torch = _torch()
     import tapenv
-    pos, hm, stable, ratio, scores = tapenv.calc_positions_lb_greedy(np.array([[3, 2], [1, 1], [1, 2]]), [4, 6], "C+P+S-lb-hard")
+    pos, grid, stable, ratio, scores = tapenv.calc_positions_lb_greedy(np.array([[3, 2], [1, 1], [1, 2]]), [4, 6], "C+P+S-lb-hard")
     assert pos.tolist() == [[0, 0], [3, 0], [3, 1]] and stable == [True, True, True]
-    assert ratio == 2.75 and scores == [9, 12, 0, 3, 3] and hm.tolist() == [2, 2, 2, 3]
+    assert ratio == 2.75 and scores == [9, 12, 0, 3, 3]
+    # the reference's voxel `container` (tools.py:2168-2169): block ids k+1, 0 = empty
+    assert grid.shape == (4, 6) and grid.tolist() == [[1, 1, 0, 0, 0, 0]] * 3 + [[2, 3, 3, 0, 0, 0]]
     kat = np.load(golden_path("kat.npz"))
     g1 = torch.tensor(kat["G1_blocks"], dtype=torch.float32).unsqueeze(0).repeat(3, 1, 1)
     pos, hm, stable, ratio, scores = tapenv.calc_positions_lb_greedy(g1, [5, 50], "C+P+S-lb-soft")
@@ -347,12 +365,15 @@ def test_install_patches_reference_modules():
     import types
     import tapenv
     pack, tools = types.ModuleType("pack"), types.ModuleType("tools")
-    pack.update_dynamic = pack.update_mask = pack.reward = tools.Container = tools.calc_positions_lb_greedy = "orig"
+    pack.update_dynamic = pack.update_mask = pack.reward = tools.Container = "orig"
+    tools.calc_positions_lb_greedy = tools.calc_positions_mcs = lambda blocks, size, rt: "orig-result"
     names = tapenv.install(pack, tools)
-    assert set(names) == {"update_dynamic", "update_mask", "reward", "Container", "calc_positions_lb_greedy"}
+    assert set(names) == {"update_dynamic", "update_mask", "reward", "Container", "calc_positions_lb_greedy", "calc_positions_mcs"}
+    # shapes beyond the compiled limits (49 cells > 32) go to the saved reference function (dataset generators, generate.py:908)
+    assert tools.calc_positions_lb_greedy(np.ones((3, 3)), [7, 7, 50], "C+P+S-lb-hard") == "orig-result"
     assert pack.update_dynamic is tapenv.update_dynamic and tools.Container is tapenv.Container
     tapenv.uninstall()
-    assert pack.update_mask == "orig" and tools.Container == "orig"
+    assert pack.update_mask == "orig" and tools.Container == "orig" and not hasattr(tools.calc_positions_mcs, "tapenv_original")
 
 
 def test_rolling_style_container_outlives_the_window():
