@@ -698,15 +698,19 @@ def measure_steps(ctx, args, name, B, full):
 
     # ---- timed region 2: roofline of the dominant kernel (the fused step), cold inputs ---------------
     # graph-replayed launches, each on a different ring slot, events on the launching stream
-    nl = min(len(runners), n)                                 # launches per replay (k stays < capacity between clears)
+    # One replay = the n decode steps of an episode (container fill k = 0..n-1: the placement scans lengthen with k), step t
+    # on ring slot t % RING -- consecutive launches never touch the same input set, and a slot is revisited only after
+    # RING * (inputs + outputs) >> 126 MB of other traffic.
+    nl = n
+    nbuf = min(len(runners), n)
     out_bufs = [(torch.empty_like(dyn0), torch.empty(B, S, device=dev), torch.empty(B, S, device=dev),
-                 torch.empty(B, dim, device=dev), torch.empty(B, env.enc_len, device=dev)) for _ in range(nl)]
+                 torch.empty(B, dim, device=dev), torch.empty(B, env.enc_len, device=dev)) for _ in range(nbuf)]
     mask1 = torch.ones(B, S, device=dev)
 
     def roof_launches():
         for i in range(nl):
-            r = runners[i]
-            env.step(r.ptr_seq[0, 0], r.static[0], r.dynamic[0], mask1, out=out_bufs[i])
+            r = runners[i % len(runners)]
+            env.step(r.ptr_seq[0, i], r.static[0], r.dynamic[0], mask1, out=out_bufs[i % nbuf])
 
     def graph_timed(fn, reps=12):
         env.clear_container()
@@ -733,7 +737,7 @@ def measure_steps(ctx, args, name, B, full):
     # pack.py:370) by torch's copy kernel, same cold ring slots, same graph-replay + event method
     def copy_launches():
         for i in range(nl):
-            out_bufs[i][0].copy_(runners[i].dynamic[0])
+            out_bufs[i % nbuf][0].copy_(runners[i % len(runners)].dynamic[0])
 
     copy_us, _ = graph_timed(copy_launches)
     peak, peak_src = ctx.peak()

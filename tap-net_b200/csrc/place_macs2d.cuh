@@ -36,8 +36,12 @@ __device__ __forceinline__ int longest_run(unsigned m) {
     return r;
 }
 
+// ONE_SLOT: the caller guarantees at most 32 previous blocks (compile-time shape with n <= 32): the second history slot and
+// everything derived from it drop out of the generated code.
+template <bool ONE_SLOT = false>
 __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int bx, int bz, int &h, Scal &sc,
                                                  const MacsHist &hist, unsigned *ems_keys, int &anomaly) {
+    (void)ems_keys;                                  // (the EMS key list of the r01 formulation; no longer used)
     const int W = c.W, H = c.H, k = sc.k;
     const bool hard = (c.flags & TAPENV_RF_HARD) != 0;
     const bool posvalid = (bx >= 1) && (lane + bx <= W);
@@ -53,15 +57,32 @@ __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int 
     const int add_p = bx * M - f.sumh;
     const unsigned ok_mask = __ballot_sync(TAPENV_FULL_MASK, ok_p);
 
+    // ---- ONE sweep over the columns gives every lane all it needs from "the other columns", in three roles at once:
+    //   lane = column c (list A):          le / eq masks of { h[d] <= / == h[c] }
+    //   lane = history entry i (list B):   free[s] = { d : h[d] <= t_i }                      (t_i = top level of block i)
+    //   lane = owner of an EMS at level Z: lv*  = { positions p : ok[p] and M[p] == Z }        (the `level` set of :2683-2698)
+    // (r01 evaluated the list-B and level sets with one ballot per EMS inside the sequential loop.)
+    const bool two = !ONE_SLOT && k > 32;            // second history slot in use (warp-uniform)
+    const int t0 = hist.z[0] + hist.zz[0], t1 = hist.z[1] + hist.zz[1];
+    unsigned le_mask = 0, eq_mask = 0, fr0 = 0, fr1 = 0, lvA = 0, lv0 = 0, lv1 = 0;
+    for (int d = 0; d < W; ++d) {
+        const int hd = __shfl_sync(TAPENV_FULL_MASK, h, d);
+        const int Md = __shfl_sync(TAPENV_FULL_MASK, M, d);
+        const unsigned bit = 1u << d;
+        const bool okd = (ok_mask & bit) != 0u;
+        if (hd <= h) le_mask |= bit;
+        if (hd == h) eq_mask |= bit;
+        if (hd <= t0) fr0 |= bit;
+        if (okd && Md == h) lvA |= bit;
+        if (okd && Md == t0) lv0 |= bit;
+        if (two) {
+            if (hd <= t1) fr1 |= bit;
+            if (okd && Md == t1) lv1 |= bit;
+        }
+    }
+
     // ---- list A representatives: lane c stands for (z = h[c], the run of {h <= z} around c) if it is the
     //      leftmost column of that run with h == z ----
-    unsigned le_mask = 0, eq_mask = 0;               // columns with h <= / == this lane's h
-    for (int d = 0; d < W; ++d) {
-        const int t = __shfl_sync(TAPENV_FULL_MASK, h, d);
-        le_mask |= (t <= h ? 1u : 0u) << d;
-        eq_mask |= (t == h ? 1u : 0u) << d;
-    }
-    // run of set bits of le_mask containing bit `lane`
     const unsigned below = ~le_mask & ((1u << lane) - 1u);                 // blocked columns left of lane
     const int a_x1 = below ? 32 - __clz(below) : 0;
     const unsigned above = (~le_mask & wmask) >> lane;                     // bit 0 is lane itself (clear)
@@ -69,17 +90,87 @@ __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int 
     const unsigned span_left = lane > a_x1 ? (((1u << lane) - 1u) & ~((1u << a_x1) - 1u)) : 0u;
     const bool a_rep = col && (eq_mask & span_left) == 0u && a_x1 + bx <= W && h + bz <= H;
     const unsigned a_key = ((unsigned)h << 5) | (unsigned)a_x1;            // order (z, x1)
+    // identity of an EMS for the duplicate test of list B (:2538): (level, X2, X1)
+    const unsigned a_id = a_rep ? (((unsigned)h << 10) | ((unsigned)(a_x2 & 31) << 5) | (unsigned)(a_x1 & 31)) : 0xffffffffu;
 
-    // ---- sequential candidate assignment ----
+    // ---- list B, lane-parallel (tools.py:2531-2555): entry i = previous block i, INCLUDING unplaced ones at (0,0) ----
+    // per slot: up to two EMS (a = "full top" or "left piece", b = "right piece"), packed X1:5 | X2:6 | valid:1 each
+    unsigned pk[2] = {0u, 0u}, ida[2] = {0xffffffffu, 0xffffffffu}, idb[2] = {0xffffffffu, 0xffffffffu};
+    bool full[2] = {false, false};
+    bool badent = false;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (s == 1 && !two) break;
+        const int i = lane + 32 * s;
+        const int x = hist.x[s], xx = hist.xx[s], t = s ? t1 : t0;
+        const unsigned fr = s ? fr1 : fr0;
+        const bool active = i < k && i < kMaxBlocks && t < H;
+        const bool bad = active && (xx < 1 || x < 0 || x >= W);
+        badent |= bad;
+        if (!active || bad) continue;
+        const unsigned top = ((xx >= 32 ? 0xffffffffu : ((1u << xx) - 1u)) << x) & wmask;   // numpy clips the slice at the wall
+        if ((fr & top) == top) {                                         // whole top free -> [x, x+xx-1] unless already listed
+            full[s] = true;
+            const int X2 = x + xx - 1;
+            pk[s] = (unsigned)x | ((unsigned)(X2 & 63) << 5) | (1u << 11);
+            ida[s] = ((unsigned)t << 10) | ((unsigned)(X2 & 31) << 5) | (unsigned)x;
+        } else if (x + xx > W) {
+            badent = true;                                               // the reference indexes past the wall here (IndexError)
+        } else {
+            if (((fr >> x) & 1u) && x > 0 && ((fr >> (x - 1)) & 1u)) {   // left piece (:2541-2548)
+                const unsigned occ = x + 1 >= 32 ? 1u : (~fr >> (x + 1));   // first blocked column right of x
+                const int run = occ ? __ffs(occ) - 1 : 31;
+                const int X2 = min(x + run, x + xx - 1);
+                pk[s] = (unsigned)x | ((unsigned)(X2 & 63) << 5) | (1u << 11);
+                ida[s] = ((unsigned)t << 10) | ((unsigned)(X2 & 31) << 5) | (unsigned)x;
+            }
+            const int xr = x + xx - 1;
+            if (((fr >> xr) & 1u) && x + xx < W && ((fr >> (xr + 1)) & 1u)) {   // right piece (:2549-2555)
+                const unsigned occ = ~fr & ((1u << xr) - 1u);            // blocked columns left of xr
+                const int lo = occ ? 32 - __clz(occ) : 0;
+                const int X1 = max(lo, x);
+                pk[s] |= ((unsigned)X1 << 12) | ((unsigned)(xr & 63) << 17) | (1u << 23);
+                idb[s] = ((unsigned)t << 10) | ((unsigned)(xr & 31) << 5) | (unsigned)(X1 & 31);
+            }
+        }
+    }
+    if (__any_sync(TAPENV_FULL_MASK, badent)) anomaly |= 1;
+    // duplicate test of the "full top" case: an identical EMS listed EARLIER -- in list A, or from an earlier block (any piece;
+    // an earlier identical full top that was itself dropped as a duplicate implies a still earlier identical one).
+    const unsigned anyfull = __ballot_sync(TAPENV_FULL_MASK, full[0] || full[1]);
+    if (anyfull) {
+        const unsigned lower = (1u << lane) - 1u;
+        // a-pieces of earlier blocks (full tops and left pieces share `ida`): one MATCH instead of a loop
+        bool dup0 = (__match_any_sync(TAPENV_FULL_MASK, ida[0]) & lower) != 0u, dup1 = false;
+        for (unsigned m = __ballot_sync(TAPENV_FULL_MASK, a_rep); m; m &= m - 1u) {          // list A
+            const unsigned q = __shfl_sync(TAPENV_FULL_MASK, a_id, __ffs(m) - 1);
+            dup0 |= q == ida[0]; dup1 |= q == ida[1];
+        }
+        for (unsigned m = __ballot_sync(TAPENV_FULL_MASK, idb[0] != 0xffffffffu); m; m &= m - 1u) {   // right pieces of earlier blocks
+            const int j = __ffs(m) - 1;
+            const unsigned q = __shfl_sync(TAPENV_FULL_MASK, idb[0], j);
+            if (j < lane) dup0 |= q == ida[0];
+            dup1 |= q == ida[1];                     // every slot-0 entry precedes every slot-1 entry
+        }
+        if (two) {
+            dup1 |= (__match_any_sync(TAPENV_FULL_MASK, ida[1]) & lower) != 0u;
+            for (int j = 0; j < 32; ++j) dup1 |= __shfl_sync(TAPENV_FULL_MASK, ida[0], j) == ida[1];
+            for (unsigned m = __ballot_sync(TAPENV_FULL_MASK, idb[1] != 0xffffffffu); m; m &= m - 1u) {
+                const int j = __ffs(m) - 1;
+                const unsigned q = __shfl_sync(TAPENV_FULL_MASK, idb[1], j);
+                if (j < lane) dup1 |= q == ida[1];
+            }
+        }
+        if (full[0] && dup0) pk[0] = 0u;             // ida stays: later identical entries are duplicates of the same EMS
+        if (full[1] && dup1) pk[1] = 0u;
+    }
+
+    // ---- sequential candidate assignment (shared `visited`): a few bit operations per EMS on warp-uniform values ----
     unsigned settled = 0;
     int cidx = 0x7fffffff;                           // candidate index settled on this lane's position
-    int ne = 0;                                      // EMS count so far
     const int X = W - bx + 1;
 
-    auto process_ems = [&](int X1, int Z, int X2) {
-        const int e = ne++;
-        if (lane == 0 && e < kMaxEms) ems_keys[e] = ((unsigned)Z << 10) | ((unsigned)(X2 & 31) << 5) | (unsigned)(X1 & 31);
-        const unsigned level = __ballot_sync(TAPENV_FULL_MASK, posvalid && M == Z) & ok_mask;
+    auto process_ems = [&](int X1, unsigned level, int X2, int e) {
         if (X1 < X) {                                // candidate 2e: upward from X1 (:2683-2689)
             const unsigned a = level & ~settled & ~((1u << X1) - 1u);
             if (a) { const int p = __ffs(a) - 1; settled |= 1u << p; if (lane == p) cidx = 2 * e; }
@@ -91,6 +182,7 @@ __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int 
         }
     };
 
+    int nA = 0;
     {   // list A in (z, x1) order
         unsigned left = __ballot_sync(TAPENV_FULL_MASK, a_rep);
         while (left) {
@@ -98,46 +190,23 @@ __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int 
             const int e = __ffs(__ballot_sync(TAPENV_FULL_MASK, ((left >> lane) & 1u) && a_key == kmin)) - 1;
             left &= ~(1u << e);
             const int X2 = __shfl_sync(TAPENV_FULL_MASK, a_x2, e);
-            process_ems((int)(kmin & 31u), (int)(kmin >> 5), X2);
+            const unsigned level = __shfl_sync(TAPENV_FULL_MASK, lvA, e);
+            process_ems((int)(kmin & 31u), level, X2, nA++);
         }
     }
-    __syncwarp();
-    for (int i = 0; i < k && i < kMaxBlocks; ++i) {  // list B in block order (warp-uniform loop)
-        const int slot = i >> 5, src = i & 31;
-        const int x = __shfl_sync(TAPENV_FULL_MASK, slot ? hist.x[1] : hist.x[0], src);
-        const int z = __shfl_sync(TAPENV_FULL_MASK, slot ? hist.z[1] : hist.z[0], src);
-        const int xx = __shfl_sync(TAPENV_FULL_MASK, slot ? hist.xx[1] : hist.xx[0], src);
-        const int zz = __shfl_sync(TAPENV_FULL_MASK, slot ? hist.zz[1] : hist.zz[0], src);
-        const int t = z + zz;
-        if (t >= H) continue;
-        if (xx < 1 || x < 0 || x >= W) { anomaly |= 1; continue; }
-        const unsigned freet = __ballot_sync(TAPENV_FULL_MASK, col && h <= t);
-        const unsigned top = ((xx >= 32 ? 0xffffffffu : ((1u << xx) - 1u)) << x) & wmask;   // numpy clips the slice at the wall
-        if ((freet & top) == top) {
-            const unsigned key = ((unsigned)t << 10) | ((unsigned)((x + xx - 1) & 31) << 5) | (unsigned)x;
-            bool dup = false;
-            __syncwarp();
-            for (int q = lane; q < ne && q < kMaxEms; q += 32) dup |= ems_keys[q] == key;
-            if (!__any_sync(TAPENV_FULL_MASK, dup)) process_ems(x, t, x + xx - 1);
-            __syncwarp();
-        } else {
-            if (x + xx > W) { anomaly |= 1; continue; }   // the reference indexes past the wall here (IndexError)
-            if (((freet >> x) & 1u) && x > 0 && ((freet >> (x - 1)) & 1u)) {          // left piece (:2541-2548)
-                const unsigned occ = x + 1 >= 32 ? 1u : (~freet >> (x + 1));          // first blocked column right of x
-                const int run = occ ? __ffs(occ) - 1 : 31;
-                process_ems(x, t, min(x + run, x + xx - 1));
-                __syncwarp();
-            }
-            const int xr = x + xx - 1;
-            if (((freet >> xr) & 1u) && x + xx < W && ((freet >> (xr + 1)) & 1u)) {   // right piece (:2549-2555)
-                const unsigned occ = ~freet & ((1u << xr) - 1u);                      // blocked columns left of xr
-                const int lo = occ ? 32 - __clz(occ) : 0;
-                process_ems(max(lo, x), t, xr);
-                __syncwarp();
-            }
+    // list B in block order: only the entries that contribute an EMS
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (s == 1 && !two) break;
+        for (unsigned m = __ballot_sync(TAPENV_FULL_MASK, pk[s] != 0u); m; m &= m - 1u) {
+            const int src = __ffs(m) - 1;
+            const unsigned w = __shfl_sync(TAPENV_FULL_MASK, pk[s], src);
+            const unsigned level = __shfl_sync(TAPENV_FULL_MASK, s ? lv1 : lv0, src);
+            const int e = 32 + 2 * (src + 32 * s);   // any numbering that is monotone in list order (list A: e < 32)
+            if (w & (1u << 11)) process_ems((int)(w & 31u), level, (int)((w >> 5) & 63u), e);
+            if (w & (1u << 23)) process_ems((int)((w >> 12) & 31u), level, (int)((w >> 17) & 63u), e + 1);
         }
     }
-    if (ne > kMaxEms) anomaly |= 4;
 
     PlaceOut res;
     res.placed = 0; res.x = 0; res.y = 0; res.z = 0; res.stable = 0; res.top = 0;
@@ -161,24 +230,22 @@ __device__ __forceinline__ PlaceOut macs2d_place(const DevCfg &c, int lane, int 
     if ((c.flags & TAPENV_RF_MCS_IN) && __popc(tmask) > 1) {          // tie-break (:2718-2731)
         const int maxH = warp_max(mine ? hnew : 0);                   // np.max(heightmap_ems)
         if (maxH > H) anomaly |= 1;
-        int my_mus = -1;
-        for (unsigned tm = tmask; tm; tm &= tm - 1u) {                // one tied candidate at a time
-            const int p = __ffs(tm) - 1;
-            const int ptop = __shfl_sync(TAPENV_FULL_MASK, top, p);
-            int total = 0;
-            for (int base = 0; base < maxH; base += 32) {             // lane = level
-                const int lvl = base + lane;
-                unsigned fm = 0;
-                for (int d = 0; d < W; ++d) {
-                    int t = __shfl_sync(TAPENV_FULL_MASK, h, d);
-                    if (d >= p && d < p + bx) t = ptop;
-                    fm |= (t <= lvl ? 1u : 0u) << d;
-                }
+        // maximal usable space after the placement (:2667-2678): at level lvl the free columns are those of the CURRENT
+        // heightmap outside the footprint plus -- iff the new top is <= lvl -- the footprint itself; lane = level
+        int my_mus = tied ? 0 : -1;
+        for (int base = 0; base < maxH; base += 32) {
+            const int lvl = base + lane;
+            unsigned fmb = 0;
+            for (int d = 0; d < W; ++d) fmb |= (__shfl_sync(TAPENV_FULL_MASK, h, d) <= lvl ? 1u : 0u) << d;
+            for (unsigned tm = tmask; tm; tm &= tm - 1u) {            // one tied candidate at a time
+                const int p = __ffs(tm) - 1;
+                const int ptop = __shfl_sync(TAPENV_FULL_MASK, top, p);
+                const unsigned F = (((bx >= 32 ? 0xffffffffu : ((1u << bx) - 1u)) << p)) & wmask;
+                const unsigned fm = (fmb & ~F) | (ptop <= lvl ? F : 0u);
                 const int run = longest_run(fm);
-                total += (lvl < maxH && run > 0) ? run - 1 : 0;
+                const int total = warp_add((lvl < maxH && run > 0) ? run - 1 : 0);
+                if (lane == p) my_mus += total;
             }
-            total = warp_add(total);
-            if (lane == p) my_mus = total;
         }
         // first maximum of mus in candidate order
         const int best_mus = warp_max(tied ? my_mus : -1);

@@ -66,33 +66,37 @@ TAPENV_HD bool two_point_rule(int a, int b, int c, int d) {
     return a * d == c * b && ((a < 0) != (c < 0)) && ((b < 0) != (d < 0));
 }
 
+// q / by for 0 <= q < 32, 1 <= by <= 32 with one multiply: inv = ceil(65536 / by) is exact in that range
+#define TAPENV_DIVBY(q) ((int)(((unsigned)(q) * inv) >> 16))
+
 TAPENV_HD bool stable3d_from_support(int bx, int by, unsigned sup) {
     const int cnt = tap_popc(sup);
     if (2 * cnt > bx * by) return true;
     if (cnt <= 1) return false;
+    const unsigned inv = (65536u + (unsigned)by - 1u) / (unsigned)by;
     const int cx = bx - 1, cy = by - 1;                       // doubled centre
     const int b0 = tap_ctz(sup);
-    const int i0 = b0 / by, j0 = b0 - i0 * by;                // first point (x-major order)
+    const int i0 = TAPENV_DIVBY(b0), j0 = b0 - i0 * by;       // first point (x-major order)
     if (cnt == 2) {
         const int b1 = tap_fls(sup);
-        const int i1 = b1 / by, j1 = b1 - i1 * by;
+        const int i1 = TAPENV_DIVBY(b1), j1 = b1 - i1 * by;
         return two_point_rule(cx - 2 * i0, cy - 2 * j0, cx - 2 * i1, cy - 2 * j1);
     }
     // >= 3 points: collinear?
     unsigned rest = sup & (sup - 1u);
     const int bs = tap_ctz(rest);
-    const int is = bs / by, js = bs - is * by;                // second point
+    const int is = TAPENV_DIVBY(bs), js = bs - is * by;       // second point
     rest &= rest - 1u;
     bool collinear = true;
     for (unsigned m = rest; m; m &= m - 1u) {
         const int bb = tap_ctz(m);
-        const int ii = bb / by, jj = bb - ii * by;
+        const int ii = TAPENV_DIVBY(bb), jj = bb - ii * by;
         if ((is - i0) * (jj - j0) - (js - j0) * (ii - i0) != 0) { collinear = false; break; }
     }
     if (collinear) {
         // np.argmin / np.argmax over x: first occurrence.  x-major order: the first point has minimal x;
         // the first point of maximal x is the lowest set bit of the highest occupied x-row.
-        const int imax = tap_fls(sup) / by;
+        const int imax = TAPENV_DIVBY(tap_fls(sup));
         const unsigned rowmask = (by >= 32 ? 0xffffffffu : ((1u << by) - 1u)) << (imax * by);
         const int bm = tap_ctz(sup & rowmask);
         const int jm = bm - imax * by;
@@ -102,12 +106,12 @@ TAPENV_HD bool stable3d_from_support(int bx, int by, unsigned sup) {
     bool le = false, ge = false, anyA = false, anyB = false;
     for (unsigned ma = sup; ma; ma &= ma - 1u) {
         const int ba = tap_ctz(ma);
-        const int ia = ba / by, ja = ba - ia * by;
+        const int ia = TAPENV_DIVBY(ba), ja = ba - ia * by;
         if (2 * ja < cy) continue;
         anyA = true;
         for (unsigned mb = sup; mb; mb &= mb - 1u) {
             const int bb = tap_ctz(mb);
-            const int ib = bb / by, jb = bb - ib * by;
+            const int ib = TAPENV_DIVBY(bb), jb = bb - ib * by;
             if (2 * jb >= cy) continue;
             anyB = true;
             // x_ab <= tx  <=>  (ty-ay)(bx-ax) >= (tx-ax)(by-ay)   [by-ay < 0], doubled coordinates

@@ -193,7 +193,7 @@ struct EnvRegs {
             for (int s = 0; s < 2; ++s) {
                 const int i = lane + 32 * s;
                 hist.x[s] = hist.z[s] = hist.xx[s] = hist.zz[s] = 0;
-                if (i < sc.k && i < c.cap) {
+                if (i < c.cap) {                     // rows >= k are zero since the reset and masked by the scan (i < k): no wait on `scal`
                     const int2 p = *reinterpret_cast<const int2 *>(st.positions + ((size_t)b * c.cap + i) * 2);
                     const int2 q = *reinterpret_cast<const int2 *>(st.blocks + ((size_t)b * c.cap + i) * 2);
                     hist.x[s] = p.x; hist.z[s] = p.y; hist.xx[s] = q.x; hist.zz[s] = q.y;
@@ -226,7 +226,7 @@ __device__ __forceinline__ double calc_ratio_dev(const DevCfg &c, int valid, int
 
 // Container.add_new_block for one environment (tools.py:3663-3744): placement, commit,
 // current_blocks_num += 1 even when the placement failed (tools.py:3713), heightmap encoding.
-template <int STRAT>
+template <int STRAT, bool SMALLN = false>             // SMALLN: blocks_num <= 32 known at compile time (MACS: one history slot)
 __device__ __forceinline__ void container_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane,
                                                     EnvRegs<STRAT> &e, int bx, int by, int bz, float *dec_dyn,
                                                     unsigned *ems_keys, int extra_flags, float *reward = nullptr) {
@@ -241,7 +241,7 @@ __device__ __forceinline__ void container_add_block(const DevCfg &c, const State
         if (STRAT == STRAT_LB) { }
         else if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
         else if (STRAT == STRAT_LBG3D) r = lbg3d_place(c, lane, e.x, e.y, bx, by, bz, e.h, e.sc);
-        else r = macs2d_place(c, lane, bx, bz, e.h, e.sc, e.hist, ems_keys, anomaly);
+        else r = macs2d_place<SMALLN>(c, lane, bx, bz, e.h, e.sc, e.hist, ems_keys, anomaly);
         if (lane < cells) st.heightmap[(size_t)b * cells + lane] = e.h;
         if (lane == 0) {
             const size_t o = ((size_t)b * c.cap + e.sc.k) * dim;
@@ -423,7 +423,7 @@ update_mask_kernel(DevCfg c, const float *__restrict__ mask, const float *__rest
 template <int STRAT>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
@@ -432,7 +432,7 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
     const int bx = (int)blk[0];                                            // .astype(int) tools.py:3689
     const int by = STRAT == STRAT_LBG3D ? (int)blk[1] : 1;
     const int bz = (int)blk[c.dim - 1];
-    container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+    container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
 }
 
 // LB strategy: one thread per environment (place_lb.cuh).  blocks == nullptr: take the block the fused step's tensor
@@ -565,7 +565,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
             float *__restrict__ dec_dyn, float *__restrict__ reward) {
     constexpr int DIMC = STRAT == STRAT_LBG3D ? 3 : 2;
     typedef Shape<NT, RT, DIMC> SH;
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
@@ -581,6 +581,14 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     const long long p64 = ptr[b];
     const float id0 = lane < S ? srow[lane] : 0.f;
     const float id1 = (S > 32 && lane + 32 < S) ? srow[lane + 32] : 0.f;
+    // the edge-length rows too (DIM * S floats, L2-resident across the steps of an episode): the gather of the chosen block
+    // (model.py:404-406) then needs no second DRAM round trip behind `ptr`
+    float ev0[3], ev1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        ev0[r] = (r < DIM && lane < S) ? srow[(1 + r) * S + lane] : 0.f;
+        ev1[r] = (r < DIM && S > 32 && lane + 32 < S) ? srow[(1 + r) * S + lane + 32] : 0.f;
+    }
     const float m0 = lane < S ? min_[lane] : 0.f;
     const float m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
     EnvRegs<STRAT> e; e.load(c, st, b, lane);
@@ -590,24 +598,28 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     // (2) the chosen candidate: block id (pack.py:347) and edge lengths (model.py:404-406)
     const bool badp = p64 < 0 || p64 >= S;           // the reference's gather would raise
     const int p = badp ? 0 : (int)p64;
-    const int real = (int)__shfl_sync(TAPENV_FULL_MASK, (S > 32 && p >= 32) ? id1 : id0, p & 31);
-    float dimv = 0.f;
-    if (lane < DIM) dimv = srow[(1 + lane) * S + p];
+    const bool hi = S > 32 && p >= 32;
+    const int real = (int)__shfl_sync(TAPENV_FULL_MASK, hi ? id1 : id0, p & 31);
+    const float e0 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[0] : ev0[0], p & 31);
+    const float e1 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[1] : ev0[1], p & 31);
+    const float e2 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[2] : ev0[2], p & 31);
+    const float dimv = lane == 0 ? e0 : (lane == 1 ? e1 : e2);
     if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
 
     // (3) environment transition on the register-resident state.  It only needs the pointer, the block's edge
     //     lengths and the (tiny) state, all of which arrive long before the precedence tensor has streamed in.
     //     With a single resident wave (B <= ~4.7k) it runs FIRST so its ~250 warp-instructions overlap the HBM
     //     read phase; with many waves other warps provide that overlap and the shorter register live range wins.
-    const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
-    const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
-    const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
+    const int bx = (int)e0;
+    const int by = STRAT == STRAT_LBG3D ? (int)e1 : 1;
+    const int bz = (int)(DIM == 3 ? e2 : e1);
     if (STRAT == STRAT_LB) {                         // hand the gathered block to lb_kernel (launched right behind)
         if (lane < DIM) st.pending[(size_t)b * 4 + lane] = dimv;
         if (lane == 0 && badp) st.flags[b] |= 4;
     }
+    constexpr bool SMALLN = NT > 0 && NT <= 32;
     if (PLACE_FIRST && STRAT != STRAT_LB)
-        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0, reward);
+        container_add_block<STRAT, SMALLN>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, badp ? 4 : 0, reward);
 
     // (4) masked copy + column reductions of the precedence tensor
     BandBits bits;
@@ -619,7 +631,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
                   env_ptr(mask_out, b, (unsigned)S));
 
     if (!PLACE_FIRST && STRAT != STRAT_LB)
-        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0, reward);
+        container_add_block<STRAT, SMALLN>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, badp ? 4 : 0, reward);
 }
 
 // ------------------------------------------------------------------------------------
@@ -643,12 +655,21 @@ step_split_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const
     constexpr int TPE = 32 * CW;
     typedef Shape<NT, RT, DIM> SH;
     __shared__ unsigned long long sbits[CW][3];
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys = nullptr;            // (the EMS key list of r01; the MACS scan no longer needs shared memory)
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     grid_dependency_sync();
     const int S = SH::S(c);
     const float *srow = env_ptr(static_, b, SH::static_env(c));
     const long long p64 = ptr[b];
+    // placement warp: the edge-length rows of `static` are requested before `ptr` has arrived (no second round trip)
+    float ev0[3] = {0.f, 0.f, 0.f}, ev1[3] = {0.f, 0.f, 0.f};
+    if (warp == CW) {
+#pragma unroll
+        for (int r = 0; r < DIM; ++r) {
+            ev0[r] = lane < S ? srow[(1 + r) * S + lane] : 0.f;
+            ev1[r] = (S > 32 && lane + 32 < S) ? srow[(1 + r) * S + lane + 32] : 0.f;
+        }
+    }
     const bool badp = p64 < 0 || p64 >= S;           // the reference's gather would raise
     const int p = badp ? 0 : (int)p64;
     unsigned long long blocked = 0ull;
@@ -670,13 +691,15 @@ step_split_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const
         m0 = lane < S ? min_[lane] : 0.f;
         m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
         EnvRegs<STRAT> e; e.load(c, st, b, lane);
-        float dimv = 0.f;
-        if (lane < DIM) dimv = srow[(1 + lane) * S + p];
-        if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
-        const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
-        const int by = STRAT == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
-        const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, DIM - 1);
-        container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys, badp ? 4 : 0, reward);
+        const bool hi = S > 32 && p >= 32;
+        const float e0 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[0] : ev0[0], p & 31);
+        const float e1 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[1] : ev0[1], p & 31);
+        const float e2 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[2] : ev0[2], p & 31);
+        if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = lane == 0 ? e0 : (lane == 1 ? e1 : e2);
+        const int bx = (int)e0;
+        const int by = STRAT == STRAT_LBG3D ? (int)e1 : 1;
+        const int bz = (int)(DIM == 3 ? e2 : e1);
+        container_add_block<STRAT, (NT > 0 && NT <= 32)>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys, badp ? 4 : 0, reward);
     }
     __syncthreads();
     if (warp == CW) {                                // masks (pack.py:318-331); block id for the mask is ptr mod n (pack.py:314-316)
@@ -743,7 +766,7 @@ step_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const int64_t *__restrict_
                 float *__restrict__ dec_dyn) {
     typedef Shape<0, 0, 0> SH;
     constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
@@ -768,7 +791,7 @@ step_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const int64_t *__restrict_
     const BandBits bits = dynpass<SH, FAST>(c, lane, din, dout, real);
     mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
                   env_ptr(mask_out, b, (unsigned)S));
-    mul_place<STRAT>(c, sa, sb, b, lane, tgt, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+    mul_place<STRAT>(c, sa, sb, b, lane, tgt, bx, by, bz, dec_dyn, ems_keys_none, badp ? 4 : 0);
 }
 
 template <int STRAT>
@@ -776,13 +799,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta)
 add_blocks_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const float *__restrict__ blocks, const float *__restrict__ target_ids,
                       float *__restrict__ dec_dyn) {
     constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
     const float *blk = blocks + (size_t)b * DIM;
     const int bx = (int)blk[0], by = DIM == 3 ? (int)blk[1] : 1, bz = (int)blk[DIM - 1];
-    mul_place<STRAT>(c, sa, sb, b, lane, (int)target_ids[b], bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+    mul_place<STRAT>(c, sa, sb, b, lane, (int)target_ids[b], bx, by, bz, dec_dyn, ems_keys_none, 0);
 }
 
 // scores = (calc_ratio(A) + calc_ratio(B)) / 2 accumulated in an fp32 tensor (model.py:503-507)
@@ -818,7 +841,7 @@ episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const 
     constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
     __shared__ unsigned rows[kWarpsPerCta][3][kMaxBlocks][2];          // bit j of (band, row): dynamic[band*n+row][j] != 0
     __shared__ float stat[kWarpsPerCta][1 + DIM][kMaxCandidates];
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
@@ -883,7 +906,7 @@ episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const 
         for (int r = 0; r < c.R; ++r) mask &= ~(1ull << (realm + n * r));   // pack.py:318-321
         __syncwarp();
         container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, t == steps - 1 ? dec_dyn : nullptr,
-                                   ems_keys[STRAT == STRAT_MACS2D ? warp : 0], badp ? 4 : 0);
+                                   ems_keys_none, badp ? 4 : 0);
         if (e.sc.k < c.cap) e.sc.k += 1;
         if (STRAT == STRAT_MACS2D) {                                        // refresh the history registers
             __syncwarp();
@@ -1066,7 +1089,7 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
     constexpr int ES = STRAT < 0 ? STRAT_LBG2D : STRAT;
     __shared__ WinShared shs[kWarpsPerCta];
     __shared__ uint4 lut[16];                         // nibble -> four fp32 0/1 values
-    __shared__ unsigned ems_keys[STRAT == STRAT_MACS2D ? kWarpsPerCta : 1][STRAT == STRAT_MACS2D ? kMaxEms : 1];
+    unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     if (threadIdx.x < 16) {
         const unsigned t = threadIdx.x, one = 0x3f800000u;
@@ -1117,7 +1140,7 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
         const int by = ES == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
         const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, w.dim - 1);
         if (place)
-            container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys[STRAT == STRAT_MACS2D ? warp : 0], 0);
+            container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
     }
     window_emit<FAST>(w, sh, lut, b, lane, early, ws, pe, blk, static_out, dynamic_out, cur_mask, mask_out, nodes_out,
                       remaining_out);

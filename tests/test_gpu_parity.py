@@ -749,3 +749,29 @@ def test_g6_pretrained_network_tours_on_gpu(dim, fixture, size):
     tour_idx, _, reward = tapenv.DecodeLoop(env, replay_actor, greedy=True).run(st, dyn)
     assert np.array_equal(tour_idx.cpu().numpy(), tour)
     assert np.abs(reward.cpu().numpy().astype(np.float64) - want).max() <= 1e-6
+
+
+@pytest.mark.parametrize("W,n,rt", [(7, 48, "C+P+S-mcs-hard"), (5, 60, "C+P+S-mcs-soft"), (12, 40, "mcs-hard"), (3, 64, "C+P-mcs-hard")])
+def test_macs_long_histories_two_slots(W, n, rt):
+    """MACS 2D list B (tools.py:2531-2555) over more than 32 previous blocks (second history slot), many identical block tops
+    (the duplicate test of :2538) and unplaced phantom entries: placement-only path against the oracle, every step."""
+    torch = _torch()
+    import tapenv
+    from oracle import oracle
+    B = 40
+    rng = np.random.RandomState(W * 1000 + n)
+    H = 4 * n + 8
+    env = tapenv.BatchedContainers([W, H], n, rt, "diff", packing_strategy="MACS", batch_size=B)
+    conts = [oracle.Container([W, H], n, rt, "diff", packing_strategy="MACS") for _ in range(B)]
+    for t in range(n):
+        # few distinct sizes -> many equal tops; with -hard, blocks that find no stable position stay unplaced (phantom entries)
+        blocks = rng.randint(1, min(4, W + 1), size=(B, 2)).astype(np.float32)
+        enc = env.add_new_blocks(torch.from_numpy(blocks).cuda()).cpu().numpy()
+        want = np.stack([np.asarray(conts[b].add_new_block(blocks[b])).reshape(-1) for b in range(B)])
+        assert np.array_equal(enc, want.astype(np.float32)), t
+        assert np.array_equal(env.heightmap.cpu().numpy(), np.stack([c.heightmap for c in conts])), t
+    assert np.array_equal(env.positions.cpu().numpy(), np.stack([c.positions for c in conts]))
+    assert np.array_equal(env.stable.cpu().numpy(), np.stack([np.array(c.stable, dtype=np.uint8) for c in conts]))
+    r = env.calc_ratio().cpu().numpy().astype(np.float64)
+    want_r = np.array([c.calc_ratio() for c in conts])
+    assert np.abs(r - want_r).max() <= REWARD_TOL
