@@ -45,9 +45,16 @@ WORKLOADS = {
     "c5": ("rolling3d_t50.npz", [5, 5, 250], "C+P+S-lb-soft", "diff", "LB_GREEDY",
            "3D rolling total=50 window=10 width=5 height=250 LB_GREEDY batch=65536 sharded over the GPUs (BASELINE configs[4])"),
 }
+# the voxel-state strategies (no BASELINE configuration uses them): C2 / C3 inputs, other packing strategy
+WORKLOADS["c2lb"] = ("rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "diff", "LB",
+                     "2D RAND nodes=10 width=5 LB (tools.py:1602-1754) C+P+S-lb-soft batch=4096 per GPU")
+WORKLOADS["c3lb"] = ("rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-soft", "diff", "LB",
+                     "3D RAND nodes=10 width=5 LB (tools.py:1756-1914) C+P+S-lb-soft batch=4096 per GPU")
+WORKLOADS["c3macs"] = ("rand3d_n10.npz", [5, 5, 50], "C+P+S-mcs-soft", "diff", "MACS",
+                       "3D RAND nodes=10 width=5 MACS (tools.py:2751-3165) C+P+S-mcs-soft batch=4096 per GPU")
 ROLLING = {"c5": (50, 10)}          # workload -> (total_blocks_num, network window)
 TOTAL_BATCH = {"c4": 8192, "c5": 65536}     # BASELINE's global batch, sharded over the GPUs (strong scaling)
-PER_GPU_BATCH = {"c2": 4096, "c3": 4096}    # BASELINE's single-GPU batch, kept per GPU (weak scaling)
+PER_GPU_BATCH = {"c2": 4096, "c3": 4096, "c2lb": 4096, "c3lb": 4096, "c3macs": 4096}    # single-GPU batch, kept per GPU (weak scaling)
 
 
 def default_batch(name, world):
@@ -146,7 +153,7 @@ def bench_config(name, B, world, args):
                     "%d fused decode steps in the last window (the last also emits calc_ratio) + reward sums over the batch" % (T - n, n))
         l2 = "%.0f MB of ping-pong window tensors per episode > 126 MB L2; 2 instance sets alternate" % (per_episode / 1e6)
     else:
-        n = {"c2": 10, "c3": 10, "c4": 20}[name]
+        n = 20 if name == "c4" else 10
         steps = n
         S = n * R
         per_set = B * ((1 + dim) * S + 3 * n * S) * 4
@@ -662,6 +669,7 @@ def measure_steps(ctx, args, name, B, full):
             torch.cuda.current_stream().wait_event(r.nccl_reduced)     # the slot's previous sums have been consumed
         r.run()
         if reducer is not None:
+            r.tail.wait_total()                                        # the local sums come from the side stream
             r.nccl_total, r.nccl_reduced = reducer.reduce_async(r.sums)
         return r
 
@@ -763,7 +771,12 @@ def measure_steps(ctx, args, name, B, full):
     hb = pipe.new_host_batch()                                # ONE contiguous pinned batch (what a loader fills in place): one H2D copy per episode
     hb.static.copy_(torch.from_numpy(static_h).view_as(hb.static)); hb.dynamic.copy_(torch.from_numpy(dynamic_h).view_as(hb.dynamic))
     hb.ptr.copy_(pq_pin.view_as(hb.ptr))
-    after = (lambda r: r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))) if reducer is not None else None   # in-order here: the host reads the totals
+    def nccl_after(r):                                        # NCCL fallback, in-order here: the host reads the totals
+        r.tail.wait_total()
+        with torch.cuda.stream(r.tail.stream):
+            r.sums.copy_(tapenv.dist.combine_partial_sums(r.sums))
+            r.tail.reduced.record(r.tail.stream)
+    after = nccl_after if reducer is not None else None
 
     def drive(p, batch, k):
         last = None

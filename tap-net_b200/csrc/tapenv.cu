@@ -182,7 +182,7 @@ struct EnvRegs {
     MacsHist hist;
 
     __device__ __forceinline__ void load(const DevCfg &c, const StatePtrs &st, int b, int lane) {
-        if (STRAT == STRAT_LB) return;               // the LB placement runs in its own kernel (lb_kernel)
+        if (STRAT == STRAT_LB || STRAT == STRAT_MACS3D) return;   // voxel-state strategies keep their state in global memory (voxel_add_block)
         const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
         h = lane < cells ? st.heightmap[(size_t)b * cells + lane] : 0;
         sc = load_scal(st, b);
@@ -224,12 +224,62 @@ __device__ __forceinline__ double calc_ratio_dev(const DevCfg &c, int valid, int
     }
 }
 
+template <int STRAT>
+__device__ __forceinline__ void voxel_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane, int bx, int by, int bz,
+                                                float *dec_dyn, int extra_flags, float *reward);
+
+// block dimension of a strategy instantiation: fixed for the heightmap-only strategies, from the config for the voxel ones
+template <int STRAT>
+__device__ __forceinline__ int dim_of(const DevCfg &c) {
+    return (STRAT == STRAT_LB || STRAT == STRAT_MACS3D) ? c.dim : (STRAT == STRAT_LBG3D ? 3 : 2);
+}
+
+// get_heightmap() of the state as it stands (tools.py:3824-3856), warp-parallel
+__device__ __forceinline__ int encode_state_heightmap(const DevCfg &c, const StatePtrs &st, int b, int lane, int dim, float *out) {
+    const int cells = dim == 2 ? c.W : c.W * c.L;
+    const int h = lane < cells ? *((volatile int *)(st.heightmap + (size_t)b * cells + lane)) : 0;
+    if (out) {
+        if (dim == 3) {
+            const int x = (int)(((unsigned)lane * c.inv_L) >> 16), y = lane - x * c.L;
+            encode_heightmap_3d(c, lane, x, y, h, out);
+        } else encode_heightmap_2d(c, lane, h, out);
+    }
+    return h;
+}
+
+// Container.__init__ / clear_container of one environment (tools.py:3611-3661, :3858-3885), warp-parallel
+__device__ __forceinline__ void reset_env_state(const DevCfg &c, const StatePtrs &st, int b, int lane) {
+    const int cells = c.dim == 2 ? c.W : c.W * c.L;
+    for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
+    for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
+    for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
+    if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
+    if (c.strategy == TAPENV_LB) {                   // voxel grid zero, every x list = [0] (tools.py:3649-3653)
+        const size_t nv = (size_t)cells * c.H;
+        for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
+        const size_t nl = (size_t)c.nlists * c.lcap;
+        for (size_t i = lane; i < nl; i += 32) st.lists[(size_t)b * nl + i] = (i % c.lcap) == 0 ? 1 : 0;
+    } else if (c.strategy == TAPENV_MACS && c.dim == 3) {   // every (level, row) interval list = [0, W-1] (tools.py:3644-3648)
+        const size_t nv = (size_t)cells * c.H;
+        for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
+        const size_t nl = (size_t)c.nlists * c.lcap;
+        for (size_t i = lane; i < nl; i += 32) {
+            const int q = (int)(i % c.lcap);
+            st.lists[(size_t)b * nl + i] = q == 0 ? 2 : (q == 2 ? (unsigned char)(c.W - 1) : 0);
+        }
+    }
+}
+
 // Container.add_new_block for one environment (tools.py:3663-3744): placement, commit,
 // current_blocks_num += 1 even when the placement failed (tools.py:3713), heightmap encoding.
 template <int STRAT, bool SMALLN = false>             // SMALLN: blocks_num <= 32 known at compile time (MACS: one history slot)
 __device__ __forceinline__ void container_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane,
                                                     EnvRegs<STRAT> &e, int bx, int by, int bz, float *dec_dyn,
                                                     unsigned *ems_keys, int extra_flags, float *reward = nullptr) {
+    if (STRAT == STRAT_LB || STRAT == STRAT_MACS3D) {   // voxel-state strategies: lane 0 walks the grid
+        voxel_add_block<STRAT>(c, st, b, lane, bx, by, bz, dec_dyn, extra_flags, reward);
+        return;
+    }
     const int dim = (STRAT == STRAT_LBG3D) ? 3 : 2;
     const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
     int anomaly = extra_flags;
@@ -238,8 +288,7 @@ __device__ __forceinline__ void container_add_block(const DevCfg &c, const State
     } else {
         PlaceOut r;
         r.placed = 0; r.x = r.y = r.z = r.stable = r.top = 0;
-        if (STRAT == STRAT_LB) { }
-        else if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
+        if (STRAT == STRAT_LBG2D) r = lbg2d_place(c, lane, bx, bz, e.h, e.sc);
         else if (STRAT == STRAT_LBG3D) r = lbg3d_place(c, lane, e.x, e.y, bx, by, bz, e.h, e.sc);
         else r = macs2d_place<SMALLN>(c, lane, bx, bz, e.h, e.sc, e.hist, ems_keys, anomaly);
         if (lane < cells) st.heightmap[(size_t)b * cells + lane] = e.h;
@@ -282,27 +331,7 @@ reset_kernel(DevCfg c, StatePtrs st, int clear_state, const float *__restrict__ 
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
-    if (clear_state) {
-        const int cells = c.dim == 2 ? c.W : c.W * c.L;
-        for (int i = lane; i < cells; i += 32) st.heightmap[(size_t)b * cells + i] = 0;
-        for (int i = lane; i < c.cap * c.dim; i += 32) { st.positions[(size_t)b * c.cap * c.dim + i] = 0; st.blocks[(size_t)b * c.cap * c.dim + i] = 0; }
-        for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
-        if (lane == 0) { st.scal[b] = make_int4(0, 0, 0, 0); st.flags[b] = 0; }
-        if (c.strategy == TAPENV_LB) {                   // voxel grid zero, every x list = [0] (tools.py:3649-3653)
-            const size_t nv = (size_t)cells * c.H;
-            for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
-            const size_t nl = (size_t)c.nlists * c.lcap;
-            for (size_t i = lane; i < nl; i += 32) st.lists[(size_t)b * nl + i] = (i % c.lcap) == 0 ? 1 : 0;
-        } else if (c.strategy == TAPENV_MACS && c.dim == 3) {   // every (level, row) interval list = [0, W-1] (tools.py:3644-3648)
-            const size_t nv = (size_t)cells * c.H;
-            for (size_t i = lane; i < nv; i += 32) st.voxels[(size_t)b * nv + i] = 0;
-            const size_t nl = (size_t)c.nlists * c.lcap;
-            for (size_t i = lane; i < nl; i += 32) {
-                const int q = (int)(i % c.lcap);
-                st.lists[(size_t)b * nl + i] = q == 0 ? 2 : (q == 2 ? (unsigned char)(c.W - 1) : 0);
-            }
-        }
-    }
+    if (clear_state) reset_env_state(c, st, b, lane);
     if (dynamic == nullptr) return;
     const BandBits bits = dynpass<SH, FAST>(c, lane, env_ptr(dynamic, b, c.dyn_env), nullptr, -1);
     mask_pass<SH>(c, lane, false, 0.f, 0.f, -1, bits.blocked(), cur_mask + (size_t)b * c.S, mask ? mask + (size_t)b * c.S : nullptr);
@@ -435,17 +464,18 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
     container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
 }
 
-// LB strategy: one thread per environment (place_lb.cuh).  blocks == nullptr: take the block the fused step's tensor
-// pass left in st.pending.
+// ------------------------------------------------------------------------------------
+// Voxel-state strategies (LB tools.py:1602-1914, MACS 3D :2751-3165): the placement is a sequential walk over a voxel grid
+// and incrementally edited lists kept in the state buffer.  One THREAD performs it for one environment:
+//   - lb_kernel / macs3d_kernel: thread-per-environment grids (tapenv_add_blocks),
+//   - voxel_add_block: lane 0 of the environment's warp inside the fused kernels (step / episode / rolling / mul), the other
+//     lanes wait and then encode the heightmap -- one launch per decode step, and no divergence between environments
+//     that share a warp (r02: faster than the thread-per-environment kernel behind a separate tensor pass).
+// ------------------------------------------------------------------------------------
+// Container.add_new_block for one environment, LB strategy, executed by ONE thread.  Returns the anomaly bits.
 template <int DIM>
-__global__ void __launch_bounds__(64)
-lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    grid_dependency_sync();
-    if (b >= c.B) return;
+__device__ __forceinline__ int lb_env_add_block(const DevCfg &c, const StatePtrs &st, int b, int bx, int by, int bz) {
     const int cells = DIM == 2 ? c.W : c.W * c.L;
-    const float *blk = blocks ? blocks + (size_t)b * DIM : st.pending + (size_t)b * 4;
-    const int bx = (int)blk[0], by = DIM == 3 ? (int)blk[1] : 1, bz = (int)blk[DIM - 1];   // .astype(int) tools.py:3675
     LbState s;
     s.W = c.W; s.L = DIM == 3 ? c.L : 1; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
     s.vox = st.voxels + (size_t)b * cells * c.H;
@@ -454,55 +484,31 @@ lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__res
     const int4 sc = st.scal[b];
     int anomaly = 0;
     const int k = sc.w;
-    if (k >= c.cap) {
-        anomaly |= 2;
-    } else {
-        int *positions = st.positions + (size_t)b * c.cap * DIM, *blks = st.blocks + (size_t)b * c.cap * DIM;
-        blks[k * DIM] = bx; if (DIM == 3) blks[k * DIM + 1] = by; blks[k * DIM + DIM - 1] = bz;
-        int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
-        unsigned char stable = 0;
-        if (bx >= 1 && by >= 1 && bz >= 1 && bx <= c.W && by <= s.L) {
-            const int vol = bx * by * bz;
-            const LbBest best = lb_place<DIM>(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
-            if (best.any) {
-                lb_commit<DIM>(s, k, best, bx, by, bz, anomaly);
-                if (!(anomaly & 1)) {
-                    positions[k * DIM] = best.x; if (DIM == 3) positions[k * DIM + 1] = best.y; positions[k * DIM + DIM - 1] = best.z;
-                    stable = (unsigned char)best.stable;
-                    out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
-                }
-            }
-        }
-        st.stable[(size_t)b * c.cap + k] = stable;
-        st.scal[b] = out;
-    }
-    if (anomaly) st.flags[b] |= anomaly;
-    if (dec_dyn) {                                   // heightmap encodings (tools.py:3716-3743), serial form
-        float *o = dec_dyn + (size_t)b * c.enc_len;
-        const int *h = s.h;
-        if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
-        else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
-        else if (DIM == 2) { for (int i = 0; i + 1 < c.W; ++i) o[i] = (float)(h[i + 1] - h[i]); }
-        else {
-            for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
-                o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
-                o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
+    if (k >= c.cap) return 2;
+    int *positions = st.positions + (size_t)b * c.cap * DIM, *blks = st.blocks + (size_t)b * c.cap * DIM;
+    blks[k * DIM] = bx; if (DIM == 3) blks[k * DIM + 1] = by; blks[k * DIM + DIM - 1] = bz;
+    int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
+    unsigned char stable = 0;
+    if (bx >= 1 && by >= 1 && bz >= 1 && bx <= c.W && by <= s.L) {
+        const int vol = bx * by * bz;
+        const LbBest best = lb_place<DIM>(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
+        if (best.any) {
+            lb_commit<DIM>(s, k, best, bx, by, bz, anomaly);
+            if (!(anomaly & 1)) {
+                positions[k * DIM] = best.x; if (DIM == 3) positions[k * DIM + 1] = best.y; positions[k * DIM + DIM - 1] = best.z;
+                stable = (unsigned char)best.stable;
+                out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
             }
         }
     }
+    st.stable[(size_t)b * c.cap + k] = stable;
+    st.scal[b] = out;
+    return anomaly;
 }
 
-
-// MACS 3D: one thread per environment (place_macs3d.cuh).  blocks == nullptr: take the block the fused step's tensor
-// pass left in st.pending.
-__global__ void __launch_bounds__(64)
-macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    grid_dependency_sync();
-    if (b >= c.B) return;
+// Container.add_new_block for one environment, MACS 3D, executed by ONE thread.  Returns the anomaly bits.
+__device__ __forceinline__ int macs3d_env_add_block(const DevCfg &c, const StatePtrs &st, int b, int bx, int by, int bz) {
     const int cells = c.W * c.L;
-    const float *blk = blocks ? blocks + (size_t)b * 3 : st.pending + (size_t)b * 4;
-    const int bx = (int)blk[0], by = (int)blk[1], bz = (int)blk[2];           // .astype('int') tools.py:3675
     M3State s;
     s.W = c.W; s.L = c.L; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
     s.vox = st.voxels + (size_t)b * cells * c.H;
@@ -511,38 +517,93 @@ macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *_
     const int4 sc = st.scal[b];
     int anomaly = 0;
     const int k = sc.w;
-    if (k >= c.cap) {
-        anomaly |= 2;
-    } else {
-        int *positions = st.positions + (size_t)b * c.cap * 3, *blks = st.blocks + (size_t)b * c.cap * 3;
-        blks[k * 3] = bx; blks[k * 3 + 1] = by; blks[k * 3 + 2] = bz;
-        int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
-        unsigned char stable = 0;
-        if (bx >= 1 && by >= 1 && bz >= 1 && bx * by <= 32) {
-            const int vol = bx * by * bz;
-            const M3Best best = macs3d_place(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
-            if (best.any && !(anomaly & 1)) {
-                macs3d_commit(s, k, best, bx, by, bz, anomaly);
-                if (!(anomaly & 1)) {
-                    positions[k * 3] = best.x; positions[k * 3 + 1] = best.y; positions[k * 3 + 2] = best.z;
-                    stable = (unsigned char)best.stable;
-                    out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
-                }
+    if (k >= c.cap) return 2;
+    int *positions = st.positions + (size_t)b * c.cap * 3, *blks = st.blocks + (size_t)b * c.cap * 3;
+    blks[k * 3] = bx; blks[k * 3 + 1] = by; blks[k * 3 + 2] = bz;
+    int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
+    unsigned char stable = 0;
+    if (bx >= 1 && by >= 1 && bz >= 1 && bx * by <= 32) {
+        const int vol = bx * by * bz;
+        const M3Best best = macs3d_place(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
+        if (best.any && !(anomaly & 1)) {
+            macs3d_commit(s, k, best, bx, by, bz, anomaly);
+            if (!(anomaly & 1)) {
+                positions[k * 3] = best.x; positions[k * 3 + 1] = best.y; positions[k * 3 + 2] = best.z;
+                stable = (unsigned char)best.stable;
+                out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
             }
         }
-        st.stable[(size_t)b * c.cap + k] = stable;
-        st.scal[b] = out;
     }
+    st.stable[(size_t)b * c.cap + k] = stable;
+    st.scal[b] = out;
+    return anomaly;
+}
+
+// heightmap encodings (tools.py:3716-3743), serial form for the thread-per-environment kernels
+__device__ __forceinline__ void encode_heightmap_serial(const DevCfg &c, const int *h, float *o) {
+    const int cells = c.dim == 2 ? c.W : c.W * c.L;
+    if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
+    else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
+    else if (c.dim == 2) { for (int i = 0; i + 1 < c.W; ++i) o[i] = (float)(h[i + 1] - h[i]); }
+    else {
+        for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
+            o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
+            o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
+        }
+    }
+}
+
+// thread-per-environment kernels (tapenv_add_blocks).  blocks: f32 [B,dim] (.astype(int), tools.py:3675)
+template <int DIM>
+__global__ void __launch_bounds__(64)
+lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const float *blk = blocks + (size_t)b * DIM;
+    const int anomaly = lb_env_add_block<DIM>(c, st, b, (int)blk[0], DIM == 3 ? (int)blk[1] : 1, (int)blk[DIM - 1]);
     if (anomaly) st.flags[b] |= anomaly;
-    if (dec_dyn) {                                   // heightmap encodings (tools.py:3716-3743), serial form
-        float *o = dec_dyn + (size_t)b * c.enc_len;
-        const int *h = s.h;
-        if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
-        else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
-        else {
-            for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
-                o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
-                o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
+    if (dec_dyn) encode_heightmap_serial(c, st.heightmap + (size_t)b * (DIM == 2 ? c.W : c.W * c.L), dec_dyn + (size_t)b * c.enc_len);
+}
+
+__global__ void __launch_bounds__(64)
+macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    grid_dependency_sync();
+    if (b >= c.B) return;
+    const float *blk = blocks + (size_t)b * 3;
+    const int anomaly = macs3d_env_add_block(c, st, b, (int)blk[0], (int)blk[1], (int)blk[2]);
+    if (anomaly) st.flags[b] |= anomaly;
+    if (dec_dyn) encode_heightmap_serial(c, st.heightmap + (size_t)b * c.W * c.L, dec_dyn + (size_t)b * c.enc_len);
+}
+
+// Container.add_new_block inside a warp-per-environment kernel: lane 0 walks, the warp encodes (and, optionally, emits
+// calc_ratio of the state left behind).  STRAT: STRAT_LB (dim from the config) or STRAT_MACS3D.
+template <int STRAT>
+__device__ __forceinline__ void voxel_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane, int bx, int by, int bz,
+                                                float *dec_dyn, int extra_flags, float *reward) {
+    if (lane == 0) {
+        int anomaly = extra_flags;
+        if (STRAT == STRAT_MACS3D) anomaly |= macs3d_env_add_block(c, st, b, bx, by, bz);
+        else if (c.dim == 2) anomaly |= lb_env_add_block<2>(c, st, b, bx, 1, bz);
+        else anomaly |= lb_env_add_block<3>(c, st, b, bx, by, bz);
+        if (anomaly) st.flags[b] |= anomaly;
+    }
+    __syncwarp();                                    // lane 0's global writes are visible to the warp behind this barrier
+    if (dec_dyn || reward) {
+        const int cells = c.dim == 2 ? c.W : c.W * c.L;
+        const int h = lane < cells ? *((volatile int *)(st.heightmap + (size_t)b * cells + lane)) : 0;
+        if (dec_dyn) {
+            if (c.dim == 3) {
+                const int x = (int)(((unsigned)lane * c.inv_L) >> 16), y = lane - x * c.L;
+                encode_heightmap_3d(c, lane, x, y, h, dec_dyn + (size_t)b * c.enc_len);
+            } else encode_heightmap_2d(c, lane, h, dec_dyn + (size_t)b * c.enc_len);
+        }
+        if (reward) {
+            const int height = warp_max(h);
+            if (lane == 0) {
+                const int4 s4 = st.scal[b];                 // written by this very thread
+                reward[b] = (float)calc_ratio_dev(c, s4.x, s4.y, s4.z, s4.w, height);
             }
         }
     }
@@ -569,7 +630,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
-    const int DIM = STRAT == STRAT_LB ? c.dim : DIMC;
+    const int DIM = dim_of<STRAT>(c);
     const int S = SH::S(c);
     const float *srow = env_ptr(static_, b, SH::static_env(c));
     const float *din = env_ptr(dynamic_in, b, SH::dyn_env(c));
@@ -611,14 +672,10 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     //     With a single resident wave (B <= ~4.7k) it runs FIRST so its ~250 warp-instructions overlap the HBM
     //     read phase; with many waves other warps provide that overlap and the shorter register live range wins.
     const int bx = (int)e0;
-    const int by = STRAT == STRAT_LBG3D ? (int)e1 : 1;
+    const int by = DIM == 3 ? (int)e1 : 1;
     const int bz = (int)(DIM == 3 ? e2 : e1);
-    if (STRAT == STRAT_LB) {                         // hand the gathered block to lb_kernel (launched right behind)
-        if (lane < DIM) st.pending[(size_t)b * 4 + lane] = dimv;
-        if (lane == 0 && badp) st.flags[b] |= 4;
-    }
     constexpr bool SMALLN = NT > 0 && NT <= 32;
-    if (PLACE_FIRST && STRAT != STRAT_LB)
+    if (PLACE_FIRST)
         container_add_block<STRAT, SMALLN>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, badp ? 4 : 0, reward);
 
     // (4) masked copy + column reductions of the precedence tensor
@@ -630,7 +687,7 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     mask_pass<SH>(c, lane, true, m0, m1, SH::mod_n(c, p), bits.blocked(), env_ptr(cur_mask_out, b, (unsigned)S),
                   env_ptr(mask_out, b, (unsigned)S));
 
-    if (!PLACE_FIRST && STRAT != STRAT_LB)
+    if (!PLACE_FIRST)
         container_add_block<STRAT, SMALLN>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, badp ? 4 : 0, reward);
 }
 
@@ -750,10 +807,7 @@ __device__ __forceinline__ void mul_place(const DevCfg &c, const StatePtrs &sa, 
         for (int k = 0; k < 2; ++k) {
             if (valid && k == tgt) continue;          // already written by add_new_block
             const StatePtrs &o = k ? sb : sa;
-            EnvRegs<STRAT> e2; e2.load(c, o, b, lane);
-            float *out = dec_dyn + ((size_t)b * 2 + k) * c.enc_len;
-            if (STRAT == STRAT_LBG3D) encode_heightmap_3d(c, lane, e2.x, e2.y, e2.h, out);
-            else encode_heightmap_2d(c, lane, e2.h, out);
+            encode_state_heightmap(c, o, b, lane, dim_of<STRAT>(c), dec_dyn + ((size_t)b * 2 + k) * c.enc_len);
         }
     }
 }
@@ -765,11 +819,11 @@ step_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const int64_t *__restrict_
                 float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_static, int dec_rows,
                 float *__restrict__ dec_dyn) {
     typedef Shape<0, 0, 0> SH;
-    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
     unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
+    const int DIM = dim_of<STRAT>(c);
     const int S = c.S;
     const float *srow = env_ptr(static_, b, c.static_env);
     const float *din = env_ptr(dynamic_in, b, c.dyn_env);
@@ -798,11 +852,11 @@ template <int STRAT>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 add_blocks_mul_kernel(DevCfg c, StatePtrs sa, StatePtrs sb, const float *__restrict__ blocks, const float *__restrict__ target_ids,
                       float *__restrict__ dec_dyn) {
-    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
     unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
+    const int DIM = dim_of<STRAT>(c);
     const float *blk = blocks + (size_t)b * DIM;
     const int bx = (int)blk[0], by = DIM == 3 ? (int)blk[1] : 1, bz = (int)blk[DIM - 1];
     mul_place<STRAT>(c, sa, sb, b, lane, (int)target_ids[b], bx, by, bz, dec_dyn, ems_keys_none, 0);
@@ -838,14 +892,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta)
 episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const float *__restrict__ dynamic,
                const int64_t *__restrict__ ptr_seq, int steps, float *__restrict__ reward,
                float *__restrict__ cur_mask_out, float *__restrict__ mask_out, float *__restrict__ dec_dyn) {
-    constexpr int DIM = STRAT == STRAT_LBG3D ? 3 : 2;
+    constexpr bool VOXEL = STRAT == STRAT_LB || STRAT == STRAT_MACS3D;
+    constexpr int DIMMAX = (STRAT == STRAT_LBG3D || VOXEL) ? 3 : 2;
     __shared__ unsigned rows[kWarpsPerCta][3][kMaxBlocks][2];          // bit j of (band, row): dynamic[band*n+row][j] != 0
-    __shared__ float stat[kWarpsPerCta][1 + DIM][kMaxCandidates];
+    __shared__ float stat[kWarpsPerCta][1 + DIMMAX][kMaxCandidates];
     unsigned *const ems_keys_none = nullptr;       // (the per-warp EMS key list of r01; the MACS scan no longer needs shared memory)
     int lane, warp; const int b = env_index(lane, warp);
     grid_dependency_sync();
     if (b >= c.B) return;
     const int S = c.S, n = c.n;
+    const int DIM = dim_of<STRAT>(c);
     const float *din = env_ptr(dynamic, b, c.dyn_env);
     const float *srow = env_ptr(static_, b, c.static_env);
 
@@ -878,18 +934,15 @@ episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const 
     __syncwarp();
 
     // ---- reset (Container.__init__, tools.py:3611-3661) ----
-    const int cells = (STRAT == STRAT_LBG3D) ? c.W * c.L : c.W;
-    for (int i = lane; i < c.cap * DIM; i += 32) { st.positions[(size_t)b * c.cap * DIM + i] = 0; st.blocks[(size_t)b * c.cap * DIM + i] = 0; }
-    for (int i = lane; i < c.cap; i += 32) st.stable[(size_t)b * c.cap + i] = 0;
-    if (lane == 0) st.flags[b] = 0;
+    const int cells = DIM == 3 ? c.W * c.L : c.W;
+    reset_env_state(c, st, b, lane);
+    __syncwarp();
     EnvRegs<STRAT> e;
     e.h = 0; e.sc.valid = e.sc.empty = e.sc.nstable = e.sc.k = 0;
     e.x = 0; e.y = 0;
     if (STRAT == STRAT_LBG3D) { e.x = (int)(((unsigned)lane * c.inv_L) >> 16); e.y = lane - e.x * c.L; }
 #pragma unroll
     for (int s = 0; s < 2; ++s) e.hist.x[s] = e.hist.z[s] = e.hist.xx[s] = e.hist.zz[s] = 0;
-    if (lane < cells) st.heightmap[(size_t)b * cells + lane] = 0;
-    if (lane == 0) st.scal[b] = make_int4(0, 0, 0, 0);
 
     unsigned long long mask = S >= 64 ? ~0ull : ((1ull << S) - 1ull);      // model.py:297: ones
     for (int t = 0; t < steps; ++t) {
@@ -899,7 +952,7 @@ episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const 
         const int real = (int)stat[warp][0][p];                             // pack.py:347
         const int realm = p - (int)(((unsigned)p * c.inv_n) >> 16) * n;     // pack.py:314-316
         const int bx = (int)stat[warp][1][p];
-        const int by = STRAT == STRAT_LBG3D ? (int)stat[warp][2][p] : 1;
+        const int by = DIM == 3 ? (int)stat[warp][2][p] : 1;
         const int bz = (int)stat[warp][DIM][p];
         __syncwarp();
         if (lane < 3 * 2 && real >= 0 && real < n && (lane >> 1) < c.update_time) rows[warp][lane >> 1][real][lane & 1] = 0u;   // pack.py:370-374
@@ -936,8 +989,14 @@ episode_kernel(DevCfg c, StatePtrs st, const float *__restrict__ static_, const 
         }
     }
     if (reward) {
-        const int height = warp_max(lane < cells ? e.h : 0);
-        if (lane == 0) reward[b] = (float)calc_ratio_dev(c, e.sc.valid, e.sc.empty, e.sc.nstable, e.sc.k, height);
+        if (VOXEL) {                                 // the state lives in global memory: Container.calc_ratio from there
+            __syncwarp();
+            const int height = warp_max(encode_state_heightmap(c, st, b, lane, DIM, nullptr));
+            if (lane == 0) { const int4 s4 = st.scal[b]; reward[b] = (float)calc_ratio_dev(c, s4.x, s4.y, s4.z, s4.w, height); }
+        } else {
+            const int height = warp_max(lane < cells ? e.h : 0);
+            if (lane == 0) reward[b] = (float)calc_ratio_dev(c, e.sc.valid, e.sc.empty, e.sc.nstable, e.sc.k, height);
+        }
     }
 }
 
@@ -1137,7 +1196,7 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
     if (STRAT >= 0 && ptr) {
         if (dec_static && lane < w.dim) dec_static[(size_t)b * w.dim + lane] = dimv;
         const int bx = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 0);
-        const int by = ES == STRAT_LBG3D ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
+        const int by = w.dim == 3 ? (int)__shfl_sync(TAPENV_FULL_MASK, dimv, 1) : 1;
         const int bz = (int)__shfl_sync(TAPENV_FULL_MASK, dimv, w.dim - 1);
         if (place)
             container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
@@ -1386,15 +1445,12 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
         else { if (d.n == 20 && d.R == 2) TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 20, 2); else TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 0, 0); }
         return launch_status();
     }
-    if (strat == STRAT_LB || strat == STRAT_MACS3D) { // tensor pass (no placement) + the thread-per-environment placement kernel
-        if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
-                         dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr, (float *)nullptr);
-        else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, d, st, ptr, static_, dynamic_in, mask_in,
-                    dynamic_out, cur_mask_out, mask_out, dec_static_out, (float *)nullptr, (float *)nullptr);
-        if (strat == STRAT_MACS3D) launch(macs3d_kernel, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
-        else if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
-        else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, (const float *)nullptr, dec_dynamic_out);
-        if (reward_out) launch(reward_kernel, (d.B + 127) / 128, 128, s, d, st, reward_out);
+    if (strat == STRAT_LB) {                          // voxel-state strategies: tensor pass by the warp, grid walk by lane 0, ONE launch
+        if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
+        else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
+    } else if (strat == STRAT_MACS3D) {
+        if (fast) launch(step_kernel<STRAT_MACS3D, true, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
+        else launch(step_kernel<STRAT_MACS3D, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else if (strat == STRAT_LBG2D) {
         if (fast && bot && d.n == 10 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 10, 2);
         else if (fast && bot && d.n == 20 && d.R == 2) TAPENV_STEP_SHAPE(STRAT_LBG2D, 20, 2);
@@ -1482,12 +1538,13 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
     if (strat < 0) return TAPENV_EUNSUPPORTED;
-    if (strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;      // voxel-grid strategies: stepwise API only
     if (steps < 0 || steps > 64 || steps > cfg->capacity) return TAPENV_ELIMIT;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !static_ || !dynamic || (steps > 0 && !ptr_seq)) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (strat == STRAT_LBG2D) launch(episode_kernel<STRAT_LBG2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    if (strat == STRAT_LB) launch(episode_kernel<STRAT_LB>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    else if (strat == STRAT_MACS3D) launch(episode_kernel<STRAT_MACS3D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
+    else if (strat == STRAT_LBG2D) launch(episode_kernel<STRAT_LBG2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
     else if (strat == STRAT_LBG3D) launch(episode_kernel<STRAT_LBG3D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
     else launch(episode_kernel<STRAT_MACS2D>, grid, block, s, d, st, static_, dynamic, ptr_seq, (int)steps, reward_out, cur_mask_out, mask_out, dec_dynamic_out);
     return launch_status();
@@ -1526,7 +1583,7 @@ int tapenv_step_mul(const tapenv_config *cfg, void *state_a, void *state_b, cons
                     float *mask_out, float *dec_static_out, int32_t dec_static_rows, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
     if (cfg->static_rows != 2 + cfg->dim) return TAPENV_ESHAPE;
     if (dec_static_rows != cfg->dim && dec_static_rows != cfg->dim + 1) return TAPENV_ESHAPE;
     if (d.B == 0) return TAPENV_OK;
@@ -1543,6 +1600,8 @@ int tapenv_step_mul(const tapenv_config *cfg, void *state_a, void *state_b, cons
     } while (0)
     if (strat == STRAT_LBG2D) TAPENV_MUL(STRAT_LBG2D);
     else if (strat == STRAT_LBG3D) TAPENV_MUL(STRAT_LBG3D);
+    else if (strat == STRAT_LB) TAPENV_MUL(STRAT_LB);
+    else if (strat == STRAT_MACS3D) TAPENV_MUL(STRAT_MACS3D);
     else TAPENV_MUL(STRAT_MACS2D);
     return launch_status();
 }
@@ -1551,11 +1610,13 @@ int tapenv_add_blocks_mul(const tapenv_config *cfg, void *state_a, void *state_b
                           const float *target_ids, float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
     if (d.B == 0) return TAPENV_OK;
     if (!state_a || !state_b || state_a == state_b || !blocks || !target_ids) return TAPENV_EINVAL;
     const StatePtrs sa = stateptrs_of(cfg, state_a), sb = stateptrs_of(cfg, state_b);
-    if (strat == STRAT_LBG2D) launch(add_blocks_mul_kernel<STRAT_LBG2D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    if (strat == STRAT_LB) launch(add_blocks_mul_kernel<STRAT_LB>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    else if (strat == STRAT_MACS3D) launch(add_blocks_mul_kernel<STRAT_MACS3D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
+    else if (strat == STRAT_LBG2D) launch(add_blocks_mul_kernel<STRAT_LBG2D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
     else if (strat == STRAT_LBG3D) launch(add_blocks_mul_kernel<STRAT_LBG3D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
     else launch(add_blocks_mul_kernel<STRAT_MACS2D>, grid, block, s, d, sa, sb, blocks, target_ids, dec_dynamic_out);
     return launch_status();
@@ -1668,7 +1729,7 @@ int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_wind
     if (cfg->batch != wcfg->batch || cfg->dim != wcfg->dim || cfg->blocks_num != wcfg->window ||
         cfg->rotate_types != wcfg->rotate_types || cfg->static_rows != 1 + cfg->dim) return TAPENV_ESHAPE;
     const int strat = strategy_kernel(cfg);
-    if (strat < 0 || strat == STRAT_LB || strat == STRAT_MACS3D) return TAPENV_EUNSUPPORTED;      // voxel-grid strategies: tapenv_window_next + tapenv_add_blocks
+    if (strat < 0) return TAPENV_EUNSUPPORTED;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !wstate || !pred || !blocks || !ptr || !static_out || !dynamic_out) return TAPENV_EINVAL;
     const WinCfg w = wincfg_of(wcfg);
@@ -1684,6 +1745,8 @@ int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_wind
     } while (0)
     if (strat == STRAT_LBG2D) TAPENV_ROLL(STRAT_LBG2D);
     else if (strat == STRAT_LBG3D) TAPENV_ROLL(STRAT_LBG3D);
+    else if (strat == STRAT_LB) TAPENV_ROLL(STRAT_LB);
+    else if (strat == STRAT_MACS3D) TAPENV_ROLL(STRAT_MACS3D);
     else TAPENV_ROLL(STRAT_MACS2D);
     return launch_status();
 }

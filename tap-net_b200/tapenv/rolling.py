@@ -204,18 +204,7 @@ class RollingRunner(object):
         ptr = _dev(ptr, "ptr", torch.int64)
         n, T = win.child_graph_size, self.total
         s = self.slot
-        unfused = env.cfg.strategy == _capi.LB or (env.cfg.strategy == _capi.MACS and env.block_dim == 3)
-        if self.t < T - n and unfused:                 # voxel-state strategies (thread per environment): three launches
-            o = s ^ 1
-            st_cur = self.static[self.sslot]
-            blocks = torch.gather(st_cur[:, 1:], 2, ptr.view(-1, 1, 1).expand(-1, env.block_dim, 1)).squeeze(2)   # rolling.py:417-431
-            self.dec_static.copy_(blocks)
-            self.dec_dyn.copy_(env.add_new_blocks(blocks).reshape(env.batch_size, -1))                             # rolling.py:436
-            win.remove_block(ptr)                                                                                   # rolling.py:636-640
-            win.convert_to_input(out=(self.static[self.sslot ^ 1], self.dynamic[o]), masks=(self.cur[o], self.mask[o]))
-            self.slot = o
-            self.sslot ^= 1
-        elif self.t < T - n:                           # one_step window: place + advance the window, ONE launch
+        if self.t < T - n:                             # one_step window: place + advance the window, ONE launch (every strategy)
             o = s ^ 1
             with torch.cuda.device(env.device):
                 _capi.check(_capi.lib.tapenv_rolling_step(
@@ -328,10 +317,10 @@ class RollingHostPipeline(object):
             after_episode(s["runner"])
         s["reward"].copy_(r, non_blocking=True)
         tail = s["runner"].tail
-        if tail.overlap:                                         # the totals arrive on the exchange's side stream
-            with torch.cuda.stream(tail.exchange.stream):
-                s["sums"].copy_(tail.total, non_blocking=True)
-                tail.reduced.record(tail.exchange.stream)
+        if tail.overlap:                                         # the statistics arrive on the side stream
+            with torch.cuda.stream(tail.stream):
+                s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
+                tail.reduced.record(tail.stream)
         else:
             s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
         s["done"].record(compute)

@@ -9,21 +9,36 @@ import torch
 from .containers import BatchedContainers
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One high-priority side stream per device for end-of-episode statistics without an exchange."""
+    key = torch.device(device).index
+    st = _side_streams.get(key)
+    if st is None:
+        lo, hi = torch.cuda.Stream.priority_range()
+        st = _side_streams[key] = torch.cuda.Stream(device=device, priority=hi)
+    return st
+
+
 class RewardTail(object):
     """The end of an episode: the deterministic (sum r, sum r^2, B) of the reward vector and, on several GPUs, the exchange
     of those triples (tapenv_reward_sums / PeerExchange) -- the operand of the critic-baseline statistics
     (trainer.py:216-225).
 
     overlap=False: one launch at the tail of the episode (captured in its CUDA graph).
-    overlap=True (default with an exchange): the launch goes to the exchange's high-priority side stream right behind the
-    last decode step; the next episode's reset does NOT wait for the poll on the slowest rank (r01: the in-stream poll
-    cost ~4 us per 62 us episode at 8 GPUs).  `sums` / `total` are then valid after `reduced` (wait_total())."""
+    overlap=True (default): the launch goes to a high-priority side stream (the exchange's, if there is one) right behind
+    the last decode step; the next episode's reset does NOT wait for the reduction or for the poll on the slowest rank
+    (r01: the in-stream poll cost ~4 us per 62 us episode at 8 GPUs; r02k at 2 GPUs: 60.2 -> 55.0 us per episode).
+    `sums` / `total` are then valid after `reduced` (wait_total())."""
 
     def __init__(self, env, partial_sums=True, exchange=None, overlap=None):
         self.env, self.exchange = env, exchange
         self.enabled = bool(partial_sums) or exchange is not None
-        self.overlap = (exchange is not None) if overlap is None else (bool(overlap) and exchange is not None)
+        self.overlap = self.enabled and (True if overlap is None else bool(overlap))
         dev = env.device
+        self.stream = exchange.stream if exchange is not None else (_side_stream(dev) if self.overlap else None)
         self.sums = torch.zeros(3, dtype=torch.float64, device=dev) if self.enabled else None
         self.total = torch.zeros(3, dtype=torch.float64, device=dev) if exchange is not None else None
         self.posted = torch.cuda.Event()
@@ -49,7 +64,7 @@ class RewardTail(object):
         if not (self.enabled and self.overlap):
             return
         cur = torch.cuda.current_stream(self.env.device)
-        xs = self.exchange.stream
+        xs = self.stream
         self.posted.record(cur)
         xs.wait_event(self.posted)
         with torch.cuda.stream(xs):
@@ -265,10 +280,10 @@ class HostPipeline(object):
             after_episode(s["runner"])                           # e.g. the cross-rank reduction of runner.sums
         s["reward"].copy_(r, non_blocking=True)
         tail = s["runner"].tail
-        if tail.overlap:                                         # the totals arrive on the exchange's side stream
-            with torch.cuda.stream(tail.exchange.stream):
-                s["sums"].copy_(tail.total, non_blocking=True)
-                tail.reduced.record(tail.exchange.stream)        # "consumed" now includes the D2H read of the totals
+        if tail.overlap:                                         # the statistics arrive on the side stream
+            with torch.cuda.stream(tail.stream):
+                s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
+                tail.reduced.record(tail.stream)                 # "consumed" now includes the D2H read of the totals
         else:
             s["sums"].copy_(tail.total if tail.total is not None else tail.sums, non_blocking=True)
         s["done"].record(compute)

@@ -273,8 +273,8 @@ def test_reward_partial_sums_are_deterministic():
     assert abs(float(s[0]) - r64.sum()) < 1e-9 and abs(float(s[1]) - (r64 ** 2).sum()) < 1e-9
 
 
-@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[5], CASES[7], CASES[8], CASES[9]],
-                         ids=["2d-soft", "2d-hard", "2d-w9", "macs-rand", "macs-ppsg", "3d-soft", "3d-hard"])
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[5], CASES[7], CASES[8], CASES[9], CASES[11], CASES[13], CASES[15], CASES[16]],
+                         ids=["2d-soft", "2d-hard", "2d-w9", "macs-rand", "macs-ppsg", "3d-soft", "3d-hard", "lb-2d", "lb-3d", "macs3d-soft", "macs3d-hard"])
 def test_whole_episode_kernel_matches_stepwise_oracle(case):
     """K7 (tapenv_episode): one launch per episode == reset + n steps + calc_ratio of the oracle."""
     torch = _torch()
@@ -775,3 +775,38 @@ def test_macs_long_histories_two_slots(W, n, rt):
     r = env.calc_ratio().cpu().numpy().astype(np.float64)
     want_r = np.array([c.calc_ratio() for c in conts])
     assert np.abs(r - want_r).max() <= REWARD_TOL
+
+
+@pytest.mark.parametrize("fixture,size,rt,strat,it", [("rand2d_n10.npz", [5, 50], "C+P+S-lb-soft", "LB", "mul-with"),
+                                                      ("rand3d_n10.npz", [5, 5, 50], "C+P+S-lb-hard", "LB", "mul"),
+                                                      ("rand3d_n10.npz", [5, 5, 50], "C+P+S-mcs-soft", "MACS", "mul-with")])
+def test_two_container_inputs_voxel_strategies(fixture, size, rt, strat, it):
+    """tapenv_step_mul for the voxel-state strategies (LB, MACS 3D): r01 returned TAPENV_EUNSUPPORTED; against the oracle's
+    two-container rollout (tests/rollout.py:oracle_rollout_mul), every step."""
+    torch = _torch()
+    import tapenv
+    from tests.rollout import oracle_rollout_mul
+    B = 96
+    static, dynamic = load_inputs(fixture, B)
+    dim = len(size)
+    R = 2 if dim == 2 else 6
+    n = static.shape[2] // R
+    rng = np.random.RandomState(5)
+    ids = np.tile(rng.randint(0, 2, size=(B, 1, n)).astype(np.float32), (1, 1, R))
+    static = np.ascontiguousarray(np.concatenate([static, ids], 1))
+    ptrs = random_valid_ptrs(static[:, :1 + dim], dynamic, size, seed=9)
+    want = oracle_rollout_mul(static, dynamic, ptrs, size, rt, "diff", strat, it)
+    env = tapenv.BatchedContainerPairs(size, n, rt, "diff", packing_strategy=strat, batch_size=B, input_type=it)
+    st, dyn = torch.from_numpy(static).cuda(), torch.from_numpy(dynamic).cuda()
+    cur, mask = env.reset(dyn)
+    for k in range(n):
+        dyn, cur, mask, dec_static, dec_dyn = env.step(torch.from_numpy(ptrs[k]).cuda(), st, dyn, mask)
+        assert np.array_equal(env.a.heightmap.cpu().numpy().reshape(B, -1), want["hm_a"][k]), k
+        assert np.array_equal(env.b.heightmap.cpu().numpy().reshape(B, -1), want["hm_b"][k]), k
+        assert np.array_equal(dec_dyn.cpu().numpy().reshape(B, -1), want["dec_dyn"][k].astype(np.float32)), k
+        assert np.array_equal(dec_static.cpu().numpy(), want["dec_static"][k]), k
+        assert np.array_equal(cur.cpu().numpy(), want["cur_mask"][k + 1]) and np.array_equal(mask.cpu().numpy(), want["mask"][k])
+    assert np.array_equal(env.a.positions.cpu().numpy(), want["positions_a"])
+    assert np.array_equal(env.b.positions.cpu().numpy(), want["positions_b"])
+    assert np.array_equal(env.calc_ratio().cpu().numpy(), want["scores"])
+    env.check_flags()
