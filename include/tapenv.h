@@ -49,8 +49,7 @@ extern "C" {
 #define TAPENV_ELIMIT (-3)    /* shape outside the compiled limits (see tapenv_limits) */
 #define TAPENV_ESHAPE (-4)    /* S != n*R, dyn_rows too small, ... */
 #define TAPENV_ECUDA (-5)     /* the launch itself failed (cudaGetLastError) */
-#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not served by this entry point (the 'rot-old' layout; the
-                                    voxel-state strategies LB / MACS 3D in tapenv_episode, tapenv_step_mul, tapenv_rolling_step) */
+#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not built here (the legacy 'rot-old' input layout) */
 
 /* packing_strategy (tools.py:3607, :3679-3701) */
 #define TAPENV_LB_GREEDY 0
@@ -110,7 +109,7 @@ typedef struct tapenv_state_layout {
     size_t voxels;     /* i16 [B,cells,H]  LB and MACS 3D: 0 empty, -1 empty under a block, k+1 block id   (tools.py:3629) */
     size_t lists;      /* i8  [B,nlists,max(capacity+2, width+4)]  LB: level_free_space x lists (tools.py:3649-3653); MACS 3D: the
                           per-(level,row) interval lists (tools.py:3644-3648); byte 0 = length */
-    size_t pending;    /* f32 [B,4]  LB and MACS 3D: the gathered block handed from the fused step's tensor pass to the placement pass */
+    size_t pending;    /* f32 [B,4]  reserved (r01 handed the gathered block of LB / MACS 3D to a second kernel through it) */
     size_t total;      /* == tapenv_state_bytes() */
 } tapenv_state_layout;
 

@@ -459,18 +459,18 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
     EnvRegs<STRAT> e; e.load(c, st, b, lane);
     const float *blk = blocks + (size_t)b * c.dim;
     const int bx = (int)blk[0];                                            // .astype(int) tools.py:3689
-    const int by = STRAT == STRAT_LBG3D ? (int)blk[1] : 1;
+    const int by = c.dim == 3 ? (int)blk[1] : 1;
     const int bz = (int)blk[c.dim - 1];
     container_add_block<STRAT>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
 }
 
 // ------------------------------------------------------------------------------------
 // Voxel-state strategies (LB tools.py:1602-1914, MACS 3D :2751-3165): the placement is a sequential walk over a voxel grid
-// and incrementally edited lists kept in the state buffer.  One THREAD performs it for one environment:
-//   - lb_kernel / macs3d_kernel: thread-per-environment grids (tapenv_add_blocks),
-//   - voxel_add_block: lane 0 of the environment's warp inside the fused kernels (step / episode / rolling / mul), the other
-//     lanes wait and then encode the heightmap -- one launch per decode step, and no divergence between environments
-//     that share a warp (r02: faster than the thread-per-environment kernel behind a separate tensor pass).
+// and incrementally edited lists kept in the state buffer.  One THREAD performs it for one environment: lane 0 of the
+// environment's warp (voxel_add_block) inside every kernel of the library -- add_blocks / step / episode / rolling / mul --
+// while the other lanes wait and then encode the heightmap.  One launch per decode step, and no divergence between
+// environments sharing a warp: r01's thread-per-environment kernels behind a separate tensor pass took 117 / 340 / 13 700 us
+// per step at B=4096 (LB 2D / LB 3D / MACS 3D), this form 42 / 99 / 2 940 us (profiles/r02m_voxel_ab.txt).
 // ------------------------------------------------------------------------------------
 // Container.add_new_block for one environment, LB strategy, executed by ONE thread.  Returns the anomaly bits.
 template <int DIM>
@@ -537,44 +537,6 @@ __device__ __forceinline__ int macs3d_env_add_block(const DevCfg &c, const State
     st.stable[(size_t)b * c.cap + k] = stable;
     st.scal[b] = out;
     return anomaly;
-}
-
-// heightmap encodings (tools.py:3716-3743), serial form for the thread-per-environment kernels
-__device__ __forceinline__ void encode_heightmap_serial(const DevCfg &c, const int *h, float *o) {
-    const int cells = c.dim == 2 ? c.W : c.W * c.L;
-    if (c.hm_type == TAPENV_HM_FULL) { for (int i = 0; i < cells; ++i) o[i] = (float)h[i]; }
-    else if (c.hm_type == TAPENV_HM_ZERO) { int m = h[0]; for (int i = 1; i < cells; ++i) m = min(m, h[i]); for (int i = 0; i < cells; ++i) o[i] = (float)(h[i] - m); }
-    else if (c.dim == 2) { for (int i = 0; i + 1 < c.W; ++i) o[i] = (float)(h[i + 1] - h[i]); }
-    else {
-        for (int x = 0; x < c.W; ++x) for (int y = 0; y < c.L; ++y) {
-            o[x * c.L + y] = x > 0 ? (float)(h[x * c.L + y] - h[(x - 1) * c.L + y]) : 0.f;
-            o[cells + x * c.L + y] = y > 0 ? (float)(h[x * c.L + y] - h[x * c.L + y - 1]) : 0.f;
-        }
-    }
-}
-
-// thread-per-environment kernels (tapenv_add_blocks).  blocks: f32 [B,dim] (.astype(int), tools.py:3675)
-template <int DIM>
-__global__ void __launch_bounds__(64)
-lb_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    grid_dependency_sync();
-    if (b >= c.B) return;
-    const float *blk = blocks + (size_t)b * DIM;
-    const int anomaly = lb_env_add_block<DIM>(c, st, b, (int)blk[0], DIM == 3 ? (int)blk[1] : 1, (int)blk[DIM - 1]);
-    if (anomaly) st.flags[b] |= anomaly;
-    if (dec_dyn) encode_heightmap_serial(c, st.heightmap + (size_t)b * (DIM == 2 ? c.W : c.W * c.L), dec_dyn + (size_t)b * c.enc_len);
-}
-
-__global__ void __launch_bounds__(64)
-macs3d_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, float *__restrict__ dec_dyn) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    grid_dependency_sync();
-    if (b >= c.B) return;
-    const float *blk = blocks + (size_t)b * 3;
-    const int anomaly = macs3d_env_add_block(c, st, b, (int)blk[0], (int)blk[1], (int)blk[2]);
-    if (anomaly) st.flags[b] |= anomaly;
-    if (dec_dyn) encode_heightmap_serial(c, st.heightmap + (size_t)b * c.W * c.L, dec_dyn + (size_t)b * c.enc_len);
 }
 
 // Container.add_new_block inside a warp-per-environment kernel: lane 0 walks, the warp encodes (and, optionally, emits
@@ -1391,11 +1353,9 @@ int tapenv_add_blocks(const tapenv_config *cfg, void *state, const float *blocks
     if (d.B == 0) return TAPENV_OK;
     if (!state || !blocks) return TAPENV_EINVAL;
     const StatePtrs st = stateptrs_of(cfg, state);
-    if (strat == STRAT_MACS3D) launch(macs3d_kernel, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
-    else if (strat == STRAT_LB) {
-        if (d.dim == 2) launch(lb_kernel<2>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
-        else launch(lb_kernel<3>, (d.B + 63) / 64, 64, s, d, st, blocks, dec_dynamic_out);
-    } else if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    if (strat == STRAT_MACS3D) launch(add_blocks_kernel<STRAT_MACS3D>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    else if (strat == STRAT_LB) launch(add_blocks_kernel<STRAT_LB>, grid, block, s, d, st, blocks, dec_dynamic_out);
+    else if (strat == STRAT_LBG2D) launch(add_blocks_kernel<STRAT_LBG2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     else if (strat == STRAT_LBG3D) launch(add_blocks_kernel<STRAT_LBG3D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     else launch(add_blocks_kernel<STRAT_MACS2D>, grid, block, s, d, st, blocks, dec_dynamic_out);
     return launch_status();

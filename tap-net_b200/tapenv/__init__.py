@@ -14,7 +14,7 @@ from .ops import update_dynamic, update_mask
 from .containers import BatchedContainers, BatchedContainerPairs, Container
 from .runner import EpisodeRunner, HostPipeline
 from .decode import DecodeLoop, RollingDecodeLoop
-from . import adapters, dist
+from . import adapters, dist, generators
 from .dataset import PACKDataset, pack_inputs
 from .episode import calc_positions_lb_greedy, calc_positions_mcs, reward
 from .dropin import install, uninstall

@@ -7,14 +7,14 @@
     tapenv.uninstall()
 
 Replaces exactly the hot-path symbols: pack.update_dynamic, pack.update_mask, pack.reward,
-tools.Container, tools.calc_positions_lb_greedy, tools.calc_positions_mcs (and generate.InitialContainer when `generate` is
-passed).  Everything else of the reference keeps running as it is.  The two whole-episode functions fall back to the saved
+tools.Container, tools.calc_positions_lb_greedy, tools.calc_positions_mcs (and generate.InitialContainer +
+generate.generate_blocks when `generate` is passed).  Everything else of the reference keeps running as it is.  The two whole-episode functions fall back to the saved
 reference function for shapes beyond the compiled limits (e.g. the 7x7 initial container of the 3D generators has 49 cells,
 tapenv_limits.max_cells_3d is 32) -- the dataset generators call them with containers the network never sees."""
 import functools
 import sys
 
-from . import _capi, containers, episode, ops, rolling
+from . import _capi, containers, episode, generators, ops, rolling
 
 _saved = []
 
@@ -54,7 +54,9 @@ def install(pack=None, tools=None, generate=None):
                  (tools, "calc_positions_mcs",
                   _with_fallback(episode.calc_positions_mcs, getattr(tools, "calc_positions_mcs", None)))]
     if generate is not None:
-        repl += [(generate, "InitialContainer", rolling.InitialContainer)]
+        generators._original = getattr(generate, "generate_blocks", None)
+        repl += [(generate, "InitialContainer", rolling.InitialContainer),
+                 (generate, "generate_blocks", generators.generate_blocks)]
     for mod, name, new in repl:
         _saved.append((mod, name, getattr(mod, name, None)))
         setattr(mod, name, new)
@@ -62,6 +64,7 @@ def install(pack=None, tools=None, generate=None):
 
 
 def uninstall():
+    generators._original = None
     while _saved:
         mod, name, old = _saved.pop()
         if old is None:

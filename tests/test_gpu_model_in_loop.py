@@ -157,3 +157,41 @@ def test_generate_blocks_runs_after_install(installed):
         tapenv.install(mods["pack"], mods["tools"])
         for a, b in zip(got, want):
             assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.parametrize("dim,W", [(2, 7), (2, 0), (3, 5), (3, 7)])
+def test_create_dataset_identical_with_batched_generator(dim, W, tmp_path, monkeypatch):
+    """pack.create_dataset (pack.py:580-667) with generate.generate_blocks replaced by the speculative GPU rejection loop
+    (tapenv.generators): byte-identical dataset files under the same seed -- same block sets accepted, same NumPy stream
+    position afterwards (the shuffle / random_integers calls between the samples see the same state).  W=7 in 3D (49 cells)
+    and W=0 in 3D (random width up to 10) exceed the compiled limits and run the saved reference function."""
+    import contextlib
+    import io
+    import os
+    import tapenv
+    mods = ref_model.reference_modules()
+    pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
+
+    def build(sub):
+        d = tmp_path / sub
+        d.mkdir()
+        monkeypatch.chdir(d)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            train_dir, valid_dir = pack.create_dataset(10, 10, 4, dim, W, 50, 1, [1, 5], seed=77)
+        out = {}
+        for sdir in (train_dir, valid_dir):
+            for f in sorted(os.listdir(sdir)):
+                out[os.path.join(sdir, f)] = open(os.path.join(sdir, f)).read()
+        return out
+
+    want = build("reference")
+    tapenv.install(pack, tools, generate)
+    try:
+        assert generate.generate_blocks is tapenv.generators.generate_blocks
+        got = build("tapenv")
+    finally:
+        tapenv.uninstall()
+    assert generate.generate_blocks is not tapenv.generators.generate_blocks
+    assert sorted(got) == sorted(want) and len(want) == 12
+    for k in want:
+        assert got[k] == want[k], k
