@@ -1100,7 +1100,7 @@ __global__ void window_reset_kernel(int B, int T, unsigned *wstate) {
 #ifndef TAPENV_WINDOW_MIN_BLOCKS
 #define TAPENV_WINDOW_MIN_BLOCKS (32 / TAPENV_WARPS_PER_CTA)
 #endif
-template <int STRAT, bool FAST>                      // STRAT < 0: window only
+template <int STRAT, bool FAST, int NWc = 0, int RWc = 0>   // STRAT < 0: window only; NWc/RWc > 0: compile-time window shape
 __global__ void __launch_bounds__(32 * kWarpsPerCta, TAPENV_WINDOW_MIN_BLOCKS)
 window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, const unsigned long long *__restrict__ pred,
               const int *__restrict__ blocks, const int64_t *__restrict__ ptr, float *__restrict__ dec_static,
@@ -1163,8 +1163,8 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
         if (place)
             container_add_block<ES>(c, st, b, lane, e, bx, by, bz, dec_dyn, ems_keys_none, 0);
     }
-    window_emit<FAST>(w, sh, lut, b, lane, early, ws, pe, blk, static_out, dynamic_out, cur_mask, mask_out, nodes_out,
-                      remaining_out);
+    window_emit<FAST, NWc, RWc>(w, sh, lut, b, lane, early, ws, pe, blk, static_out, dynamic_out, cur_mask, mask_out, nodes_out,
+                                remaining_out);
 }
 
 // fast path needs 128-bit rows and 16-byte aligned tensors
@@ -1696,12 +1696,13 @@ int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_wind
     const DevCfg c = d;
     const StatePtrs st = stateptrs_of(cfg, state);
     const bool fast = win_fast_ok(w, dynamic_out, cur_mask_out, mask_out);
+#define TAPENV_ROLL_ARGS TAPENV_WIN_ARGS, ptr, dec_static_out, dec_dynamic_out, static_out, dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out
 #define TAPENV_ROLL(STRAT)                                                                                              \
     do {                                                                                                                \
-        if (fast) launch(window_kernel<STRAT, true>, grid, block, s, TAPENV_WIN_ARGS, ptr, dec_static_out, dec_dynamic_out, \
-                         static_out, dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);      \
-        else launch(window_kernel<STRAT, false>, grid, block, s, TAPENV_WIN_ARGS, ptr, dec_static_out, dec_dynamic_out, \
-                    static_out, dynamic_out, cur_mask_out, mask_out, (int *)nodes_out, (int *)remaining_out);           \
+        if (fast && w.n == 10 && w.R == 6) launch(window_kernel<STRAT, true, 10, 6>, grid, block, s, TAPENV_ROLL_ARGS);   \
+        else if (fast && w.n == 10 && w.R == 2) launch(window_kernel<STRAT, true, 10, 2>, grid, block, s, TAPENV_ROLL_ARGS); \
+        else if (fast) launch(window_kernel<STRAT, true>, grid, block, s, TAPENV_ROLL_ARGS);                            \
+        else launch(window_kernel<STRAT, false>, grid, block, s, TAPENV_ROLL_ARGS);                                     \
     } while (0)
     if (strat == STRAT_LBG2D) TAPENV_ROLL(STRAT_LBG2D);
     else if (strat == STRAT_LBG3D) TAPENV_ROLL(STRAT_LBG3D);

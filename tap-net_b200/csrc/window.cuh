@@ -204,7 +204,9 @@ __device__ __forceinline__ WinEarly window_refill(const WinCfg &w, WinShared &sh
 }
 
 // Phase B: decompose + convert_to_input for environment b.  Emits the tensors and stores the new state.
-template <bool FAST>
+// NWc / RWc > 0: window size and rotation count known at compile time (the emission loop unrolls into straight-line code
+// with immediate offsets; r01 spent 350 warp-instructions per instance in it).  0 = runtime shape from WinCfg.
+template <bool FAST, int NWc = 0, int RWc = 0>
 __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, const uint4 *lut, int b, int lane, WinEarly e,
                                             unsigned *ws, const unsigned long long *__restrict__ pe,
                                             const int *__restrict__ blk, float *__restrict__ static_out,
@@ -242,16 +244,28 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
                 unsigned phi = __shfl_sync(TAPENV_FULL_MASK, (unsigned)(word >> 32), src);
                 if (!act) { plo = 0u; phi = 0u; }
                 const bool loop = g >= 1 && ((plo & alo) | (phi & ahi)) != 0u;      // :1690-1705
+                // lane (q, jj) now also OWNS row jj of sub-matrix g: entry (row jj, column c) = "P[jj] is a predecessor of
+                // P[c]" = bit P[jj] of the word lane (q, c) holds.  (r01 built every row with one ballot per row and pass:
+                // 426 of the kernel's 2 560 warp-instructions per instance; this gather form needs 2 shuffles per column.)
                 unsigned keep = 0u;
+                const unsigned ubit = (unsigned)v & 31u;
+                const bool uhi = v >= 32;
+                const int sbase = q * len;
 #pragma unroll 1
-                for (int i = 0; i < len; ++i) {
-                    const int u = sh.perm[i];                   // warp-uniform
-                    const unsigned bit = (u < 32 ? (plo >> u) : (phi >> (u - 32))) & 1u;
-                    const unsigned rowbits = __ballot_sync(TAPENV_FULL_MASK, bit != 0u || (loop && jj == i));
-                    if (lane == i) keep = rowbits;
+                for (int cc = 0; cc < len; ++cc) {
+                    const unsigned wlo = __shfl_sync(TAPENV_FULL_MASK, plo, sbase + cc);
+                    const unsigned whi = __shfl_sync(TAPENV_FULL_MASK, phi, sbase + cc);
+                    keep |= (((uhi ? whi : wlo) >> ubit) & 1u) << cc;
                 }
-                if (pass == 0) { myrow[0] = keep & fld; myrow[1] = (keep >> len) & fld; myrow[2] = (keep >> (2 * len)) & fld; }
-                else { myrow[3] = keep & fld; myrow[4] = (keep >> len) & fld; }
+                if (loop) keep |= 1u << jj;                     // diagonal self-loop of the rotation graphs
+                if (!act) keep = 0u;
+                // rows of graph slot q live in lanes q*len .. q*len+len-1: hand them to the row lanes 0 .. len-1
+                const unsigned k1 = __shfl_sync(TAPENV_FULL_MASK, keep, (lane + len) & 31);
+                const unsigned k2 = __shfl_sync(TAPENV_FULL_MASK, keep, (lane + 2 * len) & 31);
+                if (lane < len) {
+                    if (pass == 0) { myrow[0] = keep & fld; myrow[1] = k1 & fld; myrow[2] = k2 & fld; }
+                    else { myrow[3] = keep & fld; myrow[4] = k1 & fld; }
+                }
             }
         } else {
             unsigned lo[5] = {0u, 0u, 0u, 0u, 0u}, hi[5] = {0u, 0u, 0u, 0u, 0u};
@@ -340,7 +354,24 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
             if (mask_out) mask_out[(size_t)b * S + j] = 1.f;
         }
     }
-    if (FAST) {
+    if (FAST && NWc > 0) {
+        // compile-time shape: lane = (row-in-pass, column group), every pass at an immediate offset
+        constexpr int SVc = NWc > 0 ? NWc * RWc / 4 : 1, RPc = 32 / SVc, rows3c = 3 * NWc, ITER = (rows3c + RPc - 1) / RPc;
+        const int rsub = lane / SVc, cv = lane - rsub * SVc;
+        const bool on = rsub < RPc;
+        const bool hi_half = 4 * cv >= 32;
+        const int sh4 = (4 * cv) & 31;
+        uint4 *dst = reinterpret_cast<uint4 *>(dyo) + lane;
+        const uint2 *rws = reinterpret_cast<const uint2 *>(sh.rows) + rsub;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            if (on && it * RPc + rsub < rows3c) {
+                const uint2 rw = rws[it * RPc];
+                const unsigned nib = ((hi_half ? rw.y : rw.x) >> sh4) & 0xfu;
+                stg_stream4(dst + it * RPc * SVc, lut[nib]);
+            }
+        }
+    } else if (FAST) {
         // lane = (row-in-pass, column group): one 64-bit row word from shared memory, one nibble, one 128-bit store
         const int rsub = (int)(((unsigned)lane * w.inv_SV) >> 16), cv = lane - rsub * w.SV;
         const bool on = rsub < w.RP;

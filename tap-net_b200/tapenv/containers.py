@@ -512,6 +512,9 @@ class Container(object):
         if cache is None or cache[0] != bt._version:
             cache = (bt._version, bt.calc_ratio().cpu().numpy())
             bt.__dict__["_ratio_cache"] = cache
+            # once per batch state: conditions under which the reference's NumPy raises IndexError (a stack above the
+            # container height, more blocks than blocks_num) must not pass silently through an unmodified model.py
+            bt.check_flags()
         return float(cache[1][self._row])
 
     def calc_CPS(self):

@@ -8,6 +8,18 @@ from . import _capi
 from .config import tensor_config
 
 
+# The reference's gather / scatter raise IndexError for a pointer outside [0, S) (pack.py:347, :318-321); the kernels cannot
+# raise, and silently clamping would corrupt the precedence state.  With CHECK_POINTERS (default) update_dynamic / update_mask
+# test the range first -- one tiny reduction and a host sync, negligible beside the syncs an unmodified model.py performs per
+# step.  The fused paths (BatchedContainers.step, DecodeLoop) never sync: they set sticky flag 4 instead (check_flags()).
+CHECK_POINTERS = True
+
+
+def _check_ptr(ptr, S, who):
+    if CHECK_POINTERS and ptr.numel() and bool(((ptr < 0) | (ptr >= S)).any()):
+        raise IndexError("tapenv.%s: chosen_idx outside [0, %d)" % (who, S))
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -32,6 +44,7 @@ def update_dynamic(dynamic, static, chosen_idx, input_type, allow_rot):
     ptr = _dev(chosen_idx, "chosen_idx", torch.int64)
     B, rows, S = dynamic.shape
     cfg = tensor_config(B, static.shape[1], rows, S, input_type, allow_rot)
+    _check_ptr(ptr, S, "update_dynamic")
     out = torch.empty_like(dynamic)
     with torch.cuda.device(dynamic.device):
         _capi.check(_capi.lib.tapenv_update_dynamic(C.byref(cfg), _p(dynamic), _p(static), _p(ptr), _p(out), _stream()),
@@ -48,6 +61,7 @@ def update_mask(mask, dynamic, static, chosen_idx, input_type, allow_rot):
     ptr = _dev(chosen_idx, "chosen_idx", torch.int64)
     B, rows, S = dynamic.shape
     cfg = tensor_config(B, static.shape[1], rows, S, input_type, allow_rot)
+    _check_ptr(ptr, S, "update_mask")
     new_mask = torch.empty_like(mask)
     chosen = torch.empty_like(mask)
     with torch.cuda.device(dynamic.device):

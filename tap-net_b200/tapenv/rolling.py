@@ -18,6 +18,34 @@ from .containers import BatchedContainers
 from .ops import _dev, _p, _stream
 
 
+# node_order=REFERENCE reproduces an accident of the reference's dependencies, not a property of the algorithm: networkx's
+# subgraph view iterates a Python set when 2*window < total (coreviews.FilterAtlas.__iter__), i.e. CPython's open-addressing
+# layout (Objects/setobject.c: 8 -> 32 -> 128 slot tables, LINEAR_PROBES 9, PERTURB_SHIFT 5).  Derived from and pinned
+# against these versions; a different interpreter / networkx may enumerate differently (then use WINDOW_ORDER_SORTED, or
+# re-derive window.cuh:pyset_order_warp).
+REFERENCE_ORDER_DERIVED_FROM = {"cpython": (3, 12), "networkx": "3.6"}
+
+
+def reference_order_matches_this_interpreter():
+    """Does THIS interpreter's set() iterate the way the kernel's restatement assumes?  Two closed-form regimes are probed:
+    6 keys without a collision modulo 32 sit in slot key & 31 of the 32-slot table; 20 keys have grown the table to 128 slots
+    and iterate in ascending order."""
+    keys = [2, 5, 7, 11, 20, 44]
+    big = list(range(0, 60, 3))
+    return list(set(keys)) == sorted(keys, key=lambda k: k & 31) and list(set(big)) == big
+
+
+def _warn_if_order_unpinned(node_order):
+    import sys
+    import warnings
+    if int(node_order) != _capi.WINDOW_ORDER_REFERENCE:
+        return
+    if sys.version_info[:2] != REFERENCE_ORDER_DERIVED_FROM["cpython"] or not reference_order_matches_this_interpreter():
+        warnings.warn("tapenv: node_order=REFERENCE reproduces CPython %d.%d / networkx %s set iteration order; this interpreter "
+                      "differs, so a live reference may permute `dynamic` differently (use WINDOW_ORDER_SORTED)"
+                      % (REFERENCE_ORDER_DERIVED_FROM["cpython"] + (REFERENCE_ORDER_DERIVED_FROM["networkx"],)))
+
+
 def rotation_structured(blocks, total_blocks, dim):
     """True iff blocks[..., r*T+i, :] == blocks[..., i, perm_r] for every rotation r of itertools.permutations(range(dim))
     -- the layout generate.generate_blocks writes (numpy array [B,R*T,dim] or [R*T,dim])."""
@@ -50,6 +78,7 @@ class BatchedInitialContainers(object):
             raise RuntimeError("tapenv: a CUDA device is required (no CPU fallback exists)")
         if input_type != "bot":
             raise _capi.TapEnvError(_capi.EUNSUPPORTED, "InitialContainer.convert_to_input only works for 'bot' inputs (generate.py:1790-1806)")
+        _warn_if_order_unpinned(node_order)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         graphs = np.asarray(graphs) if not isinstance(graphs, torch.Tensor) else graphs
         if not isinstance(graphs, torch.Tensor):
