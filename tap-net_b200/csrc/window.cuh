@@ -251,11 +251,21 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
                 const unsigned ubit = (unsigned)v & 31u;
                 const bool uhi = v >= 32;
                 const int sbase = q * len;
+                if (NWc > 0) {                                  // compile-time window: straight-line code, columns >= len masked below
+#pragma unroll
+                    for (int cc = 0; cc < (NWc > 0 ? NWc : 1); ++cc) {
+                        const unsigned wlo = __shfl_sync(TAPENV_FULL_MASK, plo, (sbase + cc) & 31);
+                        const unsigned whi = __shfl_sync(TAPENV_FULL_MASK, phi, (sbase + cc) & 31);
+                        keep |= (((uhi ? whi : wlo) >> ubit) & 1u) << cc;
+                    }
+                    keep &= fld;
+                } else {
 #pragma unroll 1
-                for (int cc = 0; cc < len; ++cc) {
-                    const unsigned wlo = __shfl_sync(TAPENV_FULL_MASK, plo, sbase + cc);
-                    const unsigned whi = __shfl_sync(TAPENV_FULL_MASK, phi, sbase + cc);
-                    keep |= (((uhi ? whi : wlo) >> ubit) & 1u) << cc;
+                    for (int cc = 0; cc < len; ++cc) {
+                        const unsigned wlo = __shfl_sync(TAPENV_FULL_MASK, plo, sbase + cc);
+                        const unsigned whi = __shfl_sync(TAPENV_FULL_MASK, phi, sbase + cc);
+                        keep |= (((uhi ? whi : wlo) >> ubit) & 1u) << cc;
+                    }
                 }
                 if (loop) keep |= 1u << jj;                     // diagonal self-loop of the rotation graphs
                 if (!act) keep = 0u;
@@ -321,27 +331,34 @@ __device__ __forceinline__ void window_emit(const WinCfg &w, WinShared &sh, cons
     if (nodes_out && lane < n) nodes_out[(size_t)b * n + lane] = lane < len ? sorted : -1;
     if (remaining_out && lane == 0) remaining_out[b] = __popcll(after);
     // ---- static [1+dim,S]: row 0 = window-local index, rows 1.. = blocks[node + r*T] (:1779-1788) ----
-    float *so = static_out + (size_t)b * (1 + w.dim) * S;
+    constexpr bool FX = NWc > 0;
+    const int dimv = FX ? (RWc == 6 ? 3 : 2) : w.dim;   // compile-time with a fixed shape (R = dim!)
+    const int Sv = FX ? NWc * RWc : S, nv = FX ? NWc : n;
+    float *so = static_out + (size_t)b * (1 + dimv) * Sv;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int j = lane + 32 * half;
-        const bool on = j < S;
-        const int r = on ? (int)(((unsigned)j * w.inv_n) >> 16) : 0, i = on ? j - r * n : 0;
+        if (FX && 32 * half >= NWc * RWc) break;
+        const bool on = j < Sv;
+        const int r = on ? (FX ? j / (FX ? NWc : 1) : (int)(((unsigned)j * w.inv_n) >> 16)) : 0, i = on ? j - r * nv : 0;
         if (w.rotblocks) {                                  // blocks[r*T + node][d] == blocks[node][perm_r[d]]
             const int a0 = __shfl_sync(TAPENV_FULL_MASK, e.bd0, i), a1 = __shfl_sync(TAPENV_FULL_MASK, e.bd1, i);
-            const int a2 = __shfl_sync(TAPENV_FULL_MASK, e.bd2, i);
+            const int a2 = dimv == 3 ? __shfl_sync(TAPENV_FULL_MASK, e.bd2, i) : 0;
             if (on) {
                 so[j] = (float)i;
                 const unsigned pc = (unsigned)(w.permcodes >> (6 * r));
-                for (int d = 0; d < w.dim; ++d) {
-                    const unsigned c = (pc >> (2 * d)) & 3u;
-                    so[(1 + d) * S + j] = i < len ? (float)(c == 0u ? a0 : (c == 1u ? a1 : a2)) : 0.f;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if (d < dimv) {
+                        const unsigned c = (pc >> (2 * d)) & 3u;
+                        so[(1 + d) * Sv + j] = i < len ? (float)(c == 0u ? a0 : (c == 1u ? a1 : a2)) : 0.f;
+                    }
                 }
             }
         } else if (on) {
             so[j] = (float)i;
             const int node = i < len ? (int)sh.sorted[i] : -1;
-            for (int d = 0; d < w.dim; ++d) so[(1 + d) * S + j] = node >= 0 ? (float)blk[(node + r * T) * w.dim + d] : 0.f;
+            for (int d = 0; d < dimv; ++d) so[(1 + d) * Sv + j] = node >= 0 ? (float)blk[(node + r * T) * dimv + d] : 0.f;
         }
     }
     // ---- dynamic [3n,S] and the initial masks (rolling.py:325-335) ----
