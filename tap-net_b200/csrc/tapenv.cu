@@ -19,6 +19,14 @@
 #include "place_macs3d.cuh"
 #include "window.cuh"
 
+// Speculative load of the edge-length rows of `static` in the warp-per-environment step: removes the DRAM round trip of the
+// gather behind `ptr` at the price of (dim*S - dim) extra floats per environment.  Build-time A/B switch.  Measured
+// (profiles/r02z_spec_gather_ab.txt): within +-3 % of the dependent gather at every batch size and workload, no consistent
+// sign -- the round trip hides behind the precedence tensor that is in flight anyway -- so it is OFF (no extra bytes).
+#ifndef TAPENV_SPEC_GATHER
+#define TAPENV_SPEC_GATHER 0
+#endif
+
 namespace tapenv {
 
 enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2, STRAT_LB = 3, STRAT_MACS3D = 4 };
@@ -606,11 +614,13 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     const float id1 = (S > 32 && lane + 32 < S) ? srow[lane + 32] : 0.f;
     // the edge-length rows too (DIM * S floats, L2-resident across the steps of an episode): the gather of the chosen block
     // (model.py:404-406) then needs no second DRAM round trip behind `ptr`
-    float ev0[3], ev1[3];
+    float ev0[3] = {0.f, 0.f, 0.f}, ev1[3] = {0.f, 0.f, 0.f};
+    if (TAPENV_SPEC_GATHER) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        ev0[r] = (r < DIM && lane < S) ? srow[(1 + r) * S + lane] : 0.f;
-        ev1[r] = (r < DIM && S > 32 && lane + 32 < S) ? srow[(1 + r) * S + lane + 32] : 0.f;
+        for (int r = 0; r < 3; ++r) {
+            ev0[r] = (r < DIM && lane < S) ? srow[(1 + r) * S + lane] : 0.f;
+            ev1[r] = (r < DIM && S > 32 && lane + 32 < S) ? srow[(1 + r) * S + lane + 32] : 0.f;
+        }
     }
     const float m0 = lane < S ? min_[lane] : 0.f;
     const float m1 = (S > 32 && lane + 32 < S) ? min_[lane + 32] : 0.f;
@@ -623,10 +633,18 @@ step_kernel(DevCfg c, StatePtrs st, const int64_t *__restrict__ ptr, const float
     const int p = badp ? 0 : (int)p64;
     const bool hi = S > 32 && p >= 32;
     const int real = (int)__shfl_sync(TAPENV_FULL_MASK, hi ? id1 : id0, p & 31);
-    const float e0 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[0] : ev0[0], p & 31);
-    const float e1 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[1] : ev0[1], p & 31);
-    const float e2 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[2] : ev0[2], p & 31);
-    const float dimv = lane == 0 ? e0 : (lane == 1 ? e1 : e2);
+    float e0, e1, e2, dimv;
+    if (TAPENV_SPEC_GATHER) {
+        e0 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[0] : ev0[0], p & 31);
+        e1 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[1] : ev0[1], p & 31);
+        e2 = __shfl_sync(TAPENV_FULL_MASK, hi ? ev1[2] : ev0[2], p & 31);
+        dimv = lane == 0 ? e0 : (lane == 1 ? e1 : e2);
+    } else {                                         // dependent gather behind `ptr` (one more DRAM round trip, no extra bytes)
+        dimv = lane < DIM ? srow[(1 + lane) * S + p] : 0.f;
+        e0 = __shfl_sync(TAPENV_FULL_MASK, dimv, 0);
+        e1 = __shfl_sync(TAPENV_FULL_MASK, dimv, 1);
+        e2 = __shfl_sync(TAPENV_FULL_MASK, dimv, 2);
+    }
     if (dec_static && lane < DIM) dec_static[(size_t)b * (SH::static_rows(c) - 1) + lane] = dimv;
 
     // (3) environment transition on the register-resident state.  It only needs the pointer, the block's edge
