@@ -50,8 +50,6 @@ class PACKDataset(Dataset):
             seed = np.random.randint(123456)
         np.random.seed(seed)
         torch.manual_seed(seed)
-        if mix_data_file is not None:
-            raise NotImplementedError("mixed datasets (mix_data_file) are outside the accelerated path")
         n, N = int(blocks_num), int(num_samples)
         move = _load(data_file + "dep_move.txt")
         small = _load(data_file + "dep_small.txt")
@@ -59,6 +57,17 @@ class PACKDataset(Dataset):
         blocks = _load(data_file + "blocks.txt")
         positions = _load(data_file + "pos.txt")
         container = _load(data_file + "container.txt")
+        if mix_data_file is not None:
+            # pack.py:67-97: the first half of the samples from data_file, the second from mix_data_file.  Per-sample files are
+            # cut at num_samples/2 rows, per-rotation files at HALF THE ROWS OF data_file's blocks.txt (the reference's own rule)
+            num_mid, rot_mid = int(N / 2), int(len(blocks) / 2)
+            mix = lambda name: _load(mix_data_file + name)
+            move = np.vstack((move[:num_mid], mix("dep_move.txt")[:num_mid]))
+            positions = np.vstack((positions[:num_mid], mix("pos.txt")[:num_mid]))
+            container = np.vstack((container[:num_mid], mix("container.txt")[:num_mid]))
+            small = np.vstack((small[:rot_mid], mix("dep_small.txt")[:rot_mid]))
+            large = np.vstack((large[:rot_mid], mix("dep_large.txt")[:rot_mid]))
+            blocks = np.vstack((blocks[:rot_mid], mix("blocks.txt")[:rot_mid]))
 
         dim = positions.reshape(N, -1, n).shape[1]                      # pack.py:108
         R_file = math.factorial(dim)

@@ -105,6 +105,21 @@ def test_packdataset_matches_reference_loader(ref, dim):
             assert ours.decoder_static.shape == theirs.decoder_static.shape
             assert ours.decoder_dynamic.shape == theirs.decoder_dynamic.shape
             assert len(ours) == len(theirs) and all(np.array_equal(a.detach().numpy(), b.detach().numpy()) for a, b in zip(ours[3], theirs[3]))
+        # mixed datasets (pack.py:67-97): first half from one directory, second half from another
+        other_dir, _ = pack.create_dataset(10, 24, 6, dim, 7, 50, 1, [1, 5], seed=5)
+        assert other_dir == train_dir                       # same directory name: generate the second set elsewhere
+        os.makedirs("second", exist_ok=True)
+        os.chdir("second")
+        mix_dir, _ = pack.create_dataset(10, 24, 4, dim, 7, 50, 1, [1, 5], seed=123)
+        mix_dir = os.path.join(os.getcwd(), mix_dir) + ("" if mix_dir.endswith("/") else "/")
+        os.chdir(d)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            theirs = pack.PACKDataset(train_dir, 10, 24, 7, "bot", "diff", True, 5, mix_data_file=mix_dir)
+        ours = PACKDataset(train_dir, 10, 24, 7, "bot", "diff", True, 5, mix_data_file=mix_dir)
+        assert np.array_equal(ours.static.numpy(), theirs.static.numpy())
+        assert np.array_equal(ours.dynamic.numpy(), theirs.dynamic.numpy())
+        assert not np.array_equal(ours.static.numpy()[:12], ours.static.numpy()[12:])
     finally:
         os.chdir(cwd)
         shutil.rmtree(d, ignore_errors=True)
