@@ -1403,6 +1403,8 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
     } while (0)
     // heavy placements (3D, MACS): the 72-register build when it turns a 1.x-wave launch into a single wave
     const int kdef = strat == STRAT_LBG3D ? 5 : 4;          // resident CTAs per SM of the default build (88 / 106 registers)
+    // (r02: the capped build for EVERY multi-wave launch was measured too -- no gain at 8 192 .. 65 536 environments,
+    // profiles/r02z_lowreg_ab.txt -- so it stays limited to the range where it removes the second wave)
     const bool lowreg = (int)grid.x > sms * kdef && (int)grid.x <= sms * 7;
 #define TAPENV_STEP_SHAPE_HEAVY(STRAT, N, R)                                                               \
     do {                                                                                                   \
