@@ -93,3 +93,44 @@ def test_actor_step_adapter_reproduces_drl_forward(dim, ck, incremental):
     assert float((got_logp - want_logp).abs().max()) <= tol
     r = torch.tensor([c.calc_ratio() for c in conts], dtype=torch.float32)
     assert torch.equal(-r, want_r)
+
+
+@pytest.mark.parametrize("dim,W", [(2, 7), (2, 0), (3, 5)])
+def test_speculative_generate_blocks_host_logic(dim, W, monkeypatch):
+    """tapenv.generators.generate_blocks (the rejection loop of generate.py:896-910 evaluated K draws at a time): the HOST
+    logic -- speculation, rewinding np.random to exactly where the sequential loop stops, the rotation / dependency tail --
+    with the batched GPU evaluation replaced by the reference's own calc_positions_lb_greedy, candidate by candidate.  Same
+    outputs and same stream position as generate.generate_blocks under the same seed (the GPU evaluation itself is covered by
+    tests/test_gpu_model_in_loop.py::test_create_dataset_identical_with_batched_generator)."""
+    import torch
+    from tapenv import generators
+    mods = refshim.load(("tools", "generate"))
+    tools, generate = mods["tools"], mods["generate"]
+    calls = {"batches": 0, "cands": 0}
+
+    def fake_calc(blocks, container_size, reward_type):
+        blocks = np.asarray(blocks)
+        if blocks.ndim == 2:
+            return tools.calc_positions_lb_greedy(blocks.copy(), container_size, reward_type)
+        calls["batches"] += 1
+        calls["cands"] += len(blocks)
+        res = [tools.calc_positions_lb_greedy(b.copy(), container_size, reward_type) for b in blocks]
+        pos = torch.from_numpy(np.stack([r[0] for r in res]))
+        stable = torch.tensor([[bool(v) for v in r[2]] for r in res])
+        return pos, None, stable, None, None
+
+    monkeypatch.setattr(generators, "calc_positions_lb_greedy", fake_calc)
+    size = [W, 50] if dim == 2 else [W, W, 50]
+    for seed in (3, 4, 5):
+        np.random.seed(seed)
+        want = [generate.generate_blocks(10, list(size), 1, [1, 5]) for _ in range(3)]
+        want_next = np.random.random_sample(4)
+        np.random.seed(seed)
+        got = [generators.generate_blocks(10, list(size), 1, [1, 5], speculate=4) for _ in range(3)]
+        got_next = np.random.random_sample(4)
+        for a, b in zip(got, want):
+            for x, y in zip(a, b):
+                assert np.array_equal(np.asarray(x), np.asarray(y))
+        assert np.array_equal(got_next, want_next)           # the global stream is where the sequential loop leaves it
+    if W > 0:                                                # (with a random width the first, non-speculative draw usually fits)
+        assert calls["batches"] > 0 and calls["cands"] >= calls["batches"]
