@@ -715,6 +715,7 @@ def measure_steps(ctx, args, name, B, full):
         for k in range(ks):
             episode(k)
         e1.record()
+        sampler.sample_until(e1)                              # more clock / throttle samples under the same load
         ctx.barrier()
         sustained = {"episodes": ks, "value": world * B * n * ks / (ctx.allmax(e0.elapsed_time(e1)) * 1e-3), "unit": UNIT}
     out = {"name": name, "B": B, "n": n, "value": value, "ms_per_step": span_ms_max / args.steps, "launches": launches,
