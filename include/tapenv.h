@@ -22,7 +22,8 @@
  *    launched when an error is returned.
  *  - tensors are dense row-major with the reference's layouts:
  *      static   f32 [B, static_rows, S]   row 0 = block id, rows 1..dim = edge lengths   (pack.py:144-147,186)
- *      dynamic  f32 [B, dyn_rows, S]      3 bands of n rows: move | rot-small | rot-large (pack.py:195)
+ *      dynamic  f32 [B, dyn_rows, S]      3 bands of n rows: move | rot-small | rot-large (pack.py:195); 'simple'/'rot': the
+ *                                         move band only; legacy 'rot-old': move band + ONE rotate-state row (pack.py:218-223)
  *      mask     f32 [B, S]                0/1                                               (model.py:297)
  *      ptr      i64 [B]                   chosen candidate column                           (model.py:365-371)
  *    S = n * rotate_types candidates, rotation-major (column j = r*n + i).
@@ -49,7 +50,9 @@ extern "C" {
 #define TAPENV_ELIMIT (-3)    /* shape outside the compiled limits (see tapenv_limits) */
 #define TAPENV_ESHAPE (-4)    /* S != n*R, dyn_rows too small, ... */
 #define TAPENV_ECUDA (-5)     /* the launch itself failed (cudaGetLastError) */
-#define TAPENV_EUNSUPPORTED (-6) /* valid in the reference but not built here (the legacy 'rot-old' input layout) */
+#define TAPENV_EUNSUPPORTED (-6) /* not served by this entry point: the fused step / episode / rolling entries with the legacy
+                                    'rot-old' layout (the reference's own decode loop raises there: model.py:391-392 hands
+                                    Container.add_new_block 1+dim values, tools.py:2060); the tensor operators serve it */
 
 /* packing_strategy (tools.py:3607, :3679-3701) */
 #define TAPENV_LB_GREEDY 0
@@ -88,7 +91,7 @@ typedef struct tapenv_config {
     int32_t reward_flags;   /* TAPENV_RF_* bits                                                    */
     int32_t ratio_mode;     /* TAPENV_RATIO_*                                                      */
     int32_t static_rows;    /* rows of `static`: 1+dim ('mul-with': 2+dim)                         */
-    int32_t dyn_rows;       /* rows of `dynamic`: 3n for 'bot'-like inputs, n for 'simple'/'rot'   */
+    int32_t dyn_rows;       /* rows of `dynamic`: 3n for 'bot'-like inputs, n for 'simple'/'rot', n+1 for 'rot-old' */
     int32_t update_time;    /* bands zeroed by update_dynamic: 3 or 1 (pack.py:349)                */
     int32_t capacity;       /* blocks one container can take: rows of positions/blocks/stable per environment.
                                tapenv_config_init sets it to blocks_num; rolling inference keeps ONE container for

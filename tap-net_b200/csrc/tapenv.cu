@@ -117,7 +117,7 @@ static int check_cfg(const tapenv_config *c) {
     if (c->heightmap_type < 0 || c->heightmap_type > 2) return TAPENV_EENUM;
     if (c->ratio_mode < 0 || c->ratio_mode > TAPENV_RATIO_CP_HALF) return TAPENV_EENUM;
     if (c->static_rows < 1 + c->dim) return TAPENV_ESHAPE;
-    if (c->dyn_rows != c->blocks_num && c->dyn_rows != 3 * c->blocks_num) return TAPENV_ESHAPE;
+    if (c->dyn_rows != c->blocks_num && c->dyn_rows != 3 * c->blocks_num && c->dyn_rows != c->blocks_num + 1) return TAPENV_ESHAPE;
     if (c->update_time != 1 && c->update_time != 3) return TAPENV_ESHAPE;
     if (c->update_time * c->blocks_num > c->dyn_rows) return TAPENV_ESHAPE;
     if (c->capacity < 1) return TAPENV_ESHAPE;
@@ -129,6 +129,12 @@ static int check_cfg(const tapenv_config *c) {
     if (c->height > (1 << 18)) return TAPENV_ELIMIT;
     return TAPENV_OK;
 }
+
+// The legacy 'rot-old' layout (pack.py:218-223): dynamic = n movement rows + ONE rotate-state row.  pack.update_dynamic /
+// pack.update_mask / the initial mask are defined for it (and served: the generic row sweep), but the reference's own decode
+// loop is not -- model.py:391-392 gathers the block from ALL 1+dim rows of `static`, so Container.add_new_block receives
+// (index, w, h) and `block_x, block_z = block` (tools.py:2060) raises.  The fused entry points say EUNSUPPORTED.
+static bool rot_old_layout(const tapenv_config *c) { return c->dyn_rows == c->blocks_num + 1; }
 
 static int strategy_kernel(const tapenv_config *c) {
     if (c->strategy == TAPENV_LB_GREEDY) return c->dim == 2 ? STRAT_LBG2D : STRAT_LBG3D;
@@ -1188,7 +1194,7 @@ window_kernel(WinCfg w, DevCfg c, StatePtrs st, unsigned *__restrict__ wstate, c
 // fast path needs 128-bit rows and 16-byte aligned tensors
 static bool fast_ok(const DevCfg &d, const void *a, const void *b) {
     const uintptr_t al = (uintptr_t)a | (uintptr_t)b;
-    return d.S % 4 == 0 && d.S >= 4 && al % 16 == 0;
+    return d.S % 4 == 0 && d.S >= 4 && al % 16 == 0 && d.dyn_rows % d.n == 0;   // whole bands only ('rot-old': n+1 rows)
 }
 
 }  // namespace tapenv
@@ -1287,7 +1293,7 @@ int tapenv_config_init(tapenv_config *cfg, int32_t batch, int32_t blocks_num, in
     } else if (!strcmp(input_type, "mul") || !strcmp(input_type, "mul-with")) {
         cfg->static_rows = 2 + dim; cfg->dyn_rows = 3 * n; cfg->update_time = 3;   // + target container id row (pack.py:212-216)
     } else if (!strcmp(input_type, "rot-old")) {
-        return TAPENV_EUNSUPPORTED;   // legacy layout
+        cfg->static_rows = 1 + dim; cfg->dyn_rows = n + 1; cfg->update_time = 1;   // movement rows + one rotate-state row (pack.py:218-223)
     } else return TAPENV_EENUM;
     const int rc = check_cfg(cfg);
     if (rc != TAPENV_OK) return rc;
@@ -1384,7 +1390,7 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
                      float *mask_out, float *dec_static_out, float *dec_dynamic_out, float *reward_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (strat < 0 || rot_old_layout(cfg)) return TAPENV_EUNSUPPORTED;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !ptr || !static_ || !dynamic_in || !mask_in || !dynamic_out || !cur_mask_out || !mask_out)
         return TAPENV_EINVAL;
@@ -1517,7 +1523,7 @@ int tapenv_episode(const tapenv_config *cfg, void *state, const float *static_, 
                    float *dec_dynamic_out, void *stream) {
     TAPENV_PROLOGUE(cfg)
     const int strat = strategy_kernel(cfg);
-    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (strat < 0 || rot_old_layout(cfg)) return TAPENV_EUNSUPPORTED;
     if (steps < 0 || steps > 64 || steps > cfg->capacity) return TAPENV_ELIMIT;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !static_ || !dynamic || (steps > 0 && !ptr_seq)) return TAPENV_EINVAL;
@@ -1709,7 +1715,7 @@ int tapenv_rolling_step(const tapenv_config *cfg, void *state, const tapenv_wind
     if (cfg->batch != wcfg->batch || cfg->dim != wcfg->dim || cfg->blocks_num != wcfg->window ||
         cfg->rotate_types != wcfg->rotate_types || cfg->static_rows != 1 + cfg->dim) return TAPENV_ESHAPE;
     const int strat = strategy_kernel(cfg);
-    if (strat < 0) return TAPENV_EUNSUPPORTED;
+    if (strat < 0 || rot_old_layout(cfg)) return TAPENV_EUNSUPPORTED;
     if (d.B == 0) return TAPENV_OK;
     if (!state || !wstate || !pred || !blocks || !ptr || !static_out || !dynamic_out) return TAPENV_EINVAL;
     const WinCfg w = wincfg_of(wcfg);

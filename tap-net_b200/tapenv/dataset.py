@@ -100,6 +100,8 @@ class PACKDataset(Dataset):
         elif input_type in ("mul", "mul-with"):
             static = np.concatenate([ids, edges, cont], 1)
             dynamic = np.concatenate([move_t, small_t, large_t], 1)
+        elif input_type == "rot-old":                                   # pack.py:218-223: n movement rows + one zero rotate-state row
+            static, dynamic = np.concatenate([ids, edges], 1), np.concatenate([move_t, np.zeros_like(ids)], 1)
         else:
             raise ValueError("unknown input_type %r" % (input_type,))   # the reference prints 'Dataset OHHHHH' and dies later
         self.static = torch.from_numpy(np.ascontiguousarray(static, dtype=np.float32))

@@ -53,6 +53,8 @@ def test_config_from_reference_option_strings():
     assert lay.lists - lay.voxels >= 8 * 25 * 50 * 2 and lay.pending - lay.lists >= 8 * 50 * 5 * 12
     c = make_config(8, 10, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "simple", False)
     assert (c.rotate_types, c.dyn_rows, c.update_time) == (1, 10, 1)
+    c = make_config(8, 10, [5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "rot-old", True)         # legacy: + one rotate-state row
+    assert (c.static_rows, c.dyn_rows, c.update_time, c.rotate_types) == (3, 11, 1, 2)
     c = make_config(8, 10, [5, 5, 50], "C+P+S-lb-soft", "diff", "LB_GREEDY", "mul-with", True)     # + target-container row
     assert (c.static_rows, c.dyn_rows, c.update_time, c.rotate_types) == (5, 30, 3, 6)
 
@@ -60,7 +62,7 @@ def test_config_from_reference_option_strings():
 @pytest.mark.parametrize("kw,code", [
     (dict(reward_type="bogus"), -2), (dict(heightmap_type="bogus"), -2), (dict(packing_strategy="bogus"), -2),
     (dict(input_type="bogus"), -2), (dict(container_size=[64, 50]), -3), (dict(blocks_num=40), -3),
-    (dict(input_type="rot-old"), -6), (dict(container_size=[5, 5, 300], packing_strategy="MACS"), -3),
+    (dict(container_size=[5, 5, 300], packing_strategy="MACS"), -3),
 ])
 def test_config_errors(kw, code):
     from tapenv import make_config, TapEnvError

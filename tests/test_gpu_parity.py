@@ -810,3 +810,57 @@ def test_two_container_inputs_voxel_strategies(fixture, size, rt, strat, it):
     assert np.array_equal(env.b.positions.cpu().numpy(), want["positions_b"])
     assert np.array_equal(env.calc_ratio().cpu().numpy(), want["scores"])
     env.check_flags()
+
+
+@pytest.mark.parametrize("input_type,allow_rot", [("simple", False), ("simple", True), ("rot", True), ("rot-old", True), ("bot", True),
+                                                  ("bot-rot", True), ("use-static", True), ("use-pnet", True), ("mul", True),
+                                                  ("mul-with", True)])
+def test_tensor_ops_every_input_type(input_type, allow_rot):
+    """tapenv.update_dynamic / update_mask / the initial masks / the packed upload for EVERY input_type string of
+    pack.py:285-309 against the oracle (itself checked against the live pack.* functions for the same layouts in
+    tests/test_oracle_vs_reference.py) -- including the legacy 'rot-old' layout (n movement rows + one rotate-state row), whose
+    FUSED step is refused like the reference's own decode loop (model.py:391-392 -> tools.py:2060 raises)."""
+    torch = _torch()
+    import tapenv
+    from oracle import oracle
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(21)
+    for dim, n in ((2, 10), (3, 5), (2, 7)):                 # S % 4 != 0 at (2, 7): scalar tensor path for every layout
+        R = (2 if dim == 2 else 6) if allow_rot else 1
+        S, B = n * R, 37
+        srows = 2 + dim if input_type in ("mul", "mul-with") else 1 + dim
+        drows = n if input_type in ("simple", "rot") else (n + 1 if input_type == "rot-old" else 3 * n)
+        static = np.zeros((B, srows, S), np.float32)
+        static[:, 0] = np.tile(np.arange(n), R)
+        static[:, 1:1 + dim] = rng.randint(1, 5, size=(B, dim, S))
+        dynamic = (rng.random_sample((B, drows, S)) < 0.08).astype(np.float32)
+        size = [5, 50] if dim == 2 else [5, 5, 50]
+        if input_type in ("mul", "mul-with"):
+            static[:, -1] = rng.randint(0, 2, size=(B, S))
+            env = tapenv.BatchedContainerPairs(size, n, "C+P+S-lb-soft", "diff", batch_size=B, device=dev, input_type=input_type,
+                                               allow_rot=allow_rot).a
+        else:
+            env = tapenv.BatchedContainers(size, n, "C+P+S-lb-soft", "diff", batch_size=B, device=dev, input_type=input_type,
+                                           allow_rot=allow_rot)
+        st, dyn = torch.from_numpy(static).to(dev), torch.from_numpy(dynamic).to(dev)
+        cur0, mask0 = env.reset(dyn)
+        assert np.array_equal(cur0.cpu().numpy(), oracle.initial_mask(dynamic, n, R)) and bool((mask0 == 1).all())
+        # packed upload of the same layout
+        su8, bits = tapenv.pack_inputs(static, dynamic)
+        st2, dyn2, cur2, _ = env.reset_packed(torch.from_numpy(su8).to(dev), torch.from_numpy(bits).to(dev))
+        assert torch.equal(st2, st) and torch.equal(dyn2, dyn) and torch.equal(cur2, cur0)
+        mask = np.ones((B, S), np.float32)
+        mask_t = torch.from_numpy(mask).to(dev)
+        for t in range(n):
+            ptr = rng.randint(0, S, size=B).astype(np.int64)
+            dynamic = oracle.update_dynamic(dynamic, static, ptr, input_type, allow_rot)
+            cur, mask = oracle.update_mask(mask, dynamic, static, ptr, input_type, allow_rot)
+            ptr_t = torch.from_numpy(ptr).to(dev)
+            dyn = tapenv.update_dynamic(dyn, st, ptr_t, input_type, allow_rot)
+            cur_t, mask_t = tapenv.update_mask(mask_t, dyn, st, ptr_t, input_type, allow_rot)
+            assert np.array_equal(dyn.cpu().numpy(), dynamic)
+            assert np.array_equal(cur_t.cpu().numpy(), cur) and np.array_equal(mask_t.cpu().numpy(), mask)
+        if input_type == "rot-old":
+            with pytest.raises(tapenv.TapEnvError) as e:
+                env.step(ptr_t, st, dyn, mask_t)
+            assert e.value.code == tapenv._capi.EUNSUPPORTED

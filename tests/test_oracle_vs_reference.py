@@ -86,6 +86,43 @@ def test_mask_and_dynamic_differential(ref):
             assert np.array_equal(dynamic, dyn_t.numpy()) and np.array_equal(cur, cur_t.numpy()) and np.array_equal(mask, mask_t.numpy())
 
 
+INPUT_LAYOUTS = [("simple", False), ("simple", True), ("rot", True), ("rot-old", True), ("bot", True), ("bot-rot", True),
+                 ("use-static", True), ("mul", True), ("mul-with", True)]
+
+
+def layout_rows(input_type, n, dim):
+    """(static rows, dynamic rows) of every input_type (pack.py:186-223)."""
+    srows = 2 + dim if input_type in ("mul", "mul-with") else 1 + dim
+    drows = n if input_type in ("simple", "rot") else (n + 1 if input_type == "rot-old" else 3 * n)
+    return srows, drows
+
+
+@pytest.mark.parametrize("input_type,allow_rot", INPUT_LAYOUTS)
+def test_tensor_ops_every_input_type(ref, input_type, allow_rot):
+    """pack.update_dynamic / pack.update_mask for EVERY input_type string (pack.py:285-309, :338-365), including the
+    legacy 'rot-old' layout (n movement rows + one rotate-state row, which here carries non-zero entries on purpose)."""
+    import torch
+    pack = ref["pack"]
+    rng = np.random.RandomState(11)
+    for dim, n in ((2, 10), (3, 5)):
+        R = (2 if dim == 2 else 6) if allow_rot else 1
+        S, B = n * R, 16
+        srows, drows = layout_rows(input_type, n, dim)
+        static = np.zeros((B, srows, S), np.float32)
+        static[:, 0] = np.tile(np.arange(n), R)
+        static[:, 1:1 + dim] = rng.randint(1, 5, size=(B, dim, S))
+        dynamic = (rng.random_sample((B, drows, S)) < 0.08).astype(np.float32)
+        mask = np.ones((B, S), np.float32)
+        dyn_t, mask_t, st_t = torch.from_numpy(dynamic), torch.from_numpy(mask), torch.from_numpy(static)
+        for t in range(n):
+            ptr = rng.randint(0, S, size=B).astype(np.int64)
+            dynamic = oracle.update_dynamic(dynamic, static, ptr, input_type, allow_rot)
+            cur, mask = oracle.update_mask(mask, dynamic, static, ptr, input_type, allow_rot)
+            dyn_t = pack.update_dynamic(dyn_t, st_t, torch.from_numpy(ptr), input_type, allow_rot)
+            cur_t, mask_t = pack.update_mask(mask_t, dyn_t, st_t, torch.from_numpy(ptr), input_type, allow_rot)
+            assert np.array_equal(dynamic, dyn_t.numpy()) and np.array_equal(cur, cur_t.numpy()) and np.array_equal(mask, mask_t.numpy())
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_packdataset_matches_reference_loader(ref, dim):
     """tapenv.PACKDataset builds the same four tensors as pack.PACKDataset from the same dataset directory."""
@@ -96,7 +133,8 @@ def test_packdataset_matches_reference_loader(ref, dim):
     os.chdir(d)
     try:
         train_dir, _ = pack.create_dataset(10, 24, 4, dim, 7, 50, 1, [1, 5], seed=99)
-        for input_type, hm in (("bot", "diff"), ("bot", "full"), ("simple", "zero"), ("bot-rot", "diff")):
+        for input_type, hm in (("bot", "diff"), ("bot", "full"), ("simple", "zero"), ("bot-rot", "diff"), ("rot-old", "diff"),
+                               ("mul-with", "diff")):
             allow_rot = input_type != "simple"
             theirs = pack.PACKDataset(train_dir, 10, 24, 7, input_type, hm, True, 5)
             ours = PACKDataset(train_dir, 10, 24, 7, input_type, hm, True, 5)
