@@ -1,9 +1,39 @@
-// host_checks.cpp -- host build of the header-only integer geometry used by the kernels, so the CPU
-// test-suite can check it exhaustively (tests/test_stable3d_cpu.py).  Not part of libtapenv.so and never
-// used to produce results: the product path is CUDA only.
+// host_checks.cpp -- host build of the header-only logic the kernels share, so the CPU test-suite can check it against the
+// oracle without a GPU: the integer geometry of is_stable (tests/test_stable3d_cpu.py) and the MACS 3D placement with ONE
+// emulated lane (tests/test_macs3d_host_cpu.py).  Not part of libtapenv.so and never used to produce results: the product
+// path is CUDA only.
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include "stable3d.cuh"
+#include "place_macs3d.cuh"
 
 extern "C" void tapenv_host_stable3d_masks(int bx, int by, const uint32_t *masks, int count, unsigned char *out) {
     for (int i = 0; i < count; ++i) out[i] = tapenv::stable3d_from_support(bx, by, masks[i]) ? 1 : 0;
+}
+
+// One environment through `steps` blocks [steps][3] with the state laid out as the device keeps it (reset as reset_env_state
+// does).  Outputs after EVERY step: heightmap [steps][W*L], scal [steps][4]; at the end: positions [cap][3], stable [cap],
+// voxels [W*L*H] (int16), lists [H*L*lcap] (int8).  Returns the OR of the anomaly bits.
+extern "C" int tapenv_host_macs3d_episode(int W, int L, int H, int cap, int lcap, int flags, int steps, const int *blocks_in,
+                                          int *heightmaps, int *scals, int *positions, unsigned char *stable, short *voxels,
+                                          signed char *lists) {
+    using namespace tapenv;
+    const int cells = W * L;
+    memset(voxels, 0, sizeof(short) * cells * H);
+    for (int i = 0; i < H * L * lcap; ++i) { const int q = i % lcap; lists[i] = q == 0 ? 2 : (q == 2 ? (signed char)(W - 1) : 0); }
+    int *h = (int *)calloc(cells, sizeof(int)), *blks = (int *)calloc(cap * 3, sizeof(int));
+    memset(positions, 0, sizeof(int) * cap * 3); memset(stable, 0, cap);
+    int scal[4] = {0, 0, 0, 0};
+    M3Scratch *sm = (M3Scratch *)malloc(sizeof(M3Scratch));
+    M3State s;
+    s.vox = voxels; s.lists = lists; s.h = h; s.W = W; s.L = L; s.H = H; s.cells = cells; s.lcap = lcap; s.sm = sm; s.lane = 0; s.nl = 1;
+    int anomaly = 0;
+    for (int t = 0; t < steps; ++t) {
+        anomaly |= macs3d_env_add_block(flags, cap, s, scal, positions, blks, stable, blocks_in[t * 3], blocks_in[t * 3 + 1], blocks_in[t * 3 + 2]);
+        memcpy(heightmaps + (size_t)t * cells, h, sizeof(int) * cells);
+        memcpy(scals + (size_t)t * 4, scal, sizeof(scal));
+    }
+    free(h); free(blks); free(sm);
+    return anomaly;
 }

@@ -520,50 +520,38 @@ __device__ __forceinline__ int lb_env_add_block(const DevCfg &c, const StatePtrs
     return anomaly;
 }
 
-// Container.add_new_block for one environment, MACS 3D, executed by ONE thread.  Returns the anomaly bits.
-__device__ __forceinline__ int macs3d_env_add_block(const DevCfg &c, const StatePtrs &st, int b, int bx, int by, int bz) {
+// Container.add_new_block for one environment, MACS 3D, executed by the WHOLE warp (place_macs3d.cuh: level masks in shared
+// memory, warp-uniform walk, lane-parallel reductions; lane 0 commits).  Returns the anomaly bits (identical in every lane).
+__device__ __forceinline__ int macs3d_env_add_block_warp(const DevCfg &c, const StatePtrs &st, int b, int lane, M3Scratch *scratch,
+                                                         int bx, int by, int bz) {
     const int cells = c.W * c.L;
     M3State s;
     s.W = c.W; s.L = c.L; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
     s.vox = st.voxels + (size_t)b * cells * c.H;
     s.lists = reinterpret_cast<signed char *>(st.lists) + (size_t)b * c.nlists * c.lcap;
     s.h = st.heightmap + (size_t)b * cells;
-    const int4 sc = st.scal[b];
-    int anomaly = 0;
-    const int k = sc.w;
-    if (k >= c.cap) return 2;
-    int *positions = st.positions + (size_t)b * c.cap * 3, *blks = st.blocks + (size_t)b * c.cap * 3;
-    blks[k * 3] = bx; blks[k * 3 + 1] = by; blks[k * 3 + 2] = bz;
-    int4 out = make_int4(sc.x, sc.y, sc.z, k + 1);
-    unsigned char stable = 0;
-    if (bx >= 1 && by >= 1 && bz >= 1 && bx * by <= 32) {
-        const int vol = bx * by * bz;
-        const M3Best best = macs3d_place(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
-        if (best.any && !(anomaly & 1)) {
-            macs3d_commit(s, k, best, bx, by, bz, anomaly);
-            if (!(anomaly & 1)) {
-                positions[k * 3] = best.x; positions[k * 3 + 1] = best.y; positions[k * 3 + 2] = best.z;
-                stable = (unsigned char)best.stable;
-                out = make_int4(sc.x + vol, sc.y + best.add, sc.z + best.stable, k + 1);
-            }
-        }
-    }
-    st.stable[(size_t)b * c.cap + k] = stable;
-    st.scal[b] = out;
-    return anomaly;
+    s.sm = scratch; s.lane = lane; s.nl = 32;
+    return macs3d_env_add_block(c.flags, c.cap, s, reinterpret_cast<int *>(st.scal + b), st.positions + (size_t)b * c.cap * 3,
+                                st.blocks + (size_t)b * c.cap * 3, st.stable + (size_t)b * c.cap, bx, by, bz);
 }
 
-// Container.add_new_block inside a warp-per-environment kernel: lane 0 walks, the warp encodes (and, optionally, emits
-// calc_ratio of the state left behind).  STRAT: STRAT_LB (dim from the config) or STRAT_MACS3D.
+// Container.add_new_block inside a warp-per-environment kernel.  LB: lane 0 walks the grid; MACS 3D: the warp works together
+// on level masks in shared memory.  Then the warp encodes (and, optionally, emits calc_ratio of the state left behind).
+// STRAT: STRAT_LB (dim from the config) or STRAT_MACS3D.  Every kernel calling this runs at most kWarpsPerCta warps per CTA.
 template <int STRAT>
 __device__ __forceinline__ void voxel_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane, int bx, int by, int bz,
                                                 float *dec_dyn, int extra_flags, float *reward) {
-    if (lane == 0) {
-        int anomaly = extra_flags;
-        if (STRAT == STRAT_MACS3D) anomaly |= macs3d_env_add_block(c, st, b, bx, by, bz);
-        else if (c.dim == 2) anomaly |= lb_env_add_block<2>(c, st, b, bx, 1, bz);
-        else anomaly |= lb_env_add_block<3>(c, st, b, bx, by, bz);
-        if (anomaly) st.flags[b] |= anomaly;
+    if constexpr (STRAT == STRAT_MACS3D) {
+        __shared__ M3Scratch m3_scratch[kWarpsPerCta];
+        const int anomaly = extra_flags | macs3d_env_add_block_warp(c, st, b, lane, &m3_scratch[(threadIdx.x >> 5) % kWarpsPerCta], bx, by, bz);
+        if (anomaly && lane == 0) st.flags[b] |= anomaly;
+    } else {
+        if (lane == 0) {
+            int anomaly = extra_flags;
+            if (c.dim == 2) anomaly |= lb_env_add_block<2>(c, st, b, bx, 1, bz);
+            else anomaly |= lb_env_add_block<3>(c, st, b, bx, by, bz);
+            if (anomaly) st.flags[b] |= anomaly;
+        }
     }
     __syncwarp();                                    // lane 0's global writes are visible to the warp behind this barrier
     if (dec_dyn || reward) {
