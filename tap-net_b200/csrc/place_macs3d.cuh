@@ -125,13 +125,16 @@ TAPENV_HD unsigned m3_foot(const M3State &s, int x, int y, int bx, int by) {
     return m;
 }
 
-// emp / pos for every level, and the levels whose interval lists differ from the level below: lane = level
-TAPENV_HD void m3_build_masks(const M3State &s) {
+// emp / pos for the levels below zlim (nothing above the pile is ever examined), and the levels whose interval lists differ
+// from the level below (above the pile every list is pristine): lane = level
+TAPENV_HD void m3_build_masks(const M3State &s, int zlim) {
     M3Scratch &sm = *s.sm;
-    for (int z0 = 0; z0 < s.H; z0 += s.nl) {
+    for (int i = s.lane; i < kM3MaxH / 32; i += s.nl) sm.chg[i] = 0u;
+    m3_sync();
+    for (int z0 = 0; z0 < zlim; z0 += s.nl) {
         const int z = z0 + s.lane;
         bool changed = false;
-        if (z < s.H) {
+        if (z < zlim) {
             unsigned e = 0u, p = 0u;
             for (int x = 0; x < s.W; ++x)
                 for (int y = 0; y < s.L; ++y) {
@@ -148,7 +151,6 @@ TAPENV_HD void m3_build_masks(const M3State &s) {
         const unsigned w = __ballot_sync(0xffffffffu, changed);
         if (s.lane == 0) sm.chg[z0 >> 5] = w;
 #else
-        if ((z & 31) == 0) sm.chg[z >> 5] = 0u;
         if (changed) sm.chg[z >> 5] |= 1u << (z & 31);
 #endif
     }
@@ -348,10 +350,6 @@ TAPENV_HD M3Best macs3d_place(int flags, const M3State &s, int k, const int *pos
     const bool hard = (flags & TAPENV_RF_HARD) != 0;
     const bool mcs_start = (flags & TAPENV_RF_MCS_START) != 0, mcs_in = (flags & TAPENV_RF_MCS_IN) != 0;
     M3Best best; best.any = false; best.x = best.y = best.z = best.stable = best.add = 0;
-    m3_build_masks(s);
-    const int ne = m3_build_ems(s, k, positions, blocks, bx, by, bz, anomaly);
-    if (anomaly & 1) return best;
-    m3_sync();                                           // the EMS list is complete and visible to every lane
 #if defined(__CUDA_ARCH__)
     const int cx = s.lane / L, cy = s.lane - cx * L;     // this lane's heightmap cell
     const int hmax0 = m3_wmax(hc);
@@ -360,7 +358,17 @@ TAPENV_HD M3Best macs3d_place(int flags, const M3State &s, int k, const int *pos
     for (int i = 0; i < s.cells; ++i) hmax0 = hmax0 > s.h[i] ? hmax0 : s.h[i];
     (void)hc;
 #endif
+    // the masks are needed up to the highest level any scan can touch: the pile (or the phantom top of an unplaced block,
+    // which sits at the origin with its own height) plus the new block
+    int top = hmax0;
+    for (int i = 0; i < k; ++i) { const int t = positions[i * 3 + 2] + blocks[i * 3 + 2]; top = top > t ? top : t; }
+    m3_build_masks(s, top + bz + 1 < H ? top + bz + 1 : H);
+    const int ne = m3_build_ems(s, k, positions, blocks, bx, by, bz, anomaly);
+    if (anomaly & 1) return best;
+    m3_sync();                                           // the EMS list is complete and visible to every lane
     const int X = W - bx + 1, Y = L - by + 1;
+    const unsigned fpat = m3_foot(s, 0, 0, bx, by);     // footprint at the origin: at (x, y) it is fpat << (y*W + x)
+    const unsigned invW = (65536u + (unsigned)W - 1u) / (unsigned)W;   // c / W for c < 32 with one multiply
     int nlev = 0;
 
     double best_score = 0.0;     // np.max(ratio_ems): never-settled entries are 0.0
@@ -406,17 +414,30 @@ TAPENV_HD M3Best macs3d_place(int flags, const M3State &s, int k, const int *pos
                     else if (corner == 2) { _x = xr - 1 - ia; _y = yr - 1 - ib; }
                     else { _y = yr - 1 - ia; _x = X1 + ib; }
                     if (_x < 0 || _y < 0 || _x + bx > W || _y + by > L) { anomaly |= 1; continue; }
-                    const unsigned bit = 1u << (_y * W + _x);
+                    const int org = _y * W + _x;
+                    const unsigned bit = 1u << org;
                     if (vis & bit) continue;                                               // :2956
-                    const unsigned foot = m3_foot(s, _x, _y, bx, by);
+                    const unsigned foot = fpat << org;
                     if (Z > 0 && (below & foot) == foot) continue;                          // floating: skipped, NOT marked (:2957)
                     vis |= bit;
                     if ((freeZ & foot) != foot) continue;
                     bool stable = true;
                     if (Z > 0) {
-                        unsigned sup = 0u;
-                        for (int i = 0; i < bx; ++i) for (int j = 0; j < by; ++j) if ((sup_lvl >> ((_y + j) * W + _x + i)) & 1u) sup |= 1u << ((i * by + j) & 31);
-                        stable = stable3d_from_support(bx, by, sup);
+                        // is_stable (:710-765): the count rules need no geometry; otherwise the supporting cells in the
+                        // footprint's own x-major numbering
+                        const unsigned under = sup_lvl & foot;
+                        const int cnt = tap_popc(under);
+                        if (2 * cnt > bx * by) stable = true;
+                        else if (cnt <= 1) stable = false;
+                        else {
+                            unsigned sup = 0u;
+                            for (unsigned m = under; m; m &= m - 1u) {
+                                const int cbit = tap_ctz(m);
+                                const int yy = (int)(((unsigned)cbit * invW) >> 16), xx = cbit - yy * W;
+                                sup |= 1u << (((xx - _x) * by + (yy - _y)) & 31);
+                            }
+                            stable = stable3d_from_support(bx, by, sup);
+                        }
                     }
                     if (!stable && hard) continue;
                     settled = true; st = stable; px = _x; py = _y; pfoot = foot;

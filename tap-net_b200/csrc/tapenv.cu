@@ -505,7 +505,7 @@ __device__ __forceinline__ int lb_env_add_block(const DevCfg &c, const StatePtrs
     unsigned char stable = 0;
     if (bx >= 1 && by >= 1 && bz >= 1 && bx <= c.W && by <= s.L) {
         const int vol = bx * by * bz;
-        const LbBest best = lb_place<DIM>(c, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
+        const LbBest best = lb_place<DIM>(c.flags, s, k, positions, blks, bx, by, bz, sc.x + vol, sc.y, sc.z, anomaly);
         if (best.any) {
             lb_commit<DIM>(s, k, best, bx, by, bz, anomaly);
             if (!(anomaly & 1)) {
@@ -518,6 +518,22 @@ __device__ __forceinline__ int lb_env_add_block(const DevCfg &c, const StatePtrs
     st.stable[(size_t)b * c.cap + k] = stable;
     st.scal[b] = out;
     return anomaly;
+}
+
+// Container.add_new_block for one environment, LB strategy, executed by the WHOLE warp (place_lb.cuh, warp form; containers
+// up to kLbMaxH levels).  Returns the anomaly bits (identical in every lane).
+template <int DIM>
+__device__ __forceinline__ int lb_env_add_block_warp_dev(const DevCfg &c, const StatePtrs &st, int b, int lane, LbScratch *scratch,
+                                                         int bx, int by, int bz) {
+    const int cells = DIM == 2 ? c.W : c.W * c.L;
+    LbState s;
+    s.W = c.W; s.L = DIM == 3 ? c.L : 1; s.H = c.H; s.cells = cells; s.lcap = c.lcap;
+    s.vox = st.voxels + (size_t)b * cells * c.H;
+    s.lists = st.lists + (size_t)b * c.nlists * c.lcap;
+    s.h = st.heightmap + (size_t)b * cells;
+    LbWarp w; w.sm = scratch; w.lane = lane; w.nl = 32;
+    return lb_env_add_block_warp<DIM>(c.flags, c.cap, s, w, reinterpret_cast<int *>(st.scal + b), st.positions + (size_t)b * c.cap * DIM,
+                                      st.blocks + (size_t)b * c.cap * DIM, st.stable + (size_t)b * c.cap, bx, by, bz);
 }
 
 // Container.add_new_block for one environment, MACS 3D, executed by the WHOLE warp (place_macs3d.cuh: level masks in shared
@@ -546,7 +562,13 @@ __device__ __forceinline__ void voxel_add_block(const DevCfg &c, const StatePtrs
         const int anomaly = extra_flags | macs3d_env_add_block_warp(c, st, b, lane, &m3_scratch[(threadIdx.x >> 5) % kWarpsPerCta], bx, by, bz);
         if (anomaly && lane == 0) st.flags[b] |= anomaly;
     } else {
-        if (lane == 0) {
+        __shared__ LbScratch lb_scratch[kWarpsPerCta];
+        if (c.H <= kLbMaxH) {                            // the warp works on level masks
+            LbScratch *scr = &lb_scratch[(threadIdx.x >> 5) % kWarpsPerCta];
+            const int anomaly = extra_flags | (c.dim == 2 ? lb_env_add_block_warp_dev<2>(c, st, b, lane, scr, bx, 1, bz)
+                                                          : lb_env_add_block_warp_dev<3>(c, st, b, lane, scr, bx, by, bz));
+            if (anomaly && lane == 0) st.flags[b] |= anomaly;
+        } else if (lane == 0) {                          // tall containers: lane 0 walks the grid
             int anomaly = extra_flags;
             if (c.dim == 2) anomaly |= lb_env_add_block<2>(c, st, b, bx, 1, bz);
             else anomaly |= lb_env_add_block<3>(c, st, b, bx, by, bz);
