@@ -8,7 +8,7 @@
 
 Replaces exactly the hot-path symbols: pack.update_dynamic, pack.update_mask, pack.reward,
 tools.Container, tools.calc_positions_lb_greedy, tools.calc_positions_mcs (and generate.InitialContainer +
-generate.generate_blocks when `generate` is passed).  Everything else of the reference keeps running as it is.  The two whole-episode functions fall back to the saved
+generate.generate_blocks + generate.generate_blocks_with_GT when `generate` is passed).  Everything else of the reference keeps running as it is.  The two whole-episode functions fall back to the saved
 reference function for shapes beyond the compiled limits (e.g. the 7x7 initial container of the 3D generators has 49 cells,
 tapenv_limits.max_cells_3d is 32) -- the dataset generators call them with containers the network never sees."""
 import functools
@@ -55,8 +55,12 @@ def install(pack=None, tools=None, generate=None):
                   _with_fallback(episode.calc_positions_mcs, getattr(tools, "calc_positions_mcs", None)))]
     if generate is not None:
         generators._original = getattr(generate, "generate_blocks", None)
+        generators._original_gt = getattr(generate, "generate_blocks_with_GT", None)
+        generators._generate = generate
         repl += [(generate, "InitialContainer", rolling.InitialContainer),
                  (generate, "generate_blocks", generators.generate_blocks)]
+        if generators._original_gt is not None:
+            repl.append((generate, "generate_blocks_with_GT", generators.generate_blocks_with_GT))
     for mod, name, new in repl:
         _saved.append((mod, name, getattr(mod, name, None)))
         setattr(mod, name, new)
@@ -64,7 +68,7 @@ def install(pack=None, tools=None, generate=None):
 
 
 def uninstall():
-    generators._original = None
+    generators._original = generators._original_gt = generators._generate = None
     while _saved:
         mod, name, old = _saved.pop()
         if old is None:

@@ -134,3 +134,43 @@ def test_speculative_generate_blocks_host_logic(dim, W, monkeypatch):
         assert np.array_equal(got_next, want_next)           # the global stream is where the sequential loop leaves it
     if W > 0:                                                # (with a random width the first, non-speculative draw usually fits)
         assert calls["batches"] > 0 and calls["cands"] >= calls["batches"]
+
+
+@pytest.mark.parametrize("input_type", ["bot", "simple"])
+def test_speculative_ppsg_generator_host_logic(input_type, monkeypatch):
+    """tapenv.generators.generate_blocks_with_GT (the PPSG generator, generate.py:17-229: 20 unpacking orders of a perfect
+    packing, each re-packed with calc_positions_lb_greedy, :112): the HOST logic -- the 20 tries' draws made up front, the
+    interval-arithmetic calc_dependent on the perfect packing and on the accepted one, the unpacking check, np.random put back
+    to where the sequential loop stops -- with the batched GPU packing replaced by the reference's own function, try by try.
+    Same outputs and same stream position as generate.generate_blocks_with_GT under the same seed."""
+    import torch
+    from tapenv import generators
+    mods = refshim.load(("tools", "generate"))
+    tools, generate = mods["tools"], mods["generate"]
+    calls = {"batches": 0}
+
+    def fake_calc(blocks, container_size, reward_type):
+        blocks = np.asarray(blocks)
+        assert blocks.ndim == 3 and reward_type == "C+P+S-lb-hard"
+        calls["batches"] += 1
+        res = [tools.calc_positions_lb_greedy(b.copy(), container_size, reward_type) for b in blocks]
+        return (torch.from_numpy(np.stack([r[0] for r in res])), None, torch.tensor([[bool(v) for v in r[2]] for r in res]), None, None)
+
+    monkeypatch.setattr(generators, "calc_positions_lb_greedy", fake_calc)
+    monkeypatch.setattr(generators, "_generate", generate)
+    monkeypatch.setattr(generators, "_original_gt", generate.generate_blocks_with_GT)
+    n = 10
+    for seed in (1, 2, 3):
+        for gt_h in (8, 12):
+            np.random.seed(seed)
+            want = [generate.generate_blocks_with_GT(n, [7, gt_h], [7, 100], 1, [1, 5], input_type, i) for i in range(2)]
+            want_next = np.random.random_sample(4)
+            np.random.seed(seed)
+            got = [generators.generate_blocks_with_GT(n, [7, gt_h], [7, 100], 1, [1, 5], input_type, i) for i in range(2)]
+            got_next = np.random.random_sample(4)
+            for a, b in zip(got, want):
+                assert len(a) == len(b) == 5
+                for x, y in zip(a, b):
+                    assert np.array_equal(np.asarray(x), np.asarray(y))
+            assert np.array_equal(got_next, want_next)
+    assert calls["batches"] > 0

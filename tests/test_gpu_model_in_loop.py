@@ -195,3 +195,36 @@ def test_create_dataset_identical_with_batched_generator(dim, W, tmp_path, monke
     assert sorted(got) == sorted(want) and len(want) == 12
     for k in want:
         assert got[k] == want[k], k
+
+
+@pytest.mark.parametrize("n,gt_size,ics", [(10, [7, 8], [7, 100]), (14, [7, 12], [7, 100]), (8, [5, 5, 4], [7, 7, 100])])
+def test_ppsg_generator_identical_with_batched_tries(n, gt_size, ics):
+    """generate.generate_blocks_with_GT (the PPSG generator behind pack.create_dataset_gt / BASELINE C4, generate.py:17-229)
+    replaced by tapenv.generators.generate_blocks_with_GT: the 20 unpacking orders of every perfect packing are packed in ONE
+    GPU batch instead of 20 host calls of calc_positions_lb_greedy (:112).  Same samples and the same NumPy stream position as
+    the reference under the same seed; the 3D 7x7 initial container (49 cells) runs the saved reference function."""
+    import time
+    import tapenv
+    mods = ref_model.reference_modules()
+    pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
+    np.random.seed(2024)
+    t0 = time.perf_counter()
+    want = [generate.generate_blocks_with_GT(n, list(gt_size), list(ics), 1, [1, 5], "bot", i) for i in range(2)]
+    t_ref = time.perf_counter() - t0
+    want_next = np.random.random_sample(3)
+    tapenv.install(pack, tools, generate)
+    try:
+        assert generate.generate_blocks_with_GT is tapenv.generators.generate_blocks_with_GT
+        np.random.seed(2024)
+        t0 = time.perf_counter()
+        got = [generate.generate_blocks_with_GT(n, list(gt_size), list(ics), 1, [1, 5], "bot", i) for i in range(2)]
+        t_ours = time.perf_counter() - t0
+        got_next = np.random.random_sample(3)
+    finally:
+        tapenv.uninstall()
+    assert generate.generate_blocks_with_GT is not tapenv.generators.generate_blocks_with_GT
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert np.array_equal(got_next, want_next)
+    print("PPSG n=%d: reference %.2f s, tapenv %.2f s" % (n, t_ref, t_ours))
