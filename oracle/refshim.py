@@ -99,6 +99,12 @@ def _install_stubs():
     mpl.rcParams = {}
     mpl.rc = lambda *a, **k: None
     pyplot = mod("matplotlib.pyplot")
+
+    def _noop_attr(name):                                # trainer.train's plt.close / title / plot / savefig: no-ops
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return lambda *a, **k: None
+    pyplot.__getattr__ = _noop_attr
     patches = mod("matplotlib.patches")
     path = mod("matplotlib.path")
     path.Path = _Path

@@ -1,0 +1,39 @@
+"""GPU (B200): the UNMODIFIED reference trainer -- trainer.train_pack (trainer.py:317-504: dataset creation, PACKDataset,
+DRL + critic construction with pack.update_dynamic / pack.update_mask injected at :476-477) and trainer.train (:140-313:
+REINFORCE with the critic baseline, Adam, gradient clipping, checkpoints, validation) -- run end to end twice on a tiny RAND
+configuration under the same seeds: with the reference's own environment, and after tapenv.install(pack, tools, generate).
+Nothing of trainer.py / model.py / pack.py is edited; only plotting is off (tests/ref_trainer.py).  The environment consumes
+no random numbers and returns the same masks / heightmaps / rewards, so the two runs must log the same rewards and losses
+and save the same weights."""
+import numpy as np
+import pytest
+
+from tests import ref_model, ref_trainer
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim,strategy,reward_type", [(2, "LB_GREEDY", "C+P+S-lb-soft"), (3, "LB_GREEDY", "C+P+S-lb-hard"),
+                                                      (2, "MACS", "C+P+S-mcs-soft")])
+def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, tmp_path):
+    import torch
+    import tapenv
+    if not ref_model.available():
+        pytest.skip("reference tree not staged")
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    mods = ref_trainer.modules()
+    pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
+    kw = dict(obj_dim=dim, packing_strategy=strategy, reward_type=reward_type, train_size=64, valid_size=16, batch_size=32, epoch_num=2)
+    want = ref_trainer.run_train_pack(str(tmp_path / "reference"), **kw)
+    tapenv.install(pack, tools, generate)
+    try:
+        assert pack.update_dynamic is tapenv.update_dynamic and tools.Container is tapenv.Container
+        got = ref_trainer.run_train_pack(str(tmp_path / "tapenv"), **kw)
+    finally:
+        tapenv.uninstall()
+    assert got["files"] == want["files"] and "checkpoints/1/actor.pt" in got["files"]
+    assert np.array_equal(got["rewards"], want["rewards"]), (got["rewards"], want["rewards"])
+    np.testing.assert_allclose(got["losses"], want["losses"], rtol=1e-5, atol=1e-6)
+    for k in want["actor"]:
+        assert torch.allclose(got["actor"][k], want["actor"][k], rtol=1e-4, atol=1e-5), k
