@@ -398,6 +398,7 @@ class Container(object):
         self._batch = _batch
         self._row = _row
         self._group = None
+        self.initial_container_size = initial_container_size
         if _batch is not None:
             self._adopt(_batch)
             return
@@ -553,6 +554,39 @@ class Container(object):
         return v / (cells * h), v / (e + v), s / k
 
     # attributes the reference's callers read (rolling.py:640-658, model.py:1175)
+    @property
+    def bounding_box(self):
+        """tools.py:3633: zeros -- add_new_block never stores the bounding box the placement functions return (:3708)."""
+        return np.zeros(self.block_dim)
+
+    def draw_container(self, save_name, order=None):
+        """Container.draw_container (tools.py:3968-3996).  Visualisation stays the reference's: this container's blocks and
+        positions (2D) or its rebuilt voxel grid (3D) are handed to tools.draw_container_2d / tools.draw_container_voxel of
+        the module tapenv.install() patched.  (The rotate flags model.py passes to add_new_block are not kept: zeros.)"""
+        from . import dropin, episode
+        tools = dropin.installed_tools()
+        if tools is None:
+            raise RuntimeError("tapenv: draw_container needs the reference's drawing functions (tapenv.install(pack, tools))")
+        if self.initial_container_size is None:
+            print('Do not know the initial_conainer_size')
+            return
+        self._bind()
+        k = self.current_blocks_num
+        blocks = self._batch.blocks[self._row].cpu().numpy().astype(int)[:k]
+        positions = self.positions
+        if order is None:
+            order = [i for i in range(k)]
+        C, P, S = self.calc_CPS()
+        title = "Compactness: %.3f\nPyramidality: %.3f\nStability: %.3f\n" % (C, P, S)
+        rotate_state = np.zeros(self.blocks_num, dtype=bool)
+        if self.block_dim == 2:
+            tools.draw_container_2d(blocks, positions.astype('int'), self.container_size, self.reward_type, order, self.stable, None,
+                                    rotate_state, save_title=title, save_name=save_name)
+        else:
+            grid = episode.voxel_container(positions[:k], blocks, self.container_size)
+            tools.draw_container_voxel(grid, k, reward_type=self.reward_type, order=order, rotate_state=rotate_state,
+                                       feasibility=None, save_title=title, save_name=save_name)
+
     @property
     def heightmap(self):
         self._bind()

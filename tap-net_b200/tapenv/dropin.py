@@ -17,6 +17,11 @@ import sys
 from . import _capi, containers, episode, generators, ops, rolling
 
 _saved = []
+_tools = None          # the reference's `tools` module while installed (Container.draw_container hands its drawing to it)
+
+
+def installed_tools():
+    return _tools
 
 
 def _with_fallback(ours, original):
@@ -43,6 +48,8 @@ def install(pack=None, tools=None, generate=None):
     tools = tools if tools is not None else sys.modules.get("tools")
     if pack is None and tools is None:
         raise RuntimeError("tapenv.install: import the reference's `pack` / `tools` modules first (or pass them)")
+    global _tools
+    _tools = tools
     repl = []
     if pack is not None:
         repl += [(pack, "update_dynamic", ops.update_dynamic), (pack, "update_mask", ops.update_mask),
@@ -68,6 +75,8 @@ def install(pack=None, tools=None, generate=None):
 
 
 def uninstall():
+    global _tools
+    _tools = None
     generators._original = generators._original_gt = generators._generate = None
     while _saved:
         mod, name, old = _saved.pop()

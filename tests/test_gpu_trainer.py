@@ -37,3 +37,34 @@ def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, 
     np.testing.assert_allclose(got["losses"], want["losses"], rtol=1e-5, atol=1e-6)
     for k in want["actor"]:
         assert torch.allclose(got["actor"][k], want["actor"][k], rtol=1e-4, atol=1e-5), k
+
+
+@pytest.mark.parametrize("strategy,reward_type,total", [("LB_GREEDY", "C+P+S-lb-soft", 20), ("LB_GREEDY", "C+P+S-lb-hard", 30),
+                                                        ("MACS", "C+P+S-mcs-soft", 20)])
+def test_unmodified_rolling_driver_same_statistics_with_tapenv(strategy, reward_type, total, tmp_path):
+    """The UNMODIFIED rolling-inference driver (rolling.train_pack -> rolling.validate, rolling.py:575-760): a RollingDataset
+    of generate.InitialContainer objects, rolling.DRL decoding one block per window refill, ONE tools.Container taking all
+    `total` blocks -- run twice under the same seeds: reference environment vs tapenv.install(pack, tools, generate), which
+    swaps in the GPU-backed InitialContainer, Container, update_dynamic / update_mask and the batched dataset generator.  The
+    per-instance statistics files the driver writes (valid / box / empty size, stable count, packing height) must agree.
+    (2D only: rolling.py's own DRL constructor raises for obj_dim = 3 -- HeightmapEncoder receives a tuple, rolling.py:254/:104.)"""
+    import torch
+    import tapenv
+    from tests import ref_rolling
+    if not ref_model.available():
+        pytest.skip("reference tree not staged")
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    mods = ref_rolling.modules()
+    pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
+    kw = dict(packing_strategy=strategy, reward_type=reward_type, total_blocks_num=total, valid_size=4)
+    want = ref_rolling.run_rolling(str(tmp_path / "reference"), **kw)
+    tapenv.install(pack, tools, generate)
+    try:
+        assert generate.InitialContainer is tapenv.rolling.InitialContainer
+        got = ref_rolling.run_rolling(str(tmp_path / "tapenv"), **kw)
+    finally:
+        tapenv.uninstall()
+    for name in ref_rolling.STATS:
+        assert np.array_equal(got[name], want[name]), (name, got[name], want[name])
+    assert (want["batch-valid_size.txt"] > 0).all()
