@@ -13,9 +13,10 @@ from tests import ref_model, ref_trainer
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("dim,strategy,reward_type", [(2, "LB_GREEDY", "C+P+S-lb-soft"), (3, "LB_GREEDY", "C+P+S-lb-hard"),
-                                                      (2, "MACS", "C+P+S-mcs-soft")])
-def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, tmp_path):
+@pytest.mark.parametrize("dim,strategy,reward_type,input_type", [(2, "LB_GREEDY", "C+P+S-lb-soft", "bot"), (3, "LB_GREEDY", "C+P+S-lb-hard", "bot"),
+                                                                 (2, "MACS", "C+P+S-mcs-soft", "bot"), (2, "LB_GREEDY", "C+P+S-lb-soft", "mul-with"),
+                                                                 (2, "LB_GREEDY", "C+P+S-lb-soft", "simple")])
+def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, input_type, tmp_path):
     import torch
     import tapenv
     if not ref_model.available():
@@ -24,7 +25,10 @@ def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, 
     torch.backends.cudnn.benchmark = False
     mods = ref_trainer.modules()
     pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
-    kw = dict(obj_dim=dim, packing_strategy=strategy, reward_type=reward_type, train_size=64, valid_size=16, batch_size=32, epoch_num=2)
+    # ('mul-with': two container lists per batch, model.py:291-292 -- the per-object proxy serves them unbatched;
+    #  'simple': one precedence band, allow_rot off)
+    kw = dict(obj_dim=dim, packing_strategy=strategy, reward_type=reward_type, input_type=input_type, allow_rot=input_type != "simple",
+              train_size=64, valid_size=16, batch_size=32, epoch_num=2)
     want = ref_trainer.run_train_pack(str(tmp_path / "reference"), **kw)
     tapenv.install(pack, tools, generate)
     try:
