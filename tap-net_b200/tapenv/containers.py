@@ -555,6 +555,36 @@ class Container(object):
 
     # attributes the reference's callers read (rolling.py:640-658, model.py:1175)
     @property
+    def container(self):
+        """The reference's voxel grid (tools.py:3629: 0 empty / -1 empty under a block / k+1 block id), int [W(,L),H]: read
+        from the state for the strategies that keep it (LB, MACS 3D), rebuilt from the recorded placements otherwise."""
+        from . import episode
+        self._bind()
+        bt = self._batch
+        if bt.cfg.strategy == _capi.LB or (bt.cfg.strategy == _capi.MACS and self.block_dim == 3):
+            cells, H = bt._cells, int(self.container_size[-1])
+            v = bt._view(bt._layout.voxels, bt.batch_size * cells * H, torch.int16, (bt.batch_size, cells, H))[self._row]
+            return v.cpu().numpy().astype(np.int64).reshape([int(x) for x in self.container_size])
+        k = self.current_blocks_num
+        return episode.voxel_container(self.positions[:k], bt.blocks[self._row].cpu().numpy()[:k], self.container_size)
+
+    @property
+    def blocks(self):
+        """The blocks added so far (tools.py:3631: a list, one entry per add_new_block call)."""
+        self._bind()
+        k = self.current_blocks_num
+        return [b for b in self._batch.blocks[self._row].cpu().numpy()[:k].astype(np.int64)]
+
+    @property
+    def rotate_state(self):
+        """tools.py:3634 -- the flags model.py passes to add_new_block are only drawn, never used by the packing: not kept."""
+        return [False] * self.blocks_num
+
+    @property
+    def max_height(self):
+        return 2 * int(self.container_size[0])           # tools.py:3624-3627 (never read by the packing functions)
+
+    @property
     def bounding_box(self):
         """tools.py:3633: zeros -- add_new_block never stores the bounding box the placement functions return (:3708)."""
         return np.zeros(self.block_dim)

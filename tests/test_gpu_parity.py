@@ -866,3 +866,35 @@ def test_tensor_ops_every_input_type(input_type, allow_rot):
             with pytest.raises(tapenv.TapEnvError) as e:
                 env.step(ptr_t, st, dyn, mask_t)
             assert e.value.code == tapenv._capi.EUNSUPPORTED
+
+
+@pytest.mark.parametrize("size,strategy,rt", [([5, 50], "LB_GREEDY", "C+P+S-lb-hard"), ([5, 5, 50], "LB_GREEDY", "C+P+S-lb-soft"),
+                                              ([7, 60], "MACS", "C+P+S-mcs-hard"), ([5, 5, 50], "MACS", "C+P+S-mcs-soft"),
+                                              ([5, 50], "LB", "C+P+S-lb-soft"), ([5, 5, 50], "LB", "C+P+S-lb-hard")])
+def test_container_proxy_attributes_match_reference_container(size, strategy, rt):
+    """Every attribute of tools.Container a caller can read (tools.py:3628-3661; rolling.py:640-658, draw_container
+    :3968-3996): heightmap, positions, stable, valid / empty size, current_blocks_num, blocks, container (the voxel grid --
+    rebuilt from the placements where the kernels keep only the heightmap, read from the state for LB / MACS 3D),
+    bounding_box, calc_CPS, get_heightmap -- per-object proxies (each its own batch of one) against the oracle."""
+    import tapenv
+    from oracle import oracle
+    dim = len(size)
+    rng = np.random.RandomState(17)
+    n = 12
+    for ep in range(4):
+        hi = min(5, size[0]) + 1
+        blocks = np.stack([rng.randint(1, hi, size=n) for _ in range(dim - 1)] + [rng.randint(1, 6, size=n)], 1).astype(np.float32)
+        ours = tapenv.Container(size, n, rt, "diff", [7, 7, 50][:dim] if dim == 3 else [7, 50], packing_strategy=strategy)
+        ref = oracle.Container(size, n, rt, "diff", packing_strategy=strategy)
+        for t in range(n):
+            enc = ours.add_new_block(blocks[t], False)
+            want = ref.add_new_block(blocks[t], False)
+            assert np.array_equal(np.asarray(enc), np.asarray(want))
+            assert np.array_equal(ours.get_heightmap(), ref.get_heightmap())
+        assert np.array_equal(ours.heightmap, ref.heightmap) and np.array_equal(ours.positions, ref.positions)
+        assert ours.stable == ref.stable and ours.valid_size == ref.valid_size and ours.empty_size == ref.empty_size
+        assert ours.current_blocks_num == n and np.array_equal(np.array(ours.blocks), blocks.astype(int))
+        assert np.array_equal(ours.container, ref.container)
+        assert np.array_equal(ours.bounding_box, np.zeros(dim)) and ours.rotate_state == [False] * n
+        assert np.allclose(ours.calc_CPS(), ref.calc_CPS(), rtol=0, atol=1e-12)
+        assert abs(ours.calc_ratio() - ref.calc_ratio()) <= REWARD_TOL
