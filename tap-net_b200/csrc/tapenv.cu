@@ -31,7 +31,7 @@ namespace tapenv {
 
 enum { STRAT_LBG2D = 0, STRAT_LBG3D = 1, STRAT_MACS2D = 2, STRAT_LB = 3, STRAT_MACS3D = 4 };
 
-// strategies that keep a voxel grid + interval lists in the state and run one thread per environment
+// strategies that keep a voxel grid + interval lists in the state (the warp works on level masks of it, place_lb.cuh / place_macs3d.cuh)
 static bool voxel_state(const tapenv_config *c) { return c->strategy == TAPENV_LB || (c->strategy == TAPENV_MACS && c->dim == 3); }
 static int lcap_of(const tapenv_config *c) { const int a = c->capacity + 2, b = c->width + 4; return a > b ? a : b; }
 
@@ -290,7 +290,7 @@ template <int STRAT, bool SMALLN = false>             // SMALLN: blocks_num <= 3
 __device__ __forceinline__ void container_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane,
                                                     EnvRegs<STRAT> &e, int bx, int by, int bz, float *dec_dyn,
                                                     unsigned *ems_keys, int extra_flags, float *reward = nullptr) {
-    if (STRAT == STRAT_LB || STRAT == STRAT_MACS3D) {   // voxel-state strategies: lane 0 walks the grid
+    if (STRAT == STRAT_LB || STRAT == STRAT_MACS3D) {   // voxel-state strategies: the warp works on level masks of the grid
         voxel_add_block<STRAT>(c, st, b, lane, bx, by, bz, dec_dyn, extra_flags, reward);
         return;
     }
@@ -479,14 +479,15 @@ add_blocks_kernel(DevCfg c, StatePtrs st, const float *__restrict__ blocks, floa
 }
 
 // ------------------------------------------------------------------------------------
-// Voxel-state strategies (LB tools.py:1602-1914, MACS 3D :2751-3165): the placement is a sequential walk over a voxel grid
-// and incrementally edited lists kept in the state buffer.  One THREAD performs it for one environment: lane 0 of the
-// environment's warp (voxel_add_block) inside every kernel of the library -- add_blocks / step / episode / rolling / mul --
-// while the other lanes wait and then encode the heightmap.  One launch per decode step, and no divergence between
-// environments sharing a warp: r01's thread-per-environment kernels behind a separate tensor pass took 117 / 340 / 13 700 us
-// per step at B=4096 (LB 2D / LB 3D / MACS 3D), this form 42 / 99 / 2 940 us (profiles/r02m_voxel_ab.txt).
+// Voxel-state strategies (LB tools.py:1602-1914, MACS 3D :2751-3165): the placement walks a voxel grid and incrementally
+// edited lists kept in the state buffer.  It runs inside every kernel of the library (voxel_add_block: add_blocks / step /
+// episode / rolling / mul) -- one launch per decode step.  r01: thread-per-environment kernels behind a separate tensor pass
+// (117 / 340 / 13 700 us per step at B=4096 for LB 2D / LB 3D / MACS 3D); r02 first form: lane 0 of the environment's warp
+// walks while the warp waits (42 / 99 / 2 940 us, profiles/r02m_voxel_ab.txt); r02 second form: the WHOLE warp on level masks
+// in shared memory (place_macs3d.cuh, place_lb.cuh warp form: 31 / 84 / 370 us per fused step, profiles/r02af_bench_*.json).
 // ------------------------------------------------------------------------------------
-// Container.add_new_block for one environment, LB strategy, executed by ONE thread.  Returns the anomaly bits.
+// Container.add_new_block for one environment, LB strategy, the one-thread walk (containers above kLbMaxH levels).  Returns
+// the anomaly bits.
 template <int DIM>
 __device__ __forceinline__ int lb_env_add_block(const DevCfg &c, const StatePtrs &st, int b, int bx, int by, int bz) {
     const int cells = DIM == 2 ? c.W : c.W * c.L;
@@ -551,8 +552,8 @@ __device__ __forceinline__ int macs3d_env_add_block_warp(const DevCfg &c, const 
                                 st.blocks + (size_t)b * c.cap * 3, st.stable + (size_t)b * c.cap, bx, by, bz);
 }
 
-// Container.add_new_block inside a warp-per-environment kernel.  LB: lane 0 walks the grid; MACS 3D: the warp works together
-// on level masks in shared memory.  Then the warp encodes (and, optionally, emits calc_ratio of the state left behind).
+// Container.add_new_block inside a warp-per-environment kernel: the warp works together on level masks of the voxel grid in
+// shared memory (LB containers above kLbMaxH levels: lane 0 walks the grid).  Then the warp encodes (and, optionally, emits calc_ratio of the state left behind).
 // STRAT: STRAT_LB (dim from the config) or STRAT_MACS3D.  Every kernel calling this runs at most kWarpsPerCta warps per CTA.
 template <int STRAT>
 __device__ __forceinline__ void voxel_add_block(const DevCfg &c, const StatePtrs &st, int b, int lane, int bx, int by, int bz,
@@ -1441,7 +1442,7 @@ static int step_impl(const tapenv_config *cfg, void *state, const int64_t *ptr, 
         else { if (d.n == 20 && d.R == 2) TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 20, 2); else TAPENV_SPLIT_LAUNCH(STRAT_MACS2D, 0, 0); }
         return launch_status();
     }
-    if (strat == STRAT_LB) {                          // voxel-state strategies: tensor pass by the warp, grid walk by lane 0, ONE launch
+    if (strat == STRAT_LB) {                          // voxel-state strategies: tensor pass + placement on level masks by the warp, ONE launch
         if (fast) launch(step_kernel<STRAT_LB, true, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
         else launch(step_kernel<STRAT_LB, false, 0, 0, false>, grid, block, s, TAPENV_STEP_ARGS);
     } else if (strat == STRAT_MACS3D) {
