@@ -13,6 +13,21 @@ from tests import ref_model, ref_trainer
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def deterministic_torch():
+    """Both arms of a comparison must compute the same network numbers: deterministic cuDNN / scatter implementations for the
+    duration of a test (a harness setting -- nothing of the reference is touched)."""
+    import torch
+    prev = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.are_deterministic_algorithms_enabled(),
+            torch.is_deterministic_algorithms_warn_only_enabled())
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    yield
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = prev[0], prev[1]
+    torch.use_deterministic_algorithms(prev[2], warn_only=prev[3])
+
+
 @pytest.mark.parametrize("dim,strategy,reward_type,input_type", [(2, "LB_GREEDY", "C+P+S-lb-soft", "bot"), (3, "LB_GREEDY", "C+P+S-lb-hard", "bot"),
                                                                  (2, "MACS", "C+P+S-mcs-soft", "bot"), (2, "LB_GREEDY", "C+P+S-lb-soft", "mul-with"),
                                                                  (2, "LB_GREEDY", "C+P+S-lb-soft", "simple")])
@@ -21,8 +36,6 @@ def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, 
     import tapenv
     if not ref_model.available():
         pytest.skip("reference tree not staged")
-    torch.backends.cudnn.deterministic = True
-    torch.backends.cudnn.benchmark = False
     mods = ref_trainer.modules()
     pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
     # ('mul-with': two container lists per batch, model.py:291-292 -- the per-object proxy serves them unbatched;
@@ -57,8 +70,6 @@ def test_unmodified_rolling_driver_same_statistics_with_tapenv(strategy, reward_
     from tests import ref_rolling
     if not ref_model.available():
         pytest.skip("reference tree not staged")
-    torch.backends.cudnn.deterministic = True
-    torch.backends.cudnn.benchmark = False
     mods = ref_rolling.modules()
     pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
     kw = dict(packing_strategy=strategy, reward_type=reward_type, total_blocks_num=total, valid_size=4)
