@@ -726,6 +726,8 @@ typedef struct { int v[6]; } ems6;
 
 /* (container[xa:xb, y, z] == 0).all() with Python slice semantics on the x axis */
 static int m3_row_free(const int *c, int W, int L, int H, int xa, int xb, int y, int z) {
+    if (xa < 0) { xa += W; if (xa < 0) xa = 0; }           /* a negative bound counts from the wall (the edited interval lists */
+    if (xb < 0) { xb += W; if (xb < 0) xb = 0; }           /* can hold -1: update_level_free_space writes _x - 1, :3016-3020)  */
     if (xb > W) xb = W;
     for (int x = xa; x < xb; x++) if (C3(x, y, z) != 0) return 0;
     return 1;
