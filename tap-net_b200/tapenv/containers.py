@@ -344,8 +344,9 @@ class BatchedContainerPairs(object):
                                                   self.dec_static_rows, _p(dec_dyn), _stream()), "step_mul")
         return dyn_out, cur, mask_out, dec_static, self._shape(dec_dyn)
 
-    def add_new_blocks(self, blocks, target_ids):
-        """model.py:421-428 for the batch: blocks f32 [B,dim], target_ids [B] (0 -> A, 1 -> B) -> cat(A, B) heightmaps."""
+    def add_new_blocks(self, blocks, target_ids, raw=False):
+        """model.py:421-428 for the batch: blocks f32 [B,dim], target_ids [B] (0 -> A, 1 -> B) -> cat(A, B) heightmaps
+        (raw=True: f32 [B, 2, enc_len], A's and B's encoding side by side)."""
         blocks = _dev(blocks, "blocks", torch.float32)
         target_ids = _dev(target_ids, "target_ids", torch.float32).reshape(-1)
         if tuple(blocks.shape) != (self.batch_size, self.block_dim) or target_ids.numel() != self.batch_size:
@@ -355,7 +356,7 @@ class BatchedContainerPairs(object):
         with torch.cuda.device(self.device):
             _capi.check(_capi.lib.tapenv_add_blocks_mul(C.byref(self.cfg), _p(self.a.state), _p(self.b.state), _p(blocks),
                                                         _p(target_ids), _p(out), _stream()), "add_blocks_mul")
-        return self._shape(out)
+        return out if raw else self._shape(out)
 
     def calc_ratio(self):
         """(calc_ratio(A) + calc_ratio(B)) / 2 in fp32 (model.py:503-507) -> f32 [B]."""
@@ -378,6 +379,72 @@ class _Group(object):
         self.closed = False
 
 
+class _PairProxy(object):
+    """Two container lists driven by an UNMODIFIED model.py for input_type 'mul' / 'mul-with' (model.py:291-292, :414-428):
+    per decode step and environment b EITHER `containers_a[b].add_new_block(blocks[b]); containers_b[b].get_heightmap()` OR the
+    other way round -- which list receives the block is only revealed call by call.  The return values are merely collected
+    in lists and converted after the loop (`torch.FloatTensor(heightmaps_a)`, :430-447), so add_new_block hands out row VIEWS
+    of a host buffer that is filled when the step's last row has arrived: then ONE launch (tapenv_add_blocks_mul with the
+    targets inferred from which list was called) and ONE D2H copy serve the whole batch.  get_heightmap needs no launch: a
+    container that is only looked at keeps the encoding the previous step returned for it."""
+
+    def __init__(self, pairs):
+        self.pairs = pairs
+        self.B = pairs.batch_size
+        self.step = None          # the decode step being collected: src array, blocks, targets, next row, the two host buffers
+        self.last = None          # ((enc_a, enc_b) of the last finished step, (version_a, version_b) they describe)
+        a = pairs.a
+        if a.block_dim == 3:
+            W, L = a.container_size[0], a.container_size[1]
+            self.shape = (self.B, 2, W, L) if a.heightmap_type == "diff" else (self.B, W, L)
+        else:
+            self.shape = (self.B, a.enc_len)
+        # freshly cleared containers: every encoding of an empty heightmap is zeros
+        self.last = ((np.zeros(self.shape, np.int64), np.zeros(self.shape, np.int64)), (pairs.a._version, pairs.b._version))
+
+    def pending(self):
+        return self.step is not None
+
+    def add(self, c, block):
+        st = self.step
+        base = getattr(block, "base", None)
+        dim = self.pairs.block_dim
+        if st is None:
+            if c._row != 0 or base is None or base.ndim != 2 or base.shape[0] != self.B or base.shape[1] < dim:
+                raise RuntimeError("tapenv: with two container lists, add_new_block must be called for rows 0..B-1 in order with "
+                                   "rows of one [B,dim] array (model.py:412-428); use BatchedContainerPairs.add_new_blocks")
+            st = self.step = {"src": base, "blocks": np.ascontiguousarray(base[:, :dim], dtype=np.float32),
+                              "targets": np.zeros(self.B, np.float32), "next": 0,
+                              "enc": (np.zeros(self.shape, np.int64), np.zeros(self.shape, np.int64))}
+        b = c._row
+        if base is not st["src"] or b != st["next"]:
+            self.step = None
+            raise RuntimeError("tapenv: add_new_block rows must come, in order, from the batch handed to row 0")
+        st["targets"][b] = c._side
+        st["next"] = b + 1
+        out = st["enc"][c._side][b]
+        if b + 1 == self.B:
+            self._finish()
+        return out
+
+    def _finish(self):
+        st, pr = self.step, self.pairs
+        self.step = None
+        dev = pr.device
+        raw = pr.add_new_blocks(torch.from_numpy(st["blocks"]).to(dev), torch.from_numpy(st["targets"]).to(dev), raw=True)
+        host = raw.cpu().numpy().astype(np.int64)                        # ONE launch + ONE D2H per step
+        st["enc"][0][...] = host[:, 0].reshape(self.shape)               # fills the views handed out during the step
+        st["enc"][1][...] = host[:, 1].reshape(self.shape)
+        self.last = (st["enc"], (pr.a._version, pr.b._version))
+
+    def get(self, c):
+        pr = self.pairs
+        last = self.last
+        if last is not None and last[1] == (pr.a._version, pr.b._version):
+            return last[0][c._side][c._row]
+        return None
+
+
 _tls = threading.local()
 _ctor_cache = {}
 
@@ -398,6 +465,8 @@ class Container(object):
         self._batch = _batch
         self._row = _row
         self._group = None
+        self._pair = None          # set when this object is one of the 2B containers of a 'mul' / 'mul-with' model (_PairProxy)
+        self._side = 0
         self.initial_container_size = initial_container_size
         if _batch is not None:
             self._adopt(_batch)
@@ -446,6 +515,9 @@ class Container(object):
 
     def _bind(self, batch_hint=None):
         if self._batch is not None:
+            if self._pair is not None and self._pair.pending():
+                raise RuntimeError("tapenv: a decode step of the two container lists is still being collected "
+                                   "(add_new_block has not been called for every row yet)")
             return
         g = self._group
         g.closed = True
@@ -456,9 +528,19 @@ class Container(object):
                 for m in g.members:                      # rows 1..B-1 of this very step already take the O(1) path
                     m._batch = g.batch
                 return
+            if batch_hint is not None and 2 * batch_hint == len(g.members) and self._row in (0, batch_hint):
+                # two lists of B containers built back to back (model.py:291-292) and row 0's block: 'mul' / 'mul-with'
+                pairs = BatchedContainerPairs(size, n, rt, hm, packing_strategy=strat, batch_size=batch_hint, input_type="mul-with")
+                g.batch = pairs
+                proxy = _PairProxy(pairs)
+                for i, m in enumerate(g.members):
+                    m._side, m._row = divmod(i, batch_hint)
+                    m._batch = pairs.b if m._side else pairs.a
+                    m._pair = proxy
+                return
             else:
                 g.batch = "single"
-        if g.batch == "single":
+        if isinstance(g.batch, str):                     # "single"
             self._batch = BatchedContainers(size, n, rt, hm, packing_strategy=strat, batch_size=1)
             self._row = 0
         else:
@@ -474,6 +556,8 @@ class Container(object):
         return v
 
     def add_new_block(self, block, is_rotate=False):
+        if self._pair is not None:
+            return self._pair.add(self, block)
         bt = self._batch
         if bt is not None:
             # rows 1..B-1 of a decode step (model.py:452-453): the batch was launched by row 0; O(1) per call -- the row is
@@ -488,8 +572,13 @@ class Container(object):
         block = np.asarray(block, dtype=np.float32)
         base = block.base
         if self._batch is None:
-            hint = base.shape[0] if (base is not None and base.ndim == 2 and base.shape[1] == self.block_dim) else None
+            # ('mul-with' slices the block out of a [B, dim+1] array, model.py:409-410: the base keeps the id column)
+            hint = base.shape[0] if (base is not None and base.ndim == 2 and base.shape[1] in (self.block_dim, self.block_dim + 1)) else None
+            if hint is not None and base.shape[1] != self.block_dim and 2 * hint != len(self._group.members):
+                hint = None
             self._bind(hint)
+            if self._pair is not None:
+                return self._pair.add(self, block)
         bt, b = self._batch, self._row
         pending = bt.__dict__.get("_pending")
         if pending is not None and pending["next"] == b and b > 0:   # same protocol, rows that are copies: compare the values
@@ -512,6 +601,19 @@ class Container(object):
         return enc[b]
 
     def get_heightmap(self, is_full=None):
+        if is_full is None:
+            if self._batch is None:
+                # a freshly constructed container that nobody has touched: every encoding of an empty heightmap is zeros.  Not
+                # binding here matters: with two container lists the first call of a decode step may be containers_a[0]'s
+                # get_heightmap() (model.py:425-426), and the batch is only revealed by the add_new_block that follows.
+                W = [int(v) for v in self.container_size[:-1]]
+                if self.heightmap_type == "diff":
+                    return np.zeros(W[0] - 1 if self.block_dim == 2 else [2] + W, dtype=np.int64)
+                return np.zeros(W, dtype=np.int64)
+            if self._pair is not None:
+                enc = self._pair.get(self)
+                if enc is not None:
+                    return enc
         h = self.heightmap
         if is_full is not None or self.heightmap_type == "full":
             return h

@@ -898,3 +898,52 @@ def test_container_proxy_attributes_match_reference_container(size, strategy, rt
         assert np.array_equal(ours.bounding_box, np.zeros(dim)) and ours.rotate_state == [False] * n
         assert np.allclose(ours.calc_CPS(), ref.calc_CPS(), rtol=0, atol=1e-12)
         assert abs(ours.calc_ratio() - ref.calc_ratio()) <= REWARD_TOL
+
+
+@pytest.mark.parametrize("size,hm,strategy,rt,with_id", [([5, 50], "diff", "LB_GREEDY", "C+P+S-lb-soft", True), ([5, 50], "full", "LB_GREEDY", "C+P+S-lb-hard", False),
+                                                         ([5, 5, 50], "diff", "LB_GREEDY", "C+P+S-lb-soft", True), ([5, 5, 50], "zero", "LB_GREEDY", "C+P+S-lb-soft", False),
+                                                         ([7, 60], "diff", "MACS", "C+P+S-mcs-soft", True), ([5, 5, 50], "diff", "MACS", "C+P+S-mcs-hard", False)])
+def test_two_container_lists_as_unmodified_model_py_drives_them(size, hm, strategy, rt, with_id):
+    """model.py:291-292 builds TWO lists of B containers for input_type 'mul' / 'mul-with'; per decode step and environment
+    the block goes to one list's container while the other one is only asked for its heightmap (model.py:414-428, verbatim
+    below).  The per-object proxies recognise the pattern (2B objects, rows of one [B,dim(+1)] array) and serve a step with ONE
+    launch: returned heightmaps (after the loop, as model.py consumes them), final states and calc_ratio against two oracle
+    containers per environment."""
+    import tapenv
+    from oracle import oracle
+    from tapenv import containers as tc
+    dim = len(size)
+    B, n = 24, 8
+    rng = np.random.RandomState(5 + dim)
+    containers_a = [tapenv.Container(size, n, rt, hm, packing_strategy=strategy) for _ in range(B)]
+    containers_b = [tapenv.Container(size, n, rt, hm, packing_strategy=strategy) for _ in range(B)]
+    ref_a = [oracle.Container(size, n, rt, hm, packing_strategy=strategy) for _ in range(B)]
+    ref_b = [oracle.Container(size, n, rt, hm, packing_strategy=strategy) for _ in range(B)]
+    for t in range(n):
+        hi = min(4, size[0]) + 1
+        full = np.concatenate([rng.randint(1, hi, size=(B, dim)), rng.randint(0, 2, size=(B, 1))], 1).astype(np.float32)
+        target_ids = full[:, -1].copy()
+        blocks = full[:, :dim] if with_id else np.ascontiguousarray(full[:, :dim])      # 'mul-with' slices, 'mul' owns its array
+        is_rotate = np.zeros(B, bool)
+        heightmaps_a, heightmaps_b, want_a, want_b = [], [], [], []
+        for batch_index in range(B):                                                   # model.py:418-428
+            target_id = target_ids[batch_index]
+            if target_id == 0:
+                heightmaps_a.append(containers_a[batch_index].add_new_block(blocks[batch_index], is_rotate[batch_index]))
+                heightmaps_b.append(containers_b[batch_index].get_heightmap())
+                want_a.append(ref_a[batch_index].add_new_block(blocks[batch_index])); want_b.append(ref_b[batch_index].get_heightmap())
+            elif target_id == 1:
+                heightmaps_a.append(containers_a[batch_index].get_heightmap())
+                heightmaps_b.append(containers_b[batch_index].add_new_block(blocks[batch_index], is_rotate[batch_index]))
+                want_a.append(ref_a[batch_index].get_heightmap()); want_b.append(ref_b[batch_index].add_new_block(blocks[batch_index]))
+        assert np.array_equal(np.array(heightmaps_a), np.array(want_a)) and np.array_equal(np.array(heightmaps_b), np.array(want_b))
+    assert containers_a[0]._pair is not None and containers_a[0]._pair is containers_b[B - 1]._pair      # ONE batched pair, not 2B singles
+    assert isinstance(containers_a[0]._group.batch, tc.BatchedContainerPairs)
+    for b in range(B):                                                                 # model.py:503-507
+        assert abs(containers_a[b].calc_ratio() - ref_a[b].calc_ratio()) <= REWARD_TOL
+        assert abs(containers_b[b].calc_ratio() - ref_b[b].calc_ratio()) <= REWARD_TOL
+    assert np.array_equal(containers_b[3].positions, ref_b[3].positions) and containers_a[5].stable == ref_a[5].stable
+    # out-of-protocol use is refused loudly instead of returning heightmaps that would never be filled in
+    containers_a[0].add_new_block(blocks[0])
+    with pytest.raises(RuntimeError):
+        containers_a[2].add_new_block(blocks[2])

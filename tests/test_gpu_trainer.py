@@ -29,7 +29,7 @@ def deterministic_torch():
 
 
 @pytest.mark.parametrize("dim,strategy,reward_type,input_type", [(2, "LB_GREEDY", "C+P+S-lb-soft", "bot"), (3, "LB_GREEDY", "C+P+S-lb-hard", "bot"),
-                                                                 (2, "MACS", "C+P+S-mcs-soft", "bot"), (2, "LB_GREEDY", "C+P+S-lb-soft", "mul-with"),
+                                                                 (2, "MACS", "C+P+S-mcs-soft", "bot"), (2, "LB_GREEDY", "C+P+S-lb-soft", "mul-with"), (3, "LB_GREEDY", "C+P+S-lb-soft", "mul"),
                                                                  (2, "LB_GREEDY", "C+P+S-lb-soft", "simple")])
 def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, input_type, tmp_path):
     import torch
@@ -38,7 +38,7 @@ def test_unmodified_train_pack_same_run_with_tapenv(dim, strategy, reward_type, 
         pytest.skip("reference tree not staged")
     mods = ref_trainer.modules()
     pack, tools, generate = mods["pack"], mods["tools"], mods["generate"]
-    # ('mul-with': two container lists per batch, model.py:291-292 -- the per-object proxy serves them unbatched;
+    # ('mul' / 'mul-with': two container lists per batch, model.py:291-292 -- the per-object proxies serve each step with one launch;
     #  'simple': one precedence band, allow_rot off)
     kw = dict(obj_dim=dim, packing_strategy=strategy, reward_type=reward_type, input_type=input_type, allow_rot=input_type != "simple",
               train_size=64, valid_size=16, batch_size=32, epoch_num=2)
