@@ -415,7 +415,8 @@ class _PairProxy(object):
                                    "rows of one [B,dim] array (model.py:412-428); use BatchedContainerPairs.add_new_blocks")
             st = self.step = {"src": base, "blocks": np.ascontiguousarray(base[:, :dim], dtype=np.float32),
                               "targets": np.zeros(self.B, np.float32), "next": 0,
-                              "enc": (np.zeros(self.shape, np.int64), np.zeros(self.shape, np.int64))}
+                              # (until the step is complete the rows hold a glaring sentinel, not plausible zeros)
+                              "enc": (np.full(self.shape, -2 ** 62, np.int64), np.full(self.shape, -2 ** 62, np.int64))}
         b = c._row
         if base is not st["src"] or b != st["next"]:
             self.step = None
