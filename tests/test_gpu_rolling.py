@@ -101,6 +101,9 @@ def _record_policy(run, T, seed):
     ("rolling2d_t50.npz", 512, [7, 250], "C+P+S-mcs-soft", "MACS"),
     ("rolling3d_t50.npz", 256, [5, 5, 250], "C+P+S-mcs-soft", "MACS"),     # voxel-state strategies: unfused rolling step
     ("rolling2d_t50.npz", 256, [5, 250], "C+P+S-lb-soft", "LB"),
+    ("rolling3d_t50.npz", 128, [5, 5, 250], "C+P+S-lb-hard", "LB"),        # LB 3D, 250 levels: the warp form on level masks
+    ("rolling3d_t50.npz", 64, [5, 5, 400], "C+P+S-lb-soft", "LB"),         # above 256 levels: the one-thread walk
+    ("rolling3d_t50.npz", 128, [5, 5, 250], "C+P+S-mcs-hard", "MACS"),
 ])
 def test_rolling_batch_vs_oracle(src, B, size, rt, strat):
     """Large tiled batches under an on-device random-valid policy, against the threaded CPU oracle driver."""
