@@ -947,3 +947,34 @@ def test_two_container_lists_as_unmodified_model_py_drives_them(size, hm, strate
     containers_a[0].add_new_block(blocks[0])
     with pytest.raises(RuntimeError):
         containers_a[2].add_new_block(blocks[2])
+
+
+@pytest.mark.parametrize("WL", [(8, 4), (4, 8), (16, 2), (2, 16), (32, 1), (1, 32)])
+@pytest.mark.parametrize("strat,rt", [("LB_GREEDY", "C+P+S-lb-hard"), ("LB", "C+P+S-lb-soft"), ("MACS", "C+P+S-mcs-soft")])
+def test_full_32_cell_3d_containers(WL, strat, rt):
+    """The compiled limit of the 3D kernels: W*L = 32 heightmap cells = one lane / one mask bit per cell, bit 31 included
+    (8x4, 4x8, 16x2, 2x16 and the degenerate 32x1 / 1x32), every step against the oracle -- fused and unfused."""
+    W, L = WL
+    rng = np.random.RandomState(W * 100 + L)
+    size = [W, L, 120]
+    n, B = 6, 12
+    static, dynamic = _synthetic_inputs(rng, B, n, 3, max_edge=min(4, W, L), density=0.05)
+    r = oracle_rollout(static, dynamic, size, rt, "diff", strat, seed=3)
+    for fused in (True, False):
+        g = gpu_rollout(static, dynamic, r["ptr"], size, rt, "diff", strat, fused=fused)
+        assert (g["flags"] == 0).all()
+        assert_same(g, r, r["ptr"], static, 3)
+
+
+@pytest.mark.parametrize("strat,rt", [("LB_GREEDY", "C+P+S-lb-soft"), ("LB", "C+P+S-lb-hard"), ("MACS", "C+P+S-mcs-hard")])
+def test_full_32_column_2d_containers(strat, rt):
+    """The compiled limit in 2D: W = 32 columns = every lane / every bit of a level mask in use."""
+    rng = np.random.RandomState(32)
+    size = [32, 120]
+    n, B = 12, 16
+    static, dynamic = _synthetic_inputs(rng, B, n, 2, max_edge=6, density=0.05)
+    r = oracle_rollout(static, dynamic, size, rt, "zero", strat, seed=4)
+    for fused in (True, False):
+        g = gpu_rollout(static, dynamic, r["ptr"], size, rt, "zero", strat, fused=fused)
+        assert (g["flags"] == 0).all()
+        assert_same(g, r, r["ptr"], static, 2)
