@@ -978,3 +978,18 @@ def test_full_32_column_2d_containers(strat, rt):
         g = gpu_rollout(static, dynamic, r["ptr"], size, rt, "zero", strat, fused=fused)
         assert (g["flags"] == 0).all()
         assert_same(g, r, r["ptr"], static, 2)
+
+
+@pytest.mark.parametrize("strat,rt", [("LB_GREEDY", "C+P+S-lb-hard"), ("LB", "C+P+S-lb-soft"), ("MACS", "C+P+S-mcs-soft")])
+def test_full_64_candidate_masks(strat, rt):
+    """The compiled limit of the tensor pass: S = n * R = 64 candidates (n = 32 blocks, 2 rotations) = every bit of the 64-bit
+    accessibility words in use; every step (masks, dynamic, placements) against the oracle."""
+    rng = np.random.RandomState(64)
+    size = [9, 250]
+    n, B = 32, 10
+    static, dynamic = _synthetic_inputs(rng, B, n, 2, max_edge=4, density=0.02)
+    r = oracle_rollout(static, dynamic, size, rt, "diff", strat, seed=6)
+    for fused in (True, False):
+        g = gpu_rollout(static, dynamic, r["ptr"], size, rt, "diff", strat, fused=fused)
+        assert (g["flags"] == 0).all()
+        assert_same(g, r, r["ptr"], static, 2)
